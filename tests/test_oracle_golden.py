@@ -1,0 +1,100 @@
+"""Pin the CPU oracle (oracle/vca_oracle.py) to vectors produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import json, os
+import numpy as np
+import torch
+from conftest import make_state, golden_inputs, rel_l2, GOLD
+from oracle import vca_oracle as O
+
+TOL = 2e-5  # same math, different op order (functional vs nn.Module) on CPU fp32
+
+
+def test_known_answers(golden):
+    assert abs(float(O.gan_loss(torch.zeros(4, 1), True)) - np.log(2)) < 1e-6
+    assert abs(float(golden["known_gan_loss0"]) - np.log(2)) < 1e-6
+    assert [O.final_length(t) for t in (40, 50, 75, 160, 250)] == [10, 12, 18, 40, 62]
+    assert list(golden["known_final_length"]) == [10, 12, 18, 40, 62]
+
+
+def test_eval_forward_matches_reference(golden, state_spec):
+    vid, mel, spec, noise = golden_inputs()
+    sds = {m: make_state(state_spec, m) for m in O.MODULES}
+    with torch.no_grad():
+        phon, sent = O.visual_front(sds["v_front"], vid, False)
+        assert rel_l2(phon, golden["eval_phon"]) < TOL
+        assert rel_l2(sent, golden["eval_sent"]) < TOL
+        g1, g2, g3 = O.decoder(sds["gen"], sent, phon, [20, 13], noise, False)
+        for a, k in ((g1, "eval_g1"), (g2, "eval_g2"), (g3, "eval_g3")):
+            assert rel_l2(a, golden[k]) < TOL, k
+        gs = O.postnet(sds["post"], g3, False)
+        assert rel_l2(gs, golden["eval_gs"]) < TOL
+        mel1, mel2 = O.bilinear_half(mel, 0.25), O.bilinear_half(mel, 0.5)
+        for i, x in ((1, mel1), (2, mel2), (3, mel)):
+            u, c = O.discriminator(sds[f"dis{i}"], x, sent, 20)
+            assert rel_l2(u, golden[f"eval_d{i}_u"]) < TOL
+            assert rel_l2(c, golden[f"eval_d{i}_c"]) < TOL
+        assert rel_l2(O.sync_discriminator(sds["s_dis"], phon, mel, False, False), golden["eval_sync_nce"]) < TOL
+        assert rel_l2(O.sync_discriminator(sds["s_dis"], phon, g3, True, False), golden["eval_sync_cos"]) < TOL
+
+
+def test_masked_keys_do_not_matter(state_spec):
+    """keys at positions >= len must not influence the attention output."""
+    sd = make_state(state_spec, "gen")
+    g = torch.Generator().manual_seed(5)
+    ph = torch.randn(2, 20, 512, generator=g); feat = torch.randn(2, 128, 20, 20, generator=g)
+    a = O.av_attention(sd, "att1", ph, feat, [20, 13])
+    ph2 = ph.clone(); ph2[1, 13:] += 10.0
+    b = O.av_attention(sd, "att1", ph2, feat, [20, 13])
+    assert torch.allclose(a[1], b[1], atol=1e-6) and torch.allclose(a[0], b[0])
+
+
+def test_train_step_matches_reference(golden, state_spec):
+    vid, mel, spec, noise = golden_inputs()
+    sds = {m: make_state(state_spec, m, requires_grad=True) for m in O.MODULES}
+    par = lambda ms: [{"params": [p for p in sds[m].values() if p.requires_grad]} for m in ms]
+    g_opt = torch.optim.Adam(par(("v_front", "gen", "post")), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+    d_opt = torch.optim.Adam(par(("dis1", "dis2", "dis3", "s_dis")), lr=1e-4, weight_decay=1e-5, amsgrad=True)
+    out = O.train_step_with_adam(sds, dict(mel=mel, spec=spec, vid=vid, vid_len=[20, 13]), noise, g_opt, d_opt)
+    for k in ("dis_loss", "sync_loss", "real_loss", "fake_loss", "gen_loss", "g_sync", "recon"):
+        ref = float(golden["step_" + k]); got = float(out[k])
+        assert abs(got - ref) <= 2e-5 * max(1.0, abs(ref)), (k, got, ref)
+    assert rel_l2(out["grad_pen"], golden["step_grad_pen"]) < 1e-4
+    for k in ("g1", "g2", "g3", "gs"):
+        assert rel_l2(out[k], golden["step_" + k]) < TOL, k
+    assert rel_l2(out["r1_grads"][2], golden["step_r1_grad3"]) < 1e-4
+    assert rel_l2(out["r1_grads"][0], golden["step_r1_grad1"]) < 1e-4
+    names = json.load(open(os.path.join(GOLD, "grad_norm_names.json")))
+    dn = torch.tensor([out["d_grad_norms"][n.split(".", 1)[0]][n.split(".", 1)[1]] for n in names["d"]])
+    assert rel_l2(dn, golden["step_d_grad_norms"]) < 1e-4
+    gn = torch.tensor([out["g_grad_norms"][n.split(".", 1)[0]][n.split(".", 1)[1]] for n in names["g"]])
+    assert rel_l2(gn, golden["step_g_grad_norms"]) < 1e-4
+    vfd = torch.tensor([float(out["vf_grad_after_d"][n.split(".", 1)[1]].norm()) for n in names["vf_d"]])
+    assert rel_l2(vfd, golden["step_vf_d_grad_norms"]) < 1e-4
+    cn = json.load(open(os.path.join(GOLD, "checksum_names.json")))
+    chk = torch.tensor([[float(sds[n.split(".", 1)[0]][n.split(".", 1)[1]].double().sum()),
+                         float(sds[n.split(".", 1)[0]][n.split(".", 1)[1]].double().abs().sum())] for n in cn["params"]],
+                       dtype=torch.float64)
+    ref = torch.from_numpy(golden["step_param_checksums"])
+    assert float((chk[:, 1] - ref[:, 1]).abs().max() / ref[:, 1].abs().max()) < 1e-6
+    bs = torch.tensor([float(sds[n.split(".", 1)[0]][n.split(".", 1)[1]].double().sum()) for n in cn["buffers"]],
+                      dtype=torch.float64)
+    assert rel_l2(bs, golden["step_buffer_sums"]) < 1e-5
+
+
+def test_stft_griffin_lim_matches_reference(golden):
+    fwd, inv = O.stft_bases()
+    g = torch.Generator().manual_seed(77)
+    sig = torch.randn(2, 160 * 11, generator=g) * 0.1
+    mag, ph = O.stft_transform(sig, fwd)
+    assert rel_l2(mag, golden["stft_mag"]) < 1e-6
+    assert rel_l2(torch.cos(ph), np.cos(golden["stft_phase"])) < 1e-5
+    rec = O.stft_inverse(mag, ph, inv)
+    assert rel_l2(rec, golden["stft_rec"]) < 1e-6
+    assert float((rec.squeeze(1) - sig).abs().max()) < 1e-5  # SURVEY section 4 item 5 round trip
+    assert np.allclose(O.window_sumsquare(12), golden["window_sumsquare_12"], atol=1e-7)
+    wav = O.griffin_lim(torch.from_numpy(golden["gl_mag"]), torch.from_numpy(golden["gl_init_phase"]), 8)
+    assert rel_l2(wav, golden["gl_wav"]) < 1e-5
+    # torch.stft cross-check (hann periodic, center, reflect)
+    ts = torch.stft(sig, 640, 160, 640, torch.hann_window(640, periodic=True), center=True, pad_mode="reflect",
+                    return_complex=True)
+    assert rel_l2(mag, ts.abs()) < 1e-5
