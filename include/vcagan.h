@@ -1,0 +1,99 @@
+/* vcagan.h -- C ABI of libvcagan_b200.so (sm_100a).
+ *
+ * The reference (ms-dot-k/Visual-Context-Attentional-GAN) has no FFI layer: its hot path is the set of
+ * torch.nn modules imported at train.py:7-8 / test.py:7-8 (src/models/{visual_front,resnet,generator}.py) plus
+ * griffin_lim (src/data/audio_processing.py:51-68).  Each entry point below replaces the device work behind one
+ * family of torch calls in those files (cited per group); the Python facade in
+ * visual-context-attentional-gan_b200/src/models keeps the reference class names/signatures and calls these
+ * through ctypes.
+ *
+ * Conventions: plain pointers (device memory unless noted) and sizes; no hidden allocation; no host sync;
+ * every call enqueues on `stream`; returns 0 or a negative VCA_ERR_* code, message via vca_last_error().
+ * Activations are channels-last: [N, D, H, W, C] contiguous (D = 1 for 2-D, D = H = 1 for 1-D / linear).
+ * dtype codes: 0 = fp32, 1 = bf16 (fp32 accumulate everywhere).
+ */
+#ifndef VCAGAN_H_
+#define VCAGAN_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef __CUDA_RUNTIME_H__
+typedef struct CUstream_st* cudaStream_t;
+#endif
+
+typedef struct ConvGeom {
+  int N, ID, IH, IW, Cin;
+  int OD, OH, OW, Cout;
+  int KD, KH, KW;
+  int sd, sh, sw;
+  int pd, ph, pw;
+} ConvGeom;
+
+/* ---- library -------------------------------------------------------------------------------------------- */
+const char* vca_last_error();
+int vca_abi_version();
+int vca_device_ok();
+
+/* ---- convolutions (nn.Conv1d/2d/3d: visual_front.py:11, resnet.py:5-14, generator.py:19-25,62-66,103-108,
+ *      177-185,204-225,272-300,323-327) and their autograd (aten::convolution_backward) ------------------- */
+int vca_pack_conv_weight(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t stream);
+int vca_conv_fwd_simt(int dtype, const ConvGeom* g, const void* x, const void* wf, const float* bias, void* y, cudaStream_t stream);
+int vca_conv_dgrad_simt(int dtype, const ConvGeom* g, const void* dy, const void* wd, void* dx, cudaStream_t stream);
+int vca_conv_wgrad_simt(int dtype, const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);
+/* tcgen05/TMEM/TMA implicit GEMM, bf16 in / fp32 accumulate / bf16 out, stride 1 (conv_tc.cu) */
+int vca_conv_tc_supported(const ConvGeom* g, int kind);
+int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t stream);
+int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t stream);
+int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);
+
+
+/* ---- GEMM (nn.Linear: visual_front.py:21, generator.py:147-152,293,303,336; torch.bmm: generator.py:161,167,354;
+ *      nn.GRU projections: visual_front.py:20) ---------------------------------------------------------------- */
+int vca_gemm_simt(int dtA, int dtB, int dtC, const void* A, const void* B, void* C, const float* bias, int Z, int M, int N, int K, long long sAz, long long sAm, long long sAk, long long sBz, long long sBk, long long sBn, long long sCz, long long sCm, long long sCn, float alpha, float beta, cudaStream_t stream);
+
+/* ---- BatchNorm (+residual) (+PReLU/LeakyReLU/ReLU), activations (visual_front.py:12-13, resnet.py:34-63,
+ *      generator.py:9,52,95,105-126,179,209-225,325-329) --------------------------------------------------- */
+int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
+int vca_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t stream);
+int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, cudaStream_t stream);
+int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, cudaStream_t stream);
+int vca_lrelu_fwd(int dtype, const void* x, void* y, long long n, float slope, cudaStream_t stream);
+int vca_lrelu_bwd(int dtype, const void* dy, const void* x, void* dx, long long n, float slope, cudaStream_t stream);
+int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t stream);
+int vca_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, long long n, cudaStream_t stream);
+int vca_axpby(int dtype, const void* a, const void* b, void* out, long long n, float alpha, float beta, cudaStream_t stream);
+int vca_colsum(int dtype, const void* x, long long R, int C, float* out, cudaStream_t stream);
+int vca_cast(int dt_in, int dt_out, const void* x, void* y, long long n, cudaStream_t stream);
+int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t stream);
+
+/* ---- pooling / resampling (visual_front.py:14, resnet.py:82, generator.py:74,83,112,121,140) -------------- */
+int vca_maxpool3x3s2_fwd(int dtype, const void* x, void* y, unsigned char* idx, int NF, int H, int W, int C, cudaStream_t stream);
+int vca_maxpool3x3s2_bwd(int dtype, const void* dy, const unsigned char* idx, void* dx, int NF, int H, int W, int C, cudaStream_t stream);
+int vca_pool2x2_sum(int dtype, const void* x, void* y, int NF, int H, int W, int C, float scale, cudaStream_t stream);
+int vca_expand2x2(int dtype, const void* x, void* y, int NF, int IH, int IW, int C, int H, int W, float scale, cudaStream_t stream);
+int vca_spatial_sum(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t stream);
+int vca_spatial_bcast(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t stream);
+
+/* ---- GRU gates (visual_front.py:20,33-34), attention softmax (generator.py:161-164), sync losses
+ *      (generator.py:347-359), gan_loss (generator.py:363-366), L1 (train.py:226-229), Adam (train.py:82-83) - */
+int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const float* hprev, float* hnext, float* out, float* gates, int ndir, int T, int B, int H, int step, cudaStream_t stream);
+int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh, int ndir, int T, int B, int H, int step, cudaStream_t stream);
+int vca_masked_softmax_fwd(const float* x, float* p, const int* lens, int Z, int R, int S, cudaStream_t stream);
+int vca_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int S, cudaStream_t stream);
+int vca_l2norm_fwd(const float* x, float* y, float* norms, int rows, int D, float eps, cudaStream_t stream);
+int vca_l2norm_bwd(const float* dy, const float* y, const float* norms, float* dx, int rows, int D, float eps, cudaStream_t stream);
+int vca_nce_diag(const float* sim, float* loss, float* dsim, int Bn, int S, cudaStream_t stream);
+int vca_cos_abs_mean_fwd(const float* v, const float* a, float* loss, float* saved, int Bn, int S, int D, cudaStream_t stream);
+int vca_cos_abs_mean_bwd(const float* dloss, const float* v, const float* a, const float* saved, float* da, float* dv, int Bn, int S, int D, cudaStream_t stream);
+int vca_softplus_mean(const float* x, float* out, float* dx, int n, float sign, cudaStream_t stream);
+int vca_reduce_l1_sq(int dtype, const void* a, const void* b, long long n, float scale, int mode, float* out, cudaStream_t stream);
+int vca_l1_bwd(int dtype, const void* a, const void* b, const float* g, long long n, float scale, void* da, cudaStream_t stream);
+int vca_adam_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float gscale, cudaStream_t stream);
+int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned long long offset, int mode, float param, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCAGAN_H_ */

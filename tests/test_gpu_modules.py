@@ -1,0 +1,191 @@
+"""Module-level parity: each B200-native module (reference class name / state_dict keys, CUDA kernels through the
+C ABI) against the CPU oracle on identical weights and inputs, forward and parameter gradients, plus the committed
+golden vectors produced by the unmodified reference.  fp32 mode: <= 1e-4 relative (north-star tolerance; 3e-4 on
+gradients that pass through train-mode BatchNorm statistics of a B=2 batch, which amplify rounding).
+bf16 mode: stated bound 3e-2 relative L2 on mels / features."""
+import pytest
+import torch
+
+from conftest import make_state, golden_inputs, rel_l2
+from oracle import vca_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+GTOL = 3e-4
+BF16_TOL = 3e-2
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vcagan_b200
+    return vcagan_b200
+
+
+def build(V, spec, name, train):
+    M = V.models
+    ctor = dict(v_front=M.Visual_front, gen=M.Decoder, post=M.Postnet, dis1=lambda: M.Discriminator(phase='1'),
+                dis2=lambda: M.Discriminator(phase='2'), dis3=lambda: M.Discriminator(phase='3'), s_dis=M.sync_Discriminator)[name]
+    m = ctor()
+    m.load_state_dict(make_state(spec, name))
+    m = m.cuda()
+    m.train(train)
+    if name == "v_front":
+        m.dropout.p = 0.0
+        m.sentence_encoder.dropout = 0.0
+    return m
+
+
+def grads_close(mod, sd, tol, skip=()):
+    bad = []
+    for n, p in mod.named_parameters():
+        ref = sd[n].grad
+        if ref is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
+            continue
+        assert p.grad is not None, n
+        e = rel_l2(p.grad.cpu(), ref)
+        if e > tol and float(ref.norm()) > 1e-7 and n not in skip:
+            bad.append((n, e))
+    assert not bad, bad[:10]
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_visual_front(V, state_spec, golden, train):
+    V.set_precision("fp32")
+    vid, mel, spec, noise = golden_inputs()
+    sd = make_state(state_spec, "v_front", requires_grad=True)
+    phon_r, sent_r = O.visual_front(sd, vid, train)
+    m = build(V, state_spec, "v_front", train)
+    phon, sent = m(vid.cuda())
+    assert phon.shape == (2, 20, 512) and sent.shape == (2, 512, 20)
+    assert rel_l2(phon.detach().cpu(), phon_r) < TOL
+    assert rel_l2(sent.detach().cpu(), sent_r) < TOL
+    if not train:
+        assert rel_l2(phon.detach().cpu(), golden["eval_phon"]) < TOL
+        assert rel_l2(sent.detach().cpu(), golden["eval_sent"]) < TOL
+        return
+    g = torch.Generator().manual_seed(2)
+    dp, ds = torch.randn(phon_r.shape, generator=g), torch.randn(sent_r.shape, generator=g)
+    ((phon_r * dp).sum() + (sent_r * ds).sum()).backward()
+    ((phon * dp.cuda()).sum() + (sent * ds.cuda()).sum()).backward()
+    grads_close(m, sd, GTOL)
+    for n, b in m.named_buffers():
+        if b.is_floating_point():
+            assert rel_l2(b.cpu(), sd[n]) < 1e-4, n
+
+
+@pytest.mark.parametrize("train", [False, True])
+def test_decoder_postnet(V, state_spec, golden, train):
+    V.set_precision("fp32")
+    vid, mel, spec, noise = golden_inputs()
+    sent = torch.from_numpy(golden["eval_sent"]); phon = torch.from_numpy(golden["eval_phon"])
+    sd = make_state(state_spec, "gen", requires_grad=True)
+    sp = make_state(state_spec, "post", requires_grad=True)
+    sent_r = sent.clone().requires_grad_(True); phon_r = phon.clone().requires_grad_(True)
+    g1r, g2r, g3r = O.decoder(sd, sent_r, phon_r, [20, 13], noise, train)
+    gsr = O.postnet(sp, g3r, train)
+    m = build(V, state_spec, "gen", train); m.fixed_noise = noise
+    p = build(V, state_spec, "post", train)
+    sent_d = sent.cuda().requires_grad_(True); phon_d = phon.cuda().requires_grad_(True)
+    g1, g2, g3 = m(sent_d, phon_d, [20, 13])
+    gs = p(g3)
+    assert g1.shape == (2, 1, 20, 20) and g2.shape == (2, 1, 40, 40) and g3.shape == (2, 1, 80, 80) and gs.shape == (2, 1, 321, 80)
+    for a, b in ((g1, g1r), (g2, g2r), (g3, g3r), (gs, gsr)):
+        assert rel_l2(a.detach().cpu(), b) < TOL
+        assert float((a.detach().cpu() - b.detach()).abs().max()) < 2e-4
+    if not train:
+        for a, k in ((g1, "eval_g1"), (g2, "eval_g2"), (g3, "eval_g3"), (gs, "eval_gs")):
+            assert rel_l2(a.detach().cpu(), golden[k]) < TOL, k
+        return
+    g = torch.Generator().manual_seed(4)
+    ws = [torch.randn(t.shape, generator=g) for t in (g1r, g2r, g3r, gsr)]
+    sum((t * w).sum() for t, w in zip((g1r, g2r, g3r, gsr), ws)).backward()
+    sum((t * w.cuda()).sum() for t, w in zip((g1, g2, g3, gs), ws)).backward()
+    grads_close(m, sd, GTOL)
+    grads_close(p, sp, GTOL)
+    assert rel_l2(sent_d.grad.cpu(), sent_r.grad) < GTOL
+    assert rel_l2(phon_d.grad.cpu(), phon_r.grad) < GTOL
+
+
+def test_masked_keys_do_not_matter(V, state_spec):
+    V.set_precision("fp32")
+    m = build(V, state_spec, "gen", False)
+    g = torch.Generator().manual_seed(5)
+    ph = torch.randn(2, 20, 512, generator=g).cuda(); feat = torch.randn(2, 20, 20, 128, generator=g).cuda()
+    with torch.no_grad():
+        a = m.att1(ph, feat, [20, 13])
+        ph2 = ph.clone(); ph2[1, 13:] += 10.0
+        b = m.att1(ph2, feat, torch.tensor([20, 13]))
+    assert torch.allclose(a, b, atol=1e-6)
+
+
+@pytest.mark.parametrize("name,scale", [("dis1", 0.25), ("dis2", 0.5), ("dis3", 1.0)])
+def test_discriminator_with_r1(V, state_spec, golden, name, scale):
+    V.set_precision("fp32")
+    vid, mel, spec, noise = golden_inputs()
+    x = mel if scale == 1.0 else O.bilinear_half(mel, scale)
+    sent = torch.from_numpy(golden["eval_sent"])
+    sd = make_state(state_spec, name, requires_grad=True)
+    xr = x.clone().requires_grad_(True)
+    ur, cr = O.discriminator(sd, xr, sent, 20)
+    gr = torch.autograd.grad(ur.sum(), xr, create_graph=True)[0]
+    pen = (gr.reshape(2, -1).norm(2, dim=1) ** 2).mean()
+    (O.gan_loss(ur, True) + O.gan_loss(cr, True) + pen).backward()
+    m = build(V, state_spec, name, True)
+    xd = x.cuda().requires_grad_(True)
+    u, c = m(xd, sent.cuda(), 20)
+    assert u.shape == (2, 1) and c.shape == (2, 1)
+    assert rel_l2(u.detach().cpu(), ur) < TOL and rel_l2(c.detach().cpu(), cr) < TOL
+    assert rel_l2(u.detach().cpu(), golden[f"eval_{name[:1]}{name[-1]}_u"]) < TOL
+    gd = torch.autograd.grad(u.sum(), xd, create_graph=True)[0]
+    assert rel_l2(gd.detach().cpu(), gr) < TOL
+    pend = V.ops.sum_sq(gd, 0.5)
+    assert abs(float(pend) - float(pen)) <= 1e-4 * max(1.0, abs(float(pen)))
+    (V.models.gan_loss(u, True) + V.models.gan_loss(c, True) + pend).backward()
+    grads_close(m, sd, GTOL)
+
+
+def test_sync_discriminator(V, state_spec, golden):
+    V.set_precision("fp32")
+    vid, mel, spec, noise = golden_inputs()
+    phon = torch.from_numpy(golden["eval_phon"])
+    for gen in (False, True):
+        sd = make_state(state_spec, "s_dis", requires_grad=True)
+        pr = phon.clone().requires_grad_(True); mr = mel.clone().requires_grad_(True)
+        lr = O.sync_discriminator(sd, pr, mr, gen, True)
+        lr.mean().backward()
+        m = build(V, state_spec, "s_dis", True)
+        pd_, md = phon.cuda().requires_grad_(True), mel.cuda().requires_grad_(True)
+        l = m(pd_, md, gen)
+        assert l.shape == (2,)
+        assert rel_l2(l.detach().cpu(), lr) < TOL
+        l.mean().backward()
+        grads_close(m, sd, GTOL)
+        assert rel_l2(md.grad.cpu(), mr.grad) < GTOL
+        assert rel_l2(pd_.grad.cpu(), pr.grad) < GTOL
+    m.eval()
+    with torch.no_grad():
+        assert rel_l2(m(phon.cuda(), mel.cuda()).cpu(), golden["eval_sync_nce"]) < TOL
+
+
+def test_bf16_mode_forward_bound(V, state_spec, golden):
+    """bf16 storage + tcgen05 kernels: stated bound on the generator/front-end outputs."""
+    vid, mel, spec, noise = golden_inputs()
+    V.set_precision("bf16")
+    try:
+        with torch.no_grad():
+            vf = build(V, state_spec, "v_front", False)
+            phon, sent = vf(vid.cuda())
+            e_ph, e_s = rel_l2(phon.cpu(), golden["eval_phon"]), rel_l2(sent.cpu(), golden["eval_sent"])
+            gen = build(V, state_spec, "gen", False); gen.fixed_noise = noise
+            g1, g2, g3 = gen(torch.from_numpy(golden["eval_sent"]).cuda(), torch.from_numpy(golden["eval_phon"]).cuda(), [20, 13])
+            post = build(V, state_spec, "post", False)
+            gs = post(torch.from_numpy(golden["eval_g3"]).cuda())
+            errs = dict(phon=e_ph, sent=e_s, g1=rel_l2(g1.cpu(), golden["eval_g1"]), g2=rel_l2(g2.cpu(), golden["eval_g2"]),
+                        g3=rel_l2(g3.cpu(), golden["eval_g3"]), gs=rel_l2(gs.cpu(), golden["eval_gs"]))
+            print("bf16 forward errors", errs)
+            l1 = float((g3.cpu() - torch.from_numpy(golden["eval_g3"])).abs().mean())
+            print("mel L1 vs reference (bf16):", l1)
+            assert all(v < BF16_TOL for v in errs.values()), errs
+    finally:
+        V.set_precision("fp32")

@@ -1,0 +1,310 @@
+"""Op-level parity of the CUDA library (through the C ABI) against the oracle's primitives: the same torch fp32
+CPU functional ops the oracle (oracle/vca_oracle.py) is written in.  fp32 kernels: <= 1e-4 relative L2 (north-star
+tolerance).  bf16 tcgen05 kernels: <= 1e-2 relative L2 against fp32 math on the bf16-rounded inputs (the only
+error sources are the bf16 rounding of the output and the accumulation order)."""
+import math
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 1e-2
+
+
+@pytest.fixture(scope="module")
+def V():
+    import vcagan_b200
+    assert vcagan_b200.lib().query("vca_device_ok") == 1, "needs an sm_100 device"
+    return vcagan_b200
+
+
+def cl(x):   # NCHW -> channels-last
+    return x.permute(0, 2, 3, 1).contiguous() if x.dim() == 4 else x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous() if x.dim() == 4 else x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+CONV_CASES = [
+    # N, Cin, H, W, Cout, k, stride, pad
+    (2, 16, 9, 11, 24, 5, 1, 2),
+    (2, 1, 20, 17, 32, 5, 1, 2),
+    (3, 8, 14, 14, 16, 3, 2, 1),
+    (2, 12, 7, 7, 20, 1, 2, 0),
+    (2, 20, 5, 9, 12, 5, 1, 0),
+    (1, 70, 6, 37, 65, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(V, case):
+    N, Cin, H, W, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g, requires_grad=True)
+    w = torch.randn(Cout, Cin, k, k, generator=g, requires_grad=True) / math.sqrt(Cin * k * k)
+    w = w.detach().requires_grad_(True)
+    b = torch.randn(Cout, generator=g, requires_grad=True)
+    y = F.conv2d(x, w, b, s, p)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    xd = cl(x.detach()).cuda().requires_grad_(True)
+    wd = w.detach().cuda().requires_grad_(True)
+    bd = b.detach().cuda().requires_grad_(True)
+    V.set_precision("fp32")
+    yd = V.ops.conv(xd, wd, bd, (s, s), (p, p))
+    yd.backward(cl(dy).cuda())
+    assert rel_l2(nchw(yd.detach().cpu()), y) < FP32_TOL
+    assert rel_l2(nchw(xd.grad.cpu()), x.grad) < FP32_TOL
+    assert rel_l2(wd.grad.cpu(), w.grad) < FP32_TOL
+    assert rel_l2(bd.grad.cpu(), b.grad) < FP32_TOL
+
+
+def test_conv3d_stem_and_conv1d_fp32(V):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(1, 1, 6, 24, 20, generator=g, requires_grad=True)
+    w = (torch.randn(8, 1, 5, 7, 7, generator=g) / 15).requires_grad_(True)
+    y = F.conv3d(x, w, None, (1, 2, 2), (2, 3, 3))
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    V.set_precision("fp32")
+    xd = cl(x.detach()).cuda().requires_grad_(True); wd = w.detach().cuda().requires_grad_(True)
+    yd = V.ops.conv(xd, wd, None, (1, 2, 2), (2, 3, 3))
+    yd.backward(cl(dy).cuda())
+    assert rel_l2(nchw(yd.detach().cpu()), y) < FP32_TOL
+    assert rel_l2(wd.grad.cpu(), w.grad) < FP32_TOL
+    assert rel_l2(nchw(xd.grad.cpu()), x.grad) < FP32_TOL
+    # conv1d k7 p3 as in Postnet (generator.py:177)
+    x1 = torch.randn(2, 10, 33, generator=g, requires_grad=True)
+    w1 = (torch.randn(12, 10, 7, generator=g) / 8).requires_grad_(True)
+    y1 = F.conv1d(x1, w1, None, 1, 3)
+    y1.sum().backward()
+    xd1 = x1.detach().permute(0, 2, 1).contiguous().view(2, 1, 33, 10).cuda().requires_grad_(True)
+    wd1 = w1.detach().cuda().requires_grad_(True)
+    yd1 = V.ops.conv(xd1, wd1, None, (1,), (3,))
+    yd1.sum().backward()
+    assert rel_l2(yd1.detach().cpu().view(2, 33, 12).permute(0, 2, 1), y1) < FP32_TOL
+    assert rel_l2(wd1.grad.cpu(), w1.grad) < FP32_TOL
+
+
+def test_conv_double_backward_fp32(V):
+    """R1 needs grad-of-grad through conv + LeakyReLU + avg-pool (train.py:188-194)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 4, 8, 10, generator=g, requires_grad=True)
+    w1 = (torch.randn(6, 4, 5, 5, generator=g) / 10).requires_grad_(True)
+    w2 = (torch.randn(3, 6, 1, 1, generator=g) / 3).requires_grad_(True)
+
+    def ref(x, w1, w2):
+        h = F.avg_pool2d(F.conv2d(F.leaky_relu(x, 0.2), w1, None, 1, 2), 2)
+        return (F.conv2d(F.leaky_relu(h, 0.2), w2) / math.sqrt(2)).mean([2, 3]).sum()
+    out = ref(x, w1, w2)
+    gx = torch.autograd.grad(out, x, create_graph=True)[0]
+    pen = (gx.reshape(2, -1).norm(2, dim=1) ** 2).mean()
+    pen.backward()
+    V.set_precision("fp32")
+    O = V.ops
+    xd = cl(x.detach()).cuda().requires_grad_(True)
+    w1d = w1.detach().cuda().requires_grad_(True); w2d = w2.detach().cuda().requires_grad_(True)
+    h = O.avg_pool2(O.conv(O.lrelu(xd), w1d, None, (1, 1), (2, 2)))
+    o = O.spatial_mean(O.scale(O.conv(O.lrelu(h), w2d), 1 / math.sqrt(2))).sum()
+    gxd = torch.autograd.grad(o, xd, create_graph=True)[0]
+    assert rel_l2(nchw(gxd.detach().cpu()), gx) < FP32_TOL
+    pend = O.sum_sq(gxd, 1.0 / 2)
+    assert abs(float(pend) - float(pen)) < 1e-4 * max(1.0, abs(float(pen)))
+    pend.backward()
+    assert rel_l2(w1d.grad.cpu(), w1.grad) < 2e-4
+    assert rel_l2(w2d.grad.cpu(), w2.grad) < 2e-4
+
+
+TC_CASES = [
+    # N, Cin, H, W, Cout, k, pad
+    (8, 64, 1, 1, 64, 1, 0),       # plain GEMM 8x64x64
+    (300, 128, 1, 1, 256, 1, 0),   # GEMM with a ragged M tile
+    (2, 64, 20, 25, 128, 5, 2),    # generator-like 5x5
+    (3, 192, 20, 19, 128, 5, 2),   # attconv1 channels (3 K chunks), ragged W
+    (2, 32, 12, 30, 32, 5, 2),     # Cin = 32 (half-filled K chunk)
+    (4, 256, 7, 7, 256, 3, 1),     # resnet layer3-like, multi-image box
+    (5, 128, 5, 9, 128, 5, 0),     # discriminator uncond: pad 0
+    (2, 96, 10, 21, 64, 5, 2),     # attconv2 channels
+    (9, 512, 4, 4, 512, 3, 1),     # resnet layer4
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_bf16(V, case):
+    N, Cin, H, W, Cout, k, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float().requires_grad_(True)
+    b = torch.randn(Cout, generator=g).requires_grad_(True)
+    y = F.conv2d(x, w, b, 1, p)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    V.set_precision("bf16")
+    try:
+        from vcagan_b200._lib import ConvGeom
+        xd = cl(x.detach()).cuda().bfloat16().requires_grad_(True)
+        wd = w.detach().cuda().requires_grad_(True)
+        bd = b.detach().cuda().requires_grad_(True)
+        n0 = V.lib().launches
+        yd = V.ops.conv(xd, wd, bd, (1, 1), (p, p))
+        yd.backward(cl(dy).cuda().bfloat16())
+        torch.cuda.synchronize()
+        e = dict(fwd=rel_l2(nchw(yd.detach().float().cpu()), y), dgrad=rel_l2(nchw(xd.grad.float().cpu()), x.grad),
+                 wgrad=rel_l2(wd.grad.cpu(), w.grad), bias=rel_l2(bd.grad.cpu(), b.grad))
+        print("tc case", case, e)
+        assert e["fwd"] < BF16_TOL, e
+        assert e["dgrad"] < BF16_TOL, e
+        assert e["wgrad"] < BF16_TOL, e
+        assert e["bias"] < BF16_TOL, e
+    finally:
+        V.set_precision("fp32")
+
+
+def test_bn_act_pool(V):
+    g = torch.Generator().manual_seed(5)
+    V.set_precision("fp32")
+    O = V.ops
+    for act in ("prelu", "lrelu", "relu", "none"):
+        x = torch.randn(3, 10, 6, 7, generator=g, requires_grad=True)
+        res = torch.randn(3, 10, 6, 7, generator=g, requires_grad=True)
+        bn = torch.nn.BatchNorm2d(10)
+        bn.weight.data = 1 + 0.2 * torch.randn(10, generator=g); bn.bias.data = 0.1 * torch.randn(10, generator=g)
+        pw = (0.25 + 0.1 * torch.randn(10, generator=g)).requires_grad_(True)
+        def actf(v):
+            return {"prelu": lambda: F.prelu(v, pw), "lrelu": lambda: F.leaky_relu(v, 0.2), "relu": lambda: F.relu(v),
+                    "none": lambda: v}[act]()
+        y = actf(bn(x) + res)
+        dy = torch.randn(y.shape, generator=g)
+        y.backward(dy)
+        bnd = torch.nn.BatchNorm2d(10).cuda()
+        bnd.weight.data = bn.weight.data.clone().cuda(); bnd.bias.data = bn.bias.data.clone().cuda()
+        xd = cl(x.detach()).cuda().requires_grad_(True); rd = cl(res.detach()).cuda().requires_grad_(True)
+        pwd = pw.detach().cuda().requires_grad_(True)
+        code = {"prelu": O.ACT_PRELU, "lrelu": O.ACT_LRELU, "relu": O.ACT_RELU, "none": O.ACT_NONE}[act]
+        yd = O.bn_act(xd, bnd, code, 0.2, pwd if act == "prelu" else None, res=rd)
+        yd.backward(cl(dy).cuda())
+        assert rel_l2(nchw(yd.detach().cpu()), y) < FP32_TOL, act
+        assert rel_l2(nchw(xd.grad.cpu()), x.grad) < 2e-4, act
+        assert rel_l2(nchw(rd.grad.cpu()), res.grad) < FP32_TOL, act
+        assert rel_l2(bnd.weight.grad.cpu(), bn.weight.grad) < 2e-4, act
+        assert rel_l2(bnd.bias.grad.cpu(), bn.bias.grad) < FP32_TOL, act
+        if act == "prelu":
+            assert rel_l2(pwd.grad.cpu(), pw.grad) < 2e-4
+        assert rel_l2(bnd.running_mean.cpu(), bn.running_mean) < 1e-5
+        assert rel_l2(bnd.running_var.cpu(), bn.running_var) < 1e-5
+        assert int(bnd.num_batches_tracked) == 1
+    # eval mode
+    bn.eval(); bnd.eval()
+    x = torch.randn(2, 10, 4, 5, generator=g)
+    assert rel_l2(nchw(O.bn_act(cl(x).cuda(), bnd, O.ACT_LRELU, 0.2).cpu()), F.leaky_relu(bn(x), 0.2)) < FP32_TOL
+    # pools
+    x = torch.randn(2, 6, 9, 11, generator=g, requires_grad=True)
+    for ref_fn, fn in ((lambda t: F.avg_pool2d(t, 2), O.avg_pool2),
+                       (lambda t: F.interpolate(t, scale_factor=2, mode="nearest"), O.upsample2),
+                       (lambda t: F.max_pool2d(t, 3, 2, 1), O.maxpool3x3s2)):
+        x.grad = None
+        y = ref_fn(x); dy = torch.randn(y.shape, generator=g); y.backward(dy)
+        xd = cl(x.detach()).cuda().requires_grad_(True)
+        yd = fn(xd); yd.backward(cl(dy).cuda())
+        assert rel_l2(nchw(yd.detach().cpu()), y) < 1e-6
+        assert rel_l2(nchw(xd.grad.cpu()), x.grad) < 1e-6
+    xd = cl(x.detach()).cuda().requires_grad_(True)
+    m = O.spatial_mean(xd); m.sum().backward()
+    assert rel_l2(m.detach().cpu(), x.detach().mean([2, 3])) < 1e-6
+    assert torch.allclose(xd.grad.cpu(), torch.full_like(xd.grad.cpu(), 1.0 / 99))
+    t = torch.randn(2, 6, 9, 11, generator=g)
+    assert rel_l2(O.tanh(t.cuda()).cpu(), torch.tanh(t)) < 1e-6
+
+
+def test_gru_layer(V):
+    g = torch.Generator().manual_seed(9)
+    T, B, I, H = 7, 3, 20, 16
+    gru = torch.nn.GRU(I, H, 1, bidirectional=True)
+    x = torch.randn(T, B, I, generator=g, requires_grad=True)
+    y, _ = gru(x)
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    names = [f"{p}_l0{s}" for s in ("", "_reverse") for p in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    ps = [getattr(gru, n).detach().cuda().requires_grad_(True) for n in names]
+    xd = x.detach().cuda().requires_grad_(True)
+    yd = V.ops.gru_layer(xd, ps)
+    yd.backward(dy.cuda())
+    assert rel_l2(yd.detach().cpu(), y) < FP32_TOL
+    assert rel_l2(xd.grad.cpu(), x.grad) < FP32_TOL
+    for n, p in zip(names, ps):
+        assert rel_l2(p.grad.cpu(), getattr(gru, n).grad) < 2e-4, n
+
+
+def test_attention_and_losses(V):
+    g = torch.Generator().manual_seed(13)
+    O = V.ops
+    q = torch.randn(2, 9, 16, generator=g, requires_grad=True)
+    k = torch.randn(2, 7, 16, generator=g, requires_grad=True)
+    v = torch.randn(2, 7, 16, generator=g, requires_grad=True)
+    lens = [7, 4]
+    att = torch.bmm(q, k.transpose(1, 2)) / 4
+    for i in range(2):
+        att[i, :, lens[i]:] = float("-inf")
+    out = torch.bmm(torch.softmax(att, 2), v)
+    dout = torch.randn(out.shape, generator=g); out.backward(dout)
+    qd, kd, vd = (t.detach().cuda().requires_grad_(True) for t in (q, k, v))
+    a = O.masked_softmax(O.bmm(qd, kd.transpose(1, 2), 0.25), torch.tensor(lens, dtype=torch.int32).cuda())
+    od = O.bmm(a, vd); od.backward(dout.cuda())
+    assert rel_l2(od.detach().cpu(), out) < FP32_TOL
+    for a_, b_ in ((qd, q), (kd, k), (vd, v)):
+        assert rel_l2(a_.grad.cpu(), b_.grad) < FP32_TOL
+    # sync losses (generator.py:347-359)
+    vf = torch.randn(3, 6, 24, generator=g, requires_grad=True); af = torch.randn(3, 6, 24, generator=g, requires_grad=True)
+    vn, an = F.normalize(vf, dim=2), F.normalize(af, dim=2)
+    sim = torch.bmm(vn, an.transpose(1, 2))
+    nce = -0.5 * (torch.diagonal(F.log_softmax(sim, 2), dim1=-2, dim2=-1).mean(1) + torch.diagonal(F.log_softmax(sim, 1), dim1=-2, dim2=-1).mean(1))
+    nce.mean().backward()
+    vfd, afd = vf.detach().cuda().requires_grad_(True), af.detach().cuda().requires_grad_(True)
+    nd = O.NceDiagFn.apply(O.bmm(O.L2NormFn.apply(vfd), O.L2NormFn.apply(afd).transpose(1, 2), 1.0))
+    nd.mean().backward()
+    assert rel_l2(nd.detach().cpu(), nce) < FP32_TOL
+    assert rel_l2(vfd.grad.cpu(), vf.grad) < 2e-4 and rel_l2(afd.grad.cpu(), af.grad) < 2e-4
+    vf.grad = None; af.grad = None
+    cs = 5.0 - F.cosine_similarity(vf, af, 2).abs().mean(1)
+    cs.mean().backward()
+    vfd, afd = vf.detach().cuda().requires_grad_(True), af.detach().cuda().requires_grad_(True)
+    cd = O.CosAbsMeanFn.apply(vfd, afd); cd.mean().backward()
+    assert rel_l2(cd.detach().cpu(), cs) < FP32_TOL
+    assert rel_l2(vfd.grad.cpu(), vf.grad) < 2e-4 and rel_l2(afd.grad.cpu(), af.grad) < 2e-4
+    # gan loss, L1
+    lo = torch.randn(5, 1, generator=g, requires_grad=True)
+    for lab in (True, False):
+        lo.grad = None
+        ref = F.softplus(-lo if lab else lo).mean(); ref.backward()
+        lod = lo.detach().cuda().requires_grad_(True)
+        got = V.models.gan_loss(lod, lab); got.backward()
+        assert abs(float(got) - float(ref)) < 1e-6 and rel_l2(lod.grad.cpu(), lo.grad) < 1e-5
+    assert abs(float(V.models.gan_loss(torch.zeros(4, 1).cuda(), True)) - math.log(2)) < 1e-6
+    a = torch.randn(4, 50, generator=g, requires_grad=True); b = torch.randn(4, 50, generator=g)
+    ref = F.l1_loss(a, b) * 3; ref.backward()
+    ad = a.detach().cuda().requires_grad_(True)
+    got = O.l1_mean(ad, b.cuda(), 3.0); got.backward()
+    assert abs(float(got) - float(ref)) < 1e-5 and rel_l2(ad.grad.cpu(), a.grad) < 1e-6
+
+
+def test_adam_amsgrad(V):
+    g = torch.Generator().manual_seed(21)
+    p = torch.randn(1000, generator=g); p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=1e-4, weight_decay=1e-5, amsgrad=True)
+    pd = p.clone().cuda(); m = torch.zeros_like(pd); v = torch.zeros_like(pd); vm = torch.zeros_like(pd)
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=g)
+        p_ref.grad = gr.clone(); opt.step()
+        V.lib().call("vca_adam_step", pd, gr.cuda(), m, v, vm, 1000, 1e-4, 0.9, 0.999, 1e-8, 1e-5, step, 1.0)
+    assert rel_l2((pd.cpu() - p), (p_ref.detach() - p)) < 1e-4
+
+
+def test_rng_moments(V):
+    n = V.ops.randn((1 << 20,), torch.float32, torch.device("cuda"))
+    assert abs(float(n.mean())) < 5e-3 and abs(float(n.std()) - 1) < 5e-3
+    d = V.ops.dropout(torch.ones(1 << 20, device="cuda"), 0.3, True)
+    assert abs(float((d == 0).float().mean()) - 0.3) < 5e-3 and abs(float(d.max()) - 1 / 0.7) < 1e-5

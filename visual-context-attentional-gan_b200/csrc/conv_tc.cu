@@ -1,0 +1,537 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution kernels for sm_100a (bf16 operands, fp32 accumulate).
+//
+// Forward and dgrad (stride 1) share one kernel:  for an output tile of up to 128 pixels (a 3-D box tn x th x tw of
+// the channels-last activation) and BN output channels,
+//     D[pixel, co] = sum_{tap} sum_{cin chunk of 64}  A_tap[pixel, 64] * W_tap[co, 64]^T
+// where A_tap is the SAME box shifted by the tap offset -- fetched by one 4-D TMA box load whose out-of-bounds
+// elements are zero-filled by the TMA unit (that is the convolution's zero padding; nothing is materialised) --
+// and W_tap is a [BN x 64] K-major slab of the packed weights.  Both land in 128B-swizzled shared memory and are
+// consumed by tcgen05.mma (UMMA 128 x BN x 16) into a TMEM accumulator; 4 epilogue warps read it back with
+// tcgen05.ld, add the bias and store bf16 channels-last.
+//
+// Wgrad:  dW[tap][co, ci] = sum_pixels dY[pixel, co] * X[pixel (+) tap, ci]  -- the reduction runs over pixels, so
+// both operands are MN-major (the pixel index is the slow smem dimension); split-K over pixel tiles, fp32 red.add
+// into the parameter layout.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_id % 4).  Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor"
+// / "instruction descriptor" tables.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int KC = 64;              // bf16 channels per K chunk = 128 B = one SWIZZLE_128B row
+constexpr int TILE_ROWS = 128;      // UMMA M
+constexpr int A_STAGE_BYTES = TILE_ROWS * 128;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  const uint32_t addr = smem_u32(bar);
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > SPIN_LIMIT) __trap();  // a lost arrival must fail loudly, never hang the GPU
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// Shared-memory matrix descriptor (SM100 "version 1"), SWIZZLE_128B.
+//   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
+//   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1   bits [61,64) layout type (2 = SW128)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor, kind::f16: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
+// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits [17,23), M>>4 at bits [24,29).
+__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+struct FwdParams {
+  int NF, OH, OW, Cout;          // output tensor [NF, OH, OW, Cout]
+  int tn, th, tw;                // pixel box
+  int tiles_w, tiles_h;          // tile counts along W and H (tiles along NF = gridDim.x / (tiles_w*tiles_h))
+  int KH, KW, ph, pw;            // input coord = output coord + k - p
+  int kchunks;                   // ceil(Kdim / 64)
+  int BN;                        // output channels per CTA (multiple of 16, <= 256)
+  int stages;
+  int flip;                      // 1: weight tap index is mirrored (dgrad)
+  uint32_t a_bytes, b_bytes;     // bytes the two TMA loads of one stage deliver
+  uint32_t tmem_cols;
+  const float* bias;             // [Cout] or null
+  bf16* y;
+};
+
+__global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                          const __grid_constant__ CUtensorMap tmB, const FwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  const uint32_t b_stage = (uint32_t)p.BN * 128u;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)S * A_STAGE_BYTES;
+  uint64_t* full = (uint64_t*)(sB + (size_t)S * b_stage);
+  uint64_t* empty = full + S;
+  uint64_t* accum_bar = empty + S;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int t = blockIdx.x;
+  const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+  const int th_i = t % p.tiles_h; const int tn_i = t / p.tiles_h;
+  const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+  const int co0 = blockIdx.y * p.BN;
+  const int iters = p.KH * p.KW * p.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        const int kc = it % p.kchunks; const int tap = it / p.kchunks;
+        const int a = tap / p.KW, b = tap % p.KW;
+        const int wtap = p.flip ? (p.KH - 1 - a) * p.KW + (p.KW - 1 - b) : tap;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+        tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &tmA, &full[stage], kc * KC, ow0 + b - p.pw, oh0 + a - p.ph, n0);
+        tma_load_3d(sB + (size_t)stage * b_stage, &tmB, &full[stage], kc * KC, co0, wtap);
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(TILE_ROWS, p.BN, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int it = 0; it < iters; ++it) {
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
+        const uint32_t b0 = smem_u32(sB + (size_t)stage * b_stage);
+#pragma unroll
+        for (int k = 0; k < KC / 16; ++k) {
+          const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
+          const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
+          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+        }
+        umma_commit(&empty[stage]);  // implies tcgen05.fence::before_thread_sync
+        if (++stage == S) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(accum_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: TMEM -> registers -> (+bias) -> bf16 -> global (channels-last)
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // tile row = pixel index inside the box
+    const int hw = p.th * p.tw;
+    const int in = r / hw, rem = r - in * hw;
+    const int ih = rem / p.tw, iw = rem - ih * p.tw;
+    const int n = n0 + in, oh = oh0 + ih, ow = ow0 + iw;
+    const bool row_ok = (r < p.tn * hw) && n < p.NF && oh < p.OH && ow < p.OW;
+    bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (row_ok && co0 + c < p.Cout) {
+        if (p.bias) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
+        }
+        if (co0 + c + 16 <= p.Cout) {
+          uint4 o0, o1;
+          __nv_bfloat162 h;
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+          o0 = make_uint4(w[0], w[1], w[2], w[3]); o1 = make_uint4(w[4], w[5], w[6], w[7]);
+          *reinterpret_cast<uint4*>(yrow + c) = o0;
+          *reinterpret_cast<uint4*>(yrow + c + 8) = o1;
+        } else {
+          for (int i = 0; i < 16 && co0 + c + i < p.Cout; ++i) yrow[c + i] = __float2bfloat16_rn(v[i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// wgrad
+// ---------------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  int NF, OH, OW;                // dY spatial dims
+  int Cout, Cin, taps;
+  int tn, th, tw, tiles_w, tiles_h, num_ptiles;
+  int KW, ph, pw;
+  int BNc;                       // ci per CTA (multiple of 16, <= 128)
+  int ci_tiles;
+  int stages;
+  int ptiles_per_split;
+  int a_atoms, b_atoms;          // 64-channel atoms actually loaded for A (co) and B (ci)
+  uint32_t atom_bytes;           // bytes one TMA box delivers (box pixels * 128)
+  uint32_t ksteps;               // ceil(box pixels / 16)
+  uint32_t tmem_cols;
+  float* dw;                     // [Cout][Cin][taps] fp32, accumulated with red.add
+};
+
+__global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
+                                                            const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  const int S = p.stages;
+  const uint32_t a_stage = 2u * A_STAGE_BYTES;                       // co: 2 atoms of 64
+  const uint32_t b_stage = (uint32_t)((p.BNc + 63) / 64) * A_STAGE_BYTES;  // ci atoms
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)S * a_stage;
+  uint64_t* full = (uint64_t*)(sB + (size_t)S * b_stage);
+  uint64_t* empty = full + S;
+  uint64_t* accum_bar = empty + S;
+  uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tap = blockIdx.z;
+  const int kh = tap / p.KW, kw = tap % p.KW;
+  const int co0 = (blockIdx.y / p.ci_tiles) * TILE_ROWS;
+  const int ci0 = (blockIdx.y % p.ci_tiles) * p.BNc;
+  const int pt_beg = blockIdx.x * p.ptiles_per_split;
+  const int pt_end = min(pt_beg + p.ptiles_per_split, p.num_ptiles);
+  const int iters = pt_end - pt_beg;
+
+  // Rows a TMA box never writes (box pixels < 128, or an atom that is never loaded) must read as zero.
+  {
+    uint4 z = make_uint4(0, 0, 0, 0);
+    uint4* ptr = (uint4*)smem;
+    const size_t n16 = ((size_t)S * (a_stage + b_stage)) / 16;
+    for (size_t i = threadIdx.x; i < n16; i += blockDim.x) ptr[i] = z;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(accum_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (iters > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < iters; ++it) {
+          int t = pt_beg + it;
+          const int tw_i = t % p.tiles_w; t /= p.tiles_w;
+          const int th_i = t % p.tiles_h; const int tn_i = t / p.tiles_h;
+          const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], (uint32_t)(p.a_atoms + p.b_atoms) * p.atom_bytes);
+          for (int a = 0; a < p.a_atoms; ++a)
+            tma_load_4d(sA + (size_t)stage * a_stage + (size_t)a * A_STAGE_BYTES, &tmDY, &full[stage], co0 + a * KC, ow0, oh0, n0);
+          for (int b = 0; b < p.b_atoms; ++b)
+            tma_load_4d(sB + (size_t)stage * b_stage + (size_t)b * A_STAGE_BYTES, &tmX, &full[stage], ci0 + b * KC,
+                        ow0 + kw - p.pw, oh0 + kh - p.ph, n0);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(TILE_ROWS, p.BNc, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int it = 0; it < iters; ++it) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + (size_t)stage * a_stage);
+          const uint32_t b0 = smem_u32(sB + (size_t)stage * b_stage);
+          for (uint32_t k = 0; k < p.ksteps; ++k) {
+            // MN-major SW128: 16 pixels (K) = 16 rows of 128 B; atoms of 64 channels are A_STAGE_BYTES apart (LBO)
+            const uint64_t ad = make_desc(a0 + k * 2048, A_STAGE_BYTES, 1024);
+            const uint64_t bd = make_desc(b0 + k * 2048, A_STAGE_BYTES, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (it | (int)k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(accum_bar);
+      }
+      __syncwarp();
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      for (int c = 0; c < p.BNc; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (co < p.Cout) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int ci = ci0 + c + i;
+            if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.taps + tap, v[i]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// bf16 tensor map with a 64-channel (128 B) inner box, SWIZZLE_128B, zero OOB fill.
+// dims/box are innermost-first; rank 3 or 4.
+int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { vca_set_error("cuTensorMapEncodeTiled entry point unavailable"); return VCA_ERR_CUDA; }
+  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  long long stride = 2;
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1;
+    if (i > 0) gs[i - 1] = (cuuint64_t)stride;
+    stride *= dims[i];
+  }
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { vca_set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return VCA_ERR_CUDA; }
+  return VCA_OK;
+}
+
+// choose the pixel box (tn, th, tw), tn*th*tw <= 128, that minimises the number of tiles
+void choose_box(int NF, int H, int W, int& tn, int& th, int& tw) {
+  long long best = -1; tn = th = tw = 1;
+  for (int w = 1; w <= W && w <= 128; ++w) {
+    for (int h = 1; h <= H && w * h <= 128; ++h) {
+      int n = 128 / (w * h); if (n > NF) n = NF; if (n < 1) n = 1;
+      long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((NF + n - 1) / n);
+      if (best < 0 || tiles < best || (tiles == best && w > tw)) { best = tiles; tn = n; th = h; tw = w; }
+    }
+  }
+}
+uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
+
+int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
+             const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s) {
+  FwdParams p;
+  p.NF = NF; p.OH = OH; p.OW = OW; p.Cout = Nout;
+  choose_box(NF, OH, OW, p.tn, p.th, p.tw);
+  p.tiles_w = (OW + p.tw - 1) / p.tw; p.tiles_h = (OH + p.th - 1) / p.th;
+  int tiles_n = (NF + p.tn - 1) / p.tn;
+  p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw; p.flip = flip;
+  p.kchunks = (Kdim + KC - 1) / KC;
+  int bn = Nout >= 256 ? 256 : ((Nout + 15) / 16) * 16;
+  // keep >= ~1 wave of CTAs when the problem is small: halve BN
+  long long ptiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
+  while (bn > 64 && ptiles * ((Nout + bn - 1) / bn) < vca_num_sms() && bn % 32 == 0) bn /= 2;
+  p.BN = bn;
+  p.a_bytes = (uint32_t)(p.tn * p.th * p.tw) * 128u;
+  p.b_bytes = (uint32_t)bn * 128u;
+  p.tmem_cols = pow2_cols(bn);
+  p.bias = bias; p.y = (bf16*)y;
+  const size_t stage_bytes = A_STAGE_BYTES + (size_t)bn * 128;
+  int stages = (int)((100 * 1024) / stage_bytes);
+  if (stages > 6) stages = 6; if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024 + 256;
+
+  CUtensorMap tmA, tmB;
+  long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.tw, p.th, p.tn};
+  long long dB[3] = {Kdim, Nout, (long long)KH * KW}; int bB[3] = {KC, bn, 1};
+  int rc = make_map(&tmA, x, 4, dA, bA); if (rc) return rc;
+  rc = make_map(&tmB, wpk, 3, dB, bB); if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      vca_set_error("cudaFuncSetAttribute(conv_tc_fwd_kernel) failed"); return VCA_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((unsigned)ptiles, (unsigned)((Nout + bn - 1) / bn), 1);
+  conv_tc_fwd_kernel<<<grid, 192, smem, s>>>(tmA, tmB, p);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+
+bool tc_geom_ok(const ConvGeom& g) {
+  return g.ID == 1 && g.OD == 1 && g.KD == 1 && g.pd == 0 && g.sd == 1 && g.sh == 1 && g.sw == 1 && g.Cin % 8 == 0 &&
+         g.Cout % 8 == 0 && g.KH * g.KW <= 65535 && g.OH == g.IH + 2 * g.ph - g.KH + 1 && g.OW == g.IW + 2 * g.pw - g.KW + 1 &&
+         g.OH > 0 && g.OW > 0 && g.N > 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+// kind: 0 forward, 1 dgrad, 2 wgrad.  1 when the tcgen05 path handles this geometry.
+int vca_conv_tc_supported(const ConvGeom* g, int kind) {
+  if (!g || !tc_geom_ok(*g)) return 0;
+  if (kind == 0) return g->Cin >= 32;
+  if (kind == 1) return g->Cout >= 32;
+  if (kind == 2) return g->Cin >= 16 && g->Cout >= 16;
+  return 0;
+}
+
+// x [N,IH,IW,Cin] bf16; wd = packed [taps][Cout][Cin] bf16 (vca_pack_conv_weight "wd"); y [N,OH,OW,Cout] bf16.
+int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t s) {
+  VCA_CHECK_ARG(g && x && wd && y && vca_conv_tc_supported(g, 0));
+  return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, bias, y, s);
+}
+// dy [N,OH,OW,Cout] bf16; wf = packed [taps][Cin][Cout] bf16 (vca_pack_conv_weight "wf"); dx [N,IH,IW,Cin] bf16.
+int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t s) {
+  VCA_CHECK_ARG(g && dy && wf && dx && vca_conv_tc_supported(g, 1));
+  return fwd_like(g->N, g->OH, g->OW, g->Cout, g->IH, g->IW, g->Cin, g->KH, g->KW, g->KH - 1 - g->ph, g->KW - 1 - g->pw, 1, dy, wf,
+                  nullptr, dx, s);
+}
+// dw fp32 [Cout][Cin][taps], zero on entry (accumulated with red.add across pixel splits).
+int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t s) {
+  VCA_CHECK_ARG(g && dy && x && dw && vca_conv_tc_supported(g, 2));
+  WgradParams p;
+  p.NF = g->N; p.OH = g->OH; p.OW = g->OW; p.Cout = g->Cout; p.Cin = g->Cin; p.taps = g->KH * g->KW;
+  choose_box(g->N, g->OH, g->OW, p.tn, p.th, p.tw);
+  p.tiles_w = (g->OW + p.tw - 1) / p.tw; p.tiles_h = (g->OH + p.th - 1) / p.th;
+  p.num_ptiles = p.tiles_w * p.tiles_h * ((g->N + p.tn - 1) / p.tn);
+  p.KW = g->KW; p.ph = g->ph; p.pw = g->pw;
+  p.BNc = g->Cin >= 128 ? 128 : ((g->Cin + 15) / 16) * 16;
+  p.ci_tiles = (g->Cin + p.BNc - 1) / p.BNc;
+  const int co_tiles = (g->Cout + TILE_ROWS - 1) / TILE_ROWS;
+  p.a_atoms = g->Cout >= TILE_ROWS ? 2 : (g->Cout + KC - 1) / KC;   // per co tile; tail tiles rely on TMA zero fill
+  if (p.a_atoms > 2) p.a_atoms = 2;
+  p.b_atoms = (p.BNc + KC - 1) / KC;
+  const int box_px = p.tn * p.th * p.tw;
+  p.atom_bytes = (uint32_t)box_px * 128u;
+  p.ksteps = (uint32_t)((box_px + 15) / 16);
+  p.tmem_cols = pow2_cols(p.BNc);
+  p.dw = dw;
+  const size_t stage_bytes = 2 * A_STAGE_BYTES + (size_t)p.b_atoms * A_STAGE_BYTES;
+  int stages = (int)((190 * 1024) / stage_bytes);
+  if (stages > 4) stages = 4; if (stages < 2) stages = 2;
+  p.stages = stages;
+  const size_t smem = stages * stage_bytes + 1024 + 256;
+  const long long base_ctas = (long long)co_tiles * p.ci_tiles * p.taps;
+  int split = (int)((2ll * vca_num_sms() + base_ctas - 1) / base_ctas);
+  if (split < 1) split = 1; if (split > p.num_ptiles) split = p.num_ptiles;
+  p.ptiles_per_split = (p.num_ptiles + split - 1) / split;
+  split = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
+
+  CUtensorMap tmDY, tmX;
+  long long dY[4] = {g->Cout, g->OW, g->OH, g->N}; int bx[4] = {KC, p.tw, p.th, p.tn};
+  long long dX[4] = {g->Cin, g->IW, g->IH, g->N};
+  int rc = make_map(&tmDY, dy, 4, dY, bx); if (rc) return rc;
+  rc = make_map(&tmX, x, 4, dX, bx); if (rc) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+      vca_set_error("cudaFuncSetAttribute(conv_tc_wgrad_kernel) failed"); return VCA_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  VCA_CHECK_ARG((long long)co_tiles * p.ci_tiles <= 65535 && p.taps <= 65535);
+  dim3 grid((unsigned)split, (unsigned)(co_tiles * p.ci_tiles), (unsigned)p.taps);
+  conv_tc_wgrad_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, p);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,94 @@
+"""ctypes binding of libvcagan_b200.so.  Prototypes are parsed from include/vcagan.h so the header is the
+single source of truth for the C ABI.  There is no fallback: if the library is missing or a call fails this
+raises, it never silently routes to torch or the CPU."""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+LIB_PATH = os.path.join(_HERE, "libvcagan_b200.so")
+HEADER = os.path.join(_ROOT, "include", "vcagan.h")
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("N", "ID", "IH", "IW", "Cin", "OD", "OH", "OW", "Cout", "KD", "KH", "KW", "sd", "sh", "sw", "pd", "ph", "pw")]
+
+    def key(self):
+        return tuple(getattr(self, f) for f, _ in self._fields_)
+
+
+_CT = {
+    "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
+    "unsigned long long": ctypes.c_ulonglong, "cudaStream_t": ctypes.c_void_p,
+}
+
+
+def parse_header(path=HEADER):
+    """-> {name: (restype, [argtypes])} for every vca_* prototype in the header."""
+    txt = open(path).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"(const char\*|int)\s+(vca_\w+)\s*\(([^)]*)\)\s*;", txt):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args:
+            for a in args.split(","):
+                a = a.strip()
+                if "*" in a:
+                    argtypes.append(ctypes.POINTER(ConvGeom) if "ConvGeom" in a else ctypes.c_void_p)
+                else:
+                    ty = a.rsplit(" ", 1)[0].replace("const ", "").strip()
+                    argtypes.append(_CT[ty])
+        protos[name] = (ctypes.c_char_p if ret.startswith("const char") else ctypes.c_int, argtypes)
+    return protos
+
+
+class VcaError(RuntimeError):
+    pass
+
+
+class _Lib:
+    def __init__(self):
+        if not os.path.exists(LIB_PATH):
+            raise VcaError(f"{LIB_PATH} is missing -- build it with `python visual-context-attentional-gan_b200/build.py` "
+                           "(there is no CPU or torch fallback)")
+        self.cdll = ctypes.CDLL(LIB_PATH)
+        self.protos = parse_header()
+        self.launches = 0
+        for name, (res, args) in self.protos.items():
+            fn = getattr(self.cdll, name)
+            fn.restype, fn.argtypes = res, args
+
+    def call(self, name, *args):
+        fn = getattr(self.cdll, name)
+        conv = []
+        for a in args:
+            if isinstance(a, torch.Tensor):
+                conv.append(ctypes.c_void_p(a.data_ptr()))
+            elif isinstance(a, ConvGeom):
+                conv.append(ctypes.byref(a))
+            else:
+                conv.append(a)
+        conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        rc = fn(*conv)
+        self.launches += 1
+        if rc != 0:
+            raise VcaError(f"{name} failed ({rc}): {self.cdll.vca_last_error().decode()}")
+
+    def query(self, name, *args):
+        fn = getattr(self.cdll, name)
+        return fn(*[ctypes.byref(a) if isinstance(a, ConvGeom) else a for a in args])
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = _Lib()
+    return _lib

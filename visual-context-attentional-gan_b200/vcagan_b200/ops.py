@@ -1,0 +1,883 @@
+"""Autograd operators over the C ABI of libvcagan_b200.so.
+
+Every op is a torch.autograd.Function whose forward AND backward are calls into the hand-written CUDA library
+(see include/vcagan.h).  Ops on the discriminator path (conv / LeakyReLU / avg-pool / scale-add / spatial mean /
+linear) express their backward through other differentiable ops of this file, so
+``torch.autograd.grad(..., create_graph=True)`` (the R1 penalty of train.py:188-194) works to any order.
+
+Internal activation layout is channels-last: (N, H, W, C) or (N, D, H, W, C), contiguous, fp32 or bf16.
+torch is used for memory, streams, views/permutes/cat (data movement) only.
+"""
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from ._lib import ConvGeom, lib
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_LRELU, ACT_PRELU, ACT_RELU = 0, 1, 2, 3
+
+
+class Config:
+    """compute dtype of the activations ('fp32' = exact SIMT path, 'bf16' = tcgen05 path) and switches."""
+    dtype = torch.float32
+    use_tc = True          # use the tcgen05 kernels when dtype is bf16 and the geometry is supported
+    skip_unneeded_wgrad = True
+
+
+cfg = Config()
+
+
+def set_precision(p: str):
+    cfg.dtype = {"fp32": torch.float32, "bf16": torch.bfloat16}[p]
+
+
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported dtype {t.dtype}")
+
+
+def _c(t: torch.Tensor) -> torch.Tensor:
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _needed(ctx, i: int) -> bool:
+    """True when the engine will actually consume the gradient of input i in this backward pass."""
+    if not ctx.needs_input_grad[i]:
+        return False
+    if not cfg.skip_unneeded_wgrad:
+        return True
+    fn = ctx.next_functions[i][0]
+    if fn is None:
+        return False
+    try:
+        return bool(torch._C._will_engine_execute_node(fn))
+    except RuntimeError:
+        return True
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("vcagan_b200 ops need CUDA tensors: there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------------------
+_pack_cache = {}
+
+
+def _packed(w: torch.Tensor, dtype: torch.dtype):
+    """(wf [taps][Cin][Cout], wd [taps][Cout][Cin]) in `dtype`, cached per parameter version."""
+    base = w._base if w._base is not None else w
+    cacheable = isinstance(base, torch.nn.Parameter)
+    key = (w.data_ptr(), tuple(w.shape), dtype)
+    if cacheable:
+        hit = _pack_cache.get(key)
+        if hit is not None and hit[0] == base._version:
+            return hit[1], hit[2]
+    wc = _c(w.detach())
+    if wc.dtype != torch.float32:
+        wc = wc.float()
+    cout, cin = wc.shape[0], wc.shape[1]
+    taps = wc.numel() // (cout * cin)
+    wf = torch.empty((taps, cin, cout), dtype=dtype, device=w.device)
+    wd = torch.empty((taps, cout, cin), dtype=dtype, device=w.device)
+    lib().call("vca_pack_conv_weight", BF16 if dtype == torch.bfloat16 else F32, wc, wf, wd, cout, cin, taps)
+    if cacheable:
+        _pack_cache[key] = (base._version, wf, wd)
+    return wf, wd
+
+
+def clear_pack_cache():
+    _pack_cache.clear()
+
+
+def _geom(xshape, wshape, stride, pad) -> Tuple[ConvGeom, tuple]:
+    """xshape: (N,[D],H,W,Cin) channels-last; wshape (Cout,Cin,[KD],KH,KW) (param layout)."""
+    if len(xshape) == 4:
+        N, IH, IW, Cin = xshape; ID = 1
+    else:
+        N, ID, IH, IW, Cin = xshape
+    Cout = wshape[0]
+    ks = tuple(wshape[2:])
+    if len(ks) == 1:
+        ks = (1, 1, ks[0])
+    elif len(ks) == 2:
+        ks = (1,) + ks
+    st = (1,) * (3 - len(stride)) + tuple(stride)
+    pd = (0,) * (3 - len(pad)) + tuple(pad)
+    assert wshape[1] == Cin, (wshape, xshape)
+    OD = (ID + 2 * pd[0] - ks[0]) // st[0] + 1
+    OH = (IH + 2 * pd[1] - ks[1]) // st[1] + 1
+    OW = (IW + 2 * pd[2] - ks[2]) // st[2] + 1
+    g = ConvGeom(N, ID, IH, IW, Cin, OD, OH, OW, Cout, ks[0], ks[1], ks[2], st[0], st[1], st[2], pd[0], pd[1], pd[2])
+    oshape = (N, OH, OW, Cout) if len(xshape) == 4 else (N, OD, OH, OW, Cout)
+    return g, oshape
+
+
+def _tc_ok(g: ConvGeom, kind: int, dtype) -> bool:
+    return cfg.use_tc and dtype == torch.bfloat16 and lib().query("vca_conv_tc_supported", g, kind) == 1
+
+
+def _conv_fwd_raw(x, w, bias, stride, pad):
+    g, oshape = _geom(x.shape, w.shape, stride, pad)
+    wf, wd = _packed(w, x.dtype)
+    y = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    b = None if bias is None else _c(bias.detach().float())
+    if _tc_ok(g, 0, x.dtype):
+        lib().call("vca_conv_fwd_tc", g, x, wd, b, y)
+    else:
+        lib().call("vca_conv_fwd_simt", _dt(x), g, x, wf, b, y)
+    return y
+
+
+def _conv_dgrad_raw(dy, w, stride, pad, xshape):
+    g, oshape = _geom(xshape, w.shape, stride, pad)
+    assert tuple(dy.shape) == tuple(oshape), (dy.shape, oshape)
+    wf, wd = _packed(w, dy.dtype)
+    dx = torch.empty(xshape, dtype=dy.dtype, device=dy.device)
+    if _tc_ok(g, 1, dy.dtype):
+        lib().call("vca_conv_dgrad_tc", g, dy, wf, dx)
+    else:
+        lib().call("vca_conv_dgrad_simt", _dt(dy), g, dy, wd, dx)
+    return dx
+
+
+def _conv_wgrad_raw(x, dy, stride, pad, wshape):
+    g, oshape = _geom(x.shape, wshape, stride, pad)
+    assert tuple(dy.shape) == tuple(oshape), (dy.shape, oshape)
+    dw = torch.zeros(wshape, dtype=torch.float32, device=x.device)
+    if _tc_ok(g, 2, x.dtype):
+        lib().call("vca_conv_wgrad_tc", g, dy, x, dw)
+    else:
+        lib().call("vca_conv_wgrad_simt", _dt(x), g, dy, x, dw)
+    return dw
+
+
+class ConvFn(Function):
+    """y = conv(x, w) + bias on channels-last x; w/bias are fp32 parameters in the reference layout."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, pad):
+        _require_cuda(x, w)
+        x = _c(x)
+        ctx.save_for_backward(x, w)
+        ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
+        return _conv_fwd_raw(x, w, bias, stride, pad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = _c(dy)
+        dx = dw = db = None
+        if _needed(ctx, 0):
+            dx = ConvDgradFn.apply(dy, w, ctx.stride, ctx.pad, tuple(x.shape))
+        if _needed(ctx, 1):
+            dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
+        if ctx.has_bias and _needed(ctx, 2):
+            db = ColSumFn.apply(dy)
+        return dx, dw, db, None, None
+
+
+class ConvDgradFn(Function):
+    """dx = conv_transpose(dy, w); linear in both arguments."""
+
+    @staticmethod
+    def forward(ctx, dy, w, stride, pad, xshape):
+        dy = _c(dy)
+        ctx.save_for_backward(dy, w)
+        ctx.stride, ctx.pad, ctx.xshape = stride, pad, xshape
+        return _conv_dgrad_raw(dy, w, stride, pad, xshape)
+
+    @staticmethod
+    def backward(ctx, ggx):
+        dy, w = ctx.saved_tensors
+        ggx = _c(ggx)
+        g_dy = g_w = None
+        if _needed(ctx, 0):
+            g_dy = ConvFn.apply(ggx, w, None, ctx.stride, ctx.pad)
+        if _needed(ctx, 1):
+            g_w = ConvWgradFn.apply(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape))
+        return g_dy, g_w, None, None, None
+
+
+class ConvWgradFn(Function):
+    """dw[co,ci,tap] = sum_pixels dy * shifted x (fp32, parameter layout); linear in both arguments."""
+
+    @staticmethod
+    def forward(ctx, x, dy, stride, pad, wshape):
+        x, dy = _c(x), _c(dy)
+        ctx.save_for_backward(x, dy)
+        ctx.stride, ctx.pad, ctx.wshape = stride, pad, wshape
+        return _conv_wgrad_raw(x, dy, stride, pad, wshape)
+
+    @staticmethod
+    def backward(ctx, ggw):
+        x, dy = ctx.saved_tensors
+        g_x = g_dy = None
+        if _needed(ctx, 0):
+            g_x = ConvDgradFn.apply(dy, ggw, ctx.stride, ctx.pad, tuple(x.shape))
+        if _needed(ctx, 1):
+            g_dy = ConvFn.apply(x, ggw, None, ctx.stride, ctx.pad)
+        return g_x, g_dy, None, None, None
+
+
+class ColSumFn(Function):
+    """fp32 per-channel sum over all leading dims (bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        ctx.xshape, ctx.xdtype = tuple(x.shape), x.dtype
+        C = x.shape[-1]
+        out = torch.empty(C, dtype=torch.float32, device=x.device)
+        lib().call("vca_colsum", _dt(x), x, x.numel() // C, C, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        rows = 1
+        for s in ctx.xshape[:-1]:
+            rows *= s
+        return SpatialBcastFn.apply(g.to(ctx.xdtype).view(1, -1), rows, 1.0).view(ctx.xshape)
+
+
+def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
+    return ConvFn.apply(x, w, bias, tuple(stride), tuple(pad))
+
+
+def linear(x, w, bias=None):
+    """x (..., K) -> (..., N) with w (N, K) (nn.Linear); runs as a 1x1 convolution over rows."""
+    lead = x.shape[:-1]
+    x4 = x.reshape(-1, 1, 1, x.shape[-1])
+    y = ConvFn.apply(x4, w.view(w.shape[0], w.shape[1], 1, 1), bias, (1, 1), (0, 0))
+    return y.view(*lead, w.shape[0])
+
+
+# ------------------------------------------------------------------------------------------------------------
+# BatchNorm (+residual) + activation
+# ------------------------------------------------------------------------------------------------------------
+class BNActFn(Function):
+    """y = act(BN(x) [+ res]).  Training mode uses batch statistics over all leading dims and updates the running
+    buffers in place (momentum 0.1, unbiased variance), eval mode uses the running statistics."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, prelu_w, training, act, slope, eps, momentum):
+        _require_cuda(x)
+        x = _c(x)
+        res = None if res is None else _c(res)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dev = x.device
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        if training:
+            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
+            lib().call("vca_bn_stats", _dt(x), x, R, C, eps, momentum, sums, mean, invstd, running_mean, running_var)
+        else:
+            lib().call("vca_bn_eval_stats", running_mean, running_var, C, eps, mean, invstd)
+        y = torch.empty_like(x)
+        g32, b32 = gamma.detach(), beta.detach()
+        pw = None if prelu_w is None else prelu_w.detach()
+        lib().call("vca_bn_act_fwd", _dt(x), x, res, y, R, C, mean, invstd, g32, b32, act, slope, pw)
+        ctx.save_for_backward(x, res, gamma, beta, prelu_w, mean, invstd)
+        ctx.cfg = (training, act, slope)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, res, gamma, beta, prelu_w, mean, invstd = ctx.saved_tensors
+        training, act, slope = ctx.cfg
+        dy = _c(dy)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dev = x.device
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if res is not None else None
+        sums = torch.empty(3 * C, dtype=torch.float64, device=dev)
+        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+        dprelu = torch.empty(C, dtype=torch.float32, device=dev) if prelu_w is not None else None
+        lib().call("vca_bn_act_bwd", _dt(x), dy, x, res, dx, dres, R, C, mean, invstd, gamma.detach(), beta.detach(), act, slope,
+                   None if prelu_w is None else prelu_w.detach(), 1 if training else 0, sums, dgamma, dbeta, dprelu)
+        return dx, dres, dgamma, dbeta, None, None, dprelu, None, None, None, None, None
+
+
+def bn_act(x, bn: torch.nn.Module, act=ACT_NONE, slope=0.0, prelu_w=None, res=None):
+    """`bn` is any module holding weight/bias/running_mean/running_var/num_batches_tracked/eps/momentum/training."""
+    training = bn.training
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return BNActFn.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu_w, training, act, float(slope),
+                         float(bn.eps), float(bn.momentum))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# element-wise (double-differentiable where the discriminator path needs it)
+# ------------------------------------------------------------------------------------------------------------
+class LReluFn(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        x = _c(x)
+        ctx.save_for_backward(x)
+        ctx.slope = slope
+        y = torch.empty_like(x)
+        lib().call("vca_lrelu_fwd", _dt(x), x, y, x.numel(), slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return LReluBwdFn.apply(dy, x, ctx.slope), None
+
+
+class LReluBwdFn(Function):
+    """dx = dy * (x > 0 ? 1 : slope): linear in dy, zero derivative in x almost everywhere."""
+
+    @staticmethod
+    def forward(ctx, dy, x, slope):
+        dy = _c(dy)
+        ctx.save_for_backward(x)
+        ctx.slope = slope
+        dx = torch.empty_like(dy)
+        lib().call("vca_lrelu_bwd", _dt(dy), dy, x, dx, dy.numel(), slope)
+        return dx
+
+    @staticmethod
+    def backward(ctx, gg):
+        (x,) = ctx.saved_tensors
+        return LReluBwdFn.apply(gg, x, ctx.slope), None, None
+
+
+def lrelu(x, slope=0.2):
+    return LReluFn.apply(x, float(slope))
+
+
+class TanhFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        y = torch.empty_like(x)
+        lib().call("vca_tanh_fwd", _dt(x), x, y, x.numel())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(dy)
+        lib().call("vca_tanh_bwd", _dt(dy), dy, y, dx, dy.numel())
+        return dx
+
+
+def tanh(x):
+    return TanhFn.apply(x)
+
+
+class AxpbyFn(Function):
+    """out = alpha*a + beta*b  (b optional)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        a = _c(a)
+        b = None if b is None else _c(b)
+        ctx.alpha, ctx.beta, ctx.has_b = alpha, beta, b is not None
+        out = torch.empty_like(a)
+        lib().call("vca_axpby", _dt(a), a, b, out, a.numel(), alpha, beta)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        ga = AxpbyFn.apply(g, None, ctx.alpha, 0.0) if ctx.needs_input_grad[0] else None
+        gb = AxpbyFn.apply(g, None, ctx.beta, 0.0) if (ctx.has_b and ctx.needs_input_grad[1]) else None
+        return ga, gb, None, None
+
+
+def add_scale(a, b, s):
+    return AxpbyFn.apply(a, b, float(s), float(s))
+
+
+def scale(a, s):
+    return AxpbyFn.apply(a, None, float(s), 0.0)
+
+
+class CastFn(Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = _c(x)
+        ctx.src = x.dtype
+        if x.dtype == dtype:
+            return x
+        y = torch.empty(x.shape, dtype=dtype, device=x.device)
+        lib().call("vca_cast", _dt(x), BF16 if dtype == torch.bfloat16 else F32, x, y, x.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return CastFn.apply(g, ctx.src), None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else CastFn.apply(x, dtype)
+
+
+class MulFn(Function):
+    """y = x * mask (mask is a constant: dropout)."""
+
+    @staticmethod
+    def forward(ctx, x, mask):
+        x = _c(x)
+        ctx.save_for_backward(mask)
+        y = torch.empty_like(x)
+        lib().call("vca_mul", _dt(x), x, mask, y, x.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        (mask,) = ctx.saved_tensors
+        return MulFn.apply(g, mask), None
+
+
+_rng_state = {"seed": 0x5EED, "offset": 0}
+
+
+def manual_seed(seed: int):
+    _rng_state["seed"], _rng_state["offset"] = int(seed), 0
+
+
+def _rng(shape, dtype, device, mode, param=0.0):
+    out = torch.empty(shape, dtype=dtype, device=device)
+    n = out.numel()
+    lib().call("vca_rng", BF16 if dtype == torch.bfloat16 else F32, out, n, _rng_state["seed"], _rng_state["offset"], mode, float(param))
+    _rng_state["offset"] += (n + 3) // 4
+    return out
+
+
+def randn(shape, dtype, device):
+    """Device-side Philox N(0,1) (replaces the host torch.randn + H2D of generator.py:248)."""
+    return _rng(shape, dtype, device, 0)
+
+
+def dropout(x, p: float, training: bool, mask: Optional[torch.Tensor] = None):
+    """nn.Dropout semantics; `mask` (already scaled by 1/(1-p)) may be injected for parity tests."""
+    if mask is None:
+        if not training or p <= 0.0:
+            return x
+        mask = _rng(x.shape, x.dtype, x.device, 1, p)
+    return MulFn.apply(x, _c(mask.to(x.dtype)))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# pooling / resampling
+# ------------------------------------------------------------------------------------------------------------
+class Pool2x2Fn(Function):
+    """(N,H,W,C) -> (N,H//2,W//2,C): scale * 2x2 block sums (scale 0.25 = F.avg_pool2d(x, 2))."""
+
+    @staticmethod
+    def forward(ctx, x, scale_):
+        x = _c(x)
+        N, H, W, C = x.shape
+        ctx.hw, ctx.scale = (H, W), scale_
+        y = torch.empty((N, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+        lib().call("vca_pool2x2_sum", _dt(x), x, y, N, H, W, C, scale_)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return Expand2x2Fn.apply(g, ctx.hw, ctx.scale), None
+
+
+class Expand2x2Fn(Function):
+    """(N,h,w,C) -> (N,H,W,C) with y[i,j] = scale * x[i//2, j//2] (zero on an odd trailing row/col).
+    scale 1 with (H,W) = (2h,2w) is F.interpolate(scale_factor=2, mode='nearest')."""
+
+    @staticmethod
+    def forward(ctx, x, hw, scale_):
+        x = _c(x)
+        N, h, w, C = x.shape
+        H, W = hw
+        ctx.scale = scale_
+        y = torch.empty((N, H, W, C), dtype=x.dtype, device=x.device)
+        lib().call("vca_expand2x2", _dt(x), x, y, N, h, w, C, H, W, scale_)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return Pool2x2Fn.apply(g, ctx.scale), None, None
+
+
+def avg_pool2(x):
+    return Pool2x2Fn.apply(x, 0.25)
+
+
+def upsample2(x):
+    return Expand2x2Fn.apply(x, (2 * x.shape[1], 2 * x.shape[2]), 1.0)
+
+
+class MaxPool3x3s2Fn(Function):
+    """Per-frame 3x3/stride 2/pad 1 max pool on (NF,H,W,C)  (MaxPool3d((1,3,3),(1,2,2),(0,1,1)), visual_front.py:14)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        NF, H, W, C = x.shape
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((NF, OH, OW, C), dtype=x.dtype, device=x.device)
+        idx = torch.empty((NF, OH, OW, C), dtype=torch.uint8, device=x.device)
+        lib().call("vca_maxpool3x3s2_fwd", _dt(x), x, y, idx, NF, H, W, C)
+        ctx.save_for_backward(idx)
+        ctx.xshape = (NF, H, W, C)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        NF, H, W, C = ctx.xshape
+        dy = _c(dy)
+        dx = torch.empty(ctx.xshape, dtype=dy.dtype, device=dy.device)
+        lib().call("vca_maxpool3x3s2_bwd", _dt(dy), dy, idx, dx, NF, H, W, C)
+        return dx
+
+
+def maxpool3x3s2(x):
+    return MaxPool3x3s2Fn.apply(x)
+
+
+class SpatialSumFn(Function):
+    """(N,P,C) -> (N,C): scale * sum over P."""
+
+    @staticmethod
+    def forward(ctx, x, scale_):
+        x = _c(x)
+        N, P, C = x.shape
+        ctx.P, ctx.scale = P, scale_
+        y = torch.empty((N, C), dtype=x.dtype, device=x.device)
+        lib().call("vca_spatial_sum", _dt(x), x, y, N, P, C, scale_)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return SpatialBcastFn.apply(g, ctx.P, ctx.scale), None
+
+
+class SpatialBcastFn(Function):
+    """(N,C) -> (N,P,C): scale * x broadcast over P."""
+
+    @staticmethod
+    def forward(ctx, x, P, scale_):
+        x = _c(x)
+        N, C = x.shape
+        ctx.scale = scale_
+        y = torch.empty((N, P, C), dtype=x.dtype, device=x.device)
+        lib().call("vca_spatial_bcast", _dt(x), x, y, N, P, C, scale_)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return SpatialSumFn.apply(g, ctx.scale), None, None
+
+
+def spatial_mean(x):
+    """(N,H,W,C) -> (N,C) mean over H,W  (Avgpool of generator.py:137-140, AvgPool2d(4) of resnet.py:82)."""
+    N, C = x.shape[0], x.shape[-1]
+    P = x.numel() // (N * C)
+    return SpatialSumFn.apply(x.reshape(N, P, C), 1.0 / P)
+
+
+def spatial_tile(x, P):
+    """(N,C) -> (N,P,C)."""
+    return SpatialBcastFn.apply(x, P, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# batched GEMM, softmax, losses (fp32)
+# ------------------------------------------------------------------------------------------------------------
+def _gemm_raw(A, B, C, bias=None, alpha=1.0, beta=0.0):
+    """C[z] = alpha*A[z]@B[z] + bias + beta*C[z]; A (Z,M,K), B (Z,K,N), C (Z,M,N) arbitrary-stride views
+    (2-D inputs are treated as Z = 1; a Z-stride of 0 broadcasts)."""
+    if A.dim() == 2:
+        A, B, C = A.unsqueeze(0), B.unsqueeze(0), C.unsqueeze(0)
+    Z, M, K = A.shape
+    N = B.shape[2]
+    assert B.shape[1] == K and C.shape[1] == M and C.shape[2] == N, (A.shape, B.shape, C.shape)
+    sa, sb, sc = A.stride(), B.stride(), C.stride()
+    lib().call("vca_gemm_simt", _dt(A), _dt(B), _dt(C), A, B, C, bias, Z, M, N, K, sa[0] if A.shape[0] > 1 else 0, sa[1], sa[2],
+               sb[0] if B.shape[0] > 1 else 0, sb[1], sb[2], sc[0], sc[1], sc[2], float(alpha), float(beta))
+    return C
+
+
+class BmmFn(Function):
+    """out = alpha * a @ b for a (Z,M,K), b (Z,K,N) (views with any strides are fine)."""
+
+    @staticmethod
+    def forward(ctx, a, b, alpha):
+        ctx.save_for_backward(a, b)
+        ctx.alpha = alpha
+        out = torch.empty((a.shape[0], a.shape[1], b.shape[2]), dtype=a.dtype, device=a.device)
+        return _gemm_raw(a, b, out, None, alpha, 0.0)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        ga = BmmFn.apply(g, b.transpose(1, 2), ctx.alpha) if ctx.needs_input_grad[0] else None
+        gb = BmmFn.apply(a.transpose(1, 2), g, ctx.alpha) if ctx.needs_input_grad[1] else None
+        return ga, gb, None
+
+
+def bmm(a, b, alpha=1.0):
+    return BmmFn.apply(a, b, float(alpha))
+
+
+class MaskedSoftmaxFn(Function):
+    """softmax over the last dim of (Z,R,S) with keys >= lens[z] masked out (generator.py:161-164)."""
+
+    @staticmethod
+    def forward(ctx, x, lens):
+        x = _c(x)
+        Z, R, S = x.shape
+        p = torch.empty_like(x)
+        lib().call("vca_masked_softmax_fwd", x, p, lens, Z, R, S)
+        ctx.save_for_backward(p)
+        return p
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dp):
+        (p,) = ctx.saved_tensors
+        dp = _c(dp)
+        dx = torch.empty_like(p)
+        lib().call("vca_softmax_bwd", dp, p, dx, p.shape[0] * p.shape[1], p.shape[2])
+        return dx, None
+
+
+def masked_softmax(x, lens):
+    return MaskedSoftmaxFn.apply(x, lens)
+
+
+class L2NormFn(Function):
+    """F.normalize(x, dim=-1) (eps 1e-12)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        D = x.shape[-1]
+        rows = x.numel() // D
+        y = torch.empty_like(x)
+        norms = torch.empty(rows, dtype=torch.float32, device=x.device)
+        lib().call("vca_l2norm_fwd", x, y, norms, rows, D, 1e-12)
+        ctx.save_for_backward(y, norms)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        y, norms = ctx.saved_tensors
+        dy = _c(dy)
+        dx = torch.empty_like(y)
+        lib().call("vca_l2norm_bwd", dy, y, norms, dx, norms.numel(), y.shape[-1], 1e-12)
+        return dx
+
+
+class NceDiagFn(Function):
+    """(B,S,S) similarities -> (B,) symmetric InfoNCE of generator.py:354-359."""
+
+    @staticmethod
+    def forward(ctx, sim):
+        sim = _c(sim)
+        B, S, _ = sim.shape
+        loss = torch.empty(B, dtype=torch.float32, device=sim.device)
+        dsim = torch.empty_like(sim)
+        lib().call("vca_nce_diag", sim, loss, dsim, B, S)
+        ctx.save_for_backward(dsim)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dsim,) = ctx.saved_tensors
+        return dsim * g.view(-1, 1, 1)
+
+
+class CosAbsMeanFn(Function):
+    """(B,S,D) x (B,S,D) -> (B,): 5 - mean_t |cos(v_t, a_t)|  (generator.py:347-349)."""
+
+    @staticmethod
+    def forward(ctx, v, a):
+        v, a = _c(v), _c(a)
+        B, S, D = v.shape
+        loss = torch.empty(B, dtype=torch.float32, device=v.device)
+        saved = torch.empty((B, S, 3), dtype=torch.float32, device=v.device)
+        lib().call("vca_cos_abs_mean_fwd", v, a, loss, saved, B, S, D)
+        ctx.save_for_backward(v, a, saved)
+        return loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        v, a, saved = ctx.saved_tensors
+        B, S, D = v.shape
+        g = _c(g)
+        dv = torch.empty_like(v) if ctx.needs_input_grad[0] else None
+        da = torch.empty_like(a) if ctx.needs_input_grad[1] else None
+        if dv is None and da is None:
+            return None, None
+        lib().call("vca_cos_abs_mean_bwd", g, v, a, saved, da, dv, B, S, D)
+        return dv, da
+
+
+class SoftplusMeanFn(Function):
+    """mean(softplus(sign * x)) -> scalar  (gan_loss, generator.py:363-366)."""
+
+    @staticmethod
+    def forward(ctx, x, sign):
+        x = _c(x)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        lib().call("vca_softplus_mean", x, out, dx, x.numel(), sign)
+        ctx.save_for_backward(dx)
+        return out.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        (dx,) = ctx.saved_tensors
+        return dx * g, None
+
+
+class L1MeanFn(Function):
+    """scale * mean|a - b| (nn.L1Loss, train.py:150,226-229); gradient flows to a only."""
+
+    @staticmethod
+    def forward(ctx, a, b, scale_):
+        a, b = _c(a), _c(b)
+        out = torch.empty(1, dtype=torch.float32, device=a.device)
+        s = scale_ / a.numel()
+        lib().call("vca_reduce_l1_sq", _dt(a), a, b, a.numel(), s, 0, out)
+        ctx.save_for_backward(a, b)
+        ctx.s = s
+        return out.view(())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        da = torch.empty_like(a)
+        lib().call("vca_l1_bwd", _dt(a), a, b, _c(g.float().view(1)), a.numel(), ctx.s, da)
+        return da, None, None
+
+
+def l1_mean(a, b, scale_=1.0):
+    return L1MeanFn.apply(a, b.detach(), float(scale_))
+
+
+class SumSqFn(Function):
+    """scale * sum(x^2) -> scalar; backward 2*scale*x*g (differentiable: it is AxpbyFn)."""
+
+    @staticmethod
+    def forward(ctx, x, scale_):
+        x = _c(x)
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+        lib().call("vca_reduce_l1_sq", _dt(x), x, None, x.numel(), scale_, 1, out)
+        ctx.save_for_backward(x)
+        ctx.scale = scale_
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return scale(x, 2.0 * ctx.scale) * g.to(x.dtype), None
+
+
+def sum_sq(x, scale_=1.0):
+    return SumSqFn.apply(x, float(scale_))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GRU layer (bidirectional), fp32
+# ------------------------------------------------------------------------------------------------------------
+class GRULayerFn(Function):
+    """One bidirectional GRU layer: x (T,B,I) -> (T,B,2H).  Gate order r,z,n, b_hn inside the r-product
+    (torch.nn.GRU semantics, visual_front.py:20).  Weights: (w_ih, w_hh, b_ih, b_hh) for forward then reverse."""
+
+    @staticmethod
+    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
+        _require_cuda(x)
+        x = _c(x.float())
+        T, B, I = x.shape
+        H = w_hh_f.shape[1]
+        dev = x.device
+        gi = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
+        x2 = x.view(T * B, I)
+        for d, (w, b) in enumerate(((w_ih_f, b_ih_f), (w_ih_r, b_ih_r))):
+            _gemm_raw(x2, w.detach().t(), gi[d].view(T * B, 3 * H), b.detach())
+        whh = torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0)   # (2,3H,H)
+        bhh = torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0)   # (2,3H)
+        out = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
+        gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev)
+        h = torch.zeros((2, 2, B, H), dtype=torch.float32, device=dev)  # ping-pong
+        gh = torch.empty((2, B, 3 * H), dtype=torch.float32, device=dev)
+        whh_t = whh.transpose(1, 2)  # (2,H,3H) view
+        for s in range(T):
+            hp, hn = h[s & 1], h[(s + 1) & 1]
+            _gemm_raw(hp, whh_t, gh)
+            lib().call("vca_gru_gate_fwd", gi, gh, bhh, hp, hn, out, gates, 2, T, B, H, s)
+        ctx.save_for_backward(x, w_ih_f, w_ih_r, whh, out, gates)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        x, w_ih_f, w_ih_r, whh, out, gates = ctx.saved_tensors
+        dout = _c(dout.float())
+        T, B, I = x.shape
+        H = whh.shape[2]
+        dev = x.device
+        dgi = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
+        dgh = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
+        dh = torch.zeros((2, B, H), dtype=torch.float32, device=dev)
+        for s in range(T):
+            lib().call("vca_gru_gate_bwd", dout, dh, gates, out, dgi, dgh, 2, T, B, H, s)
+            # dh += dgh[:, t_d] @ W_hh   (direction 0 is at t = T-1-s, direction 1 at t = s)
+            row = B * 3 * H
+            cur = dgh.as_strided((2, B, 3 * H), ((2 * s + 1) * row, 3 * H, 1), (T - 1 - s) * row)
+            _gemm_raw(cur, whh, dh, None, 1.0, 1.0)
+        x2 = x.view(T * B, I)
+        grads = []
+        dx = torch.empty((T * B, I), dtype=torch.float32, device=dev)
+        for d, w_ih in enumerate((w_ih_f, w_ih_r)):
+            dgi_d = dgi[d].view(T * B, 3 * H)
+            dw_ih = torch.empty((3 * H, I), dtype=torch.float32, device=dev)
+            _gemm_raw(dgi_d.t(), x2, dw_ih)
+            db_ih = ColSumFn.apply(dgi_d)
+            # h_{t-1} of direction 0 is out[t-1,:, :H]; of direction 1 it is out[t+1,:, H:]
+            dw_hh = torch.empty((3 * H, H), dtype=torch.float32, device=dev)
+            if T > 1:
+                if d == 0:
+                    a = dgh[0, 1:].reshape((T - 1) * B, 3 * H)
+                    hprev = out[:T - 1, :, :H].reshape((T - 1) * B, H)
+                else:
+                    a = dgh[1, :T - 1].reshape((T - 1) * B, 3 * H)
+                    hprev = out[1:, :, H:].reshape((T - 1) * B, H)
+                _gemm_raw(a.t(), hprev, dw_hh)
+            else:
+                dw_hh.zero_()
+            db_hh = ColSumFn.apply(dgh[d].view(T * B, 3 * H))
+            _gemm_raw(dgi_d, w_ih.detach(), dx, None, 1.0, 0.0 if d == 0 else 1.0)
+            grads += [dw_ih, dw_hh, db_ih, db_hh]
+        return (dx.view(T, B, I), *grads)
+
+
+def gru_layer(x, params):
+    return GRULayerFn.apply(x, *params)
