@@ -1,0 +1,93 @@
+"""Step-level parity: one full G+D step (train.py:166-237) of the B200-native trainer against the golden vectors the
+unmodified reference produced for the same weights / inputs / injected noise (tests/golden/make_golden.py):
+losses, generated mels, every parameter-gradient norm after each backward, and post-Adam parameter checksums."""
+import json
+import os
+import pytest
+import torch
+
+from conftest import make_state, golden_inputs, rel_l2, GOLD
+from oracle import vca_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(precision):
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    state = {m: make_state(spec, m) for m in O.MODULES}
+    tr = Trainer(precision=precision, state=state, dropout=False)
+    vid, mel, sp, noise = golden_inputs()
+    out = tr.step(vid.cuda(), mel.cuda(), sp.cuda(), [20, 13], noise=noise)
+    torch.cuda.synchronize()
+    return V, tr, out
+
+
+def test_step_fp32_matches_reference(golden):
+    V, tr, out = _run("fp32")
+    try:
+        for k in ("dis_loss", "sync_loss", "real_loss", "fake_loss", "gen_loss", "g_sync", "recon"):
+            ref, got = float(golden["step_" + k]), float(out[k])
+            assert abs(got - ref) <= 1e-4 * max(1.0, abs(ref)), (k, got, ref)
+        assert rel_l2(out["grad_pen"].cpu(), golden["step_grad_pen"]) < 2e-4
+        for k in ("g1", "g2", "g3", "gs"):
+            assert rel_l2(out[k].cpu(), golden["step_" + k]) < 1e-4, k
+        print("mel L1 vs reference (fp32):", float((out["g3"].cpu() - torch.from_numpy(golden["step_g3"])).abs().mean()))
+        names = json.load(open(os.path.join(GOLD, "grad_norm_names.json")))
+        pd = {f"{k}.{n}": p for k, m in tr.mods.items() for n, p in m.named_parameters()}
+        dn = torch.tensor([float(pd[n].grad.norm()) for n in names["d"]])
+        assert rel_l2(dn, golden["step_d_grad_norms"]) < 3e-4
+        gn = torch.tensor([float(pd[n].grad.norm()) for n in names["g"]])
+        assert rel_l2(gn, golden["step_g_grad_norms"]) < 3e-4
+        bad = [(n, float(a), float(b)) for n, a, b in zip(names["g"], gn, torch.from_numpy(golden["step_g_grad_norms"]))
+               if abs(a - b) > 2e-3 * max(float(b), 1e-4)]
+        assert not bad, bad[:8]
+        cn = json.load(open(os.path.join(GOLD, "checksum_names.json")))
+        chk = torch.tensor([float(pd[n].detach().double().abs().sum()) for n in cn["params"]], dtype=torch.float64)
+        ref = torch.from_numpy(golden["step_param_checksums"])[:, 1]
+        assert float(((chk - ref).abs() / ref.abs().clamp_min(1e-9)).max()) < 1e-5
+        bd = {f"{k}.{n}": b for k, m in tr.mods.items() for n, b in m.named_buffers()}
+        bs = torch.tensor([float(bd[n].double().sum()) for n in cn["buffers"]], dtype=torch.float64)
+        assert rel_l2(bs, golden["step_buffer_sums"]) < 1e-5
+    finally:
+        V.set_precision("fp32")
+
+
+def test_step_bf16_bound(golden):
+    """bf16 storage + tcgen05 kernels.  Stated bound: scalar losses within 2e-2 relative, mels within 3e-2 relative L2."""
+    V, tr, out = _run("bf16")
+    try:
+        errs = {}
+        for k in ("dis_loss", "sync_loss", "fake_loss", "gen_loss", "g_sync", "recon"):
+            ref, got = float(golden["step_" + k]), float(out[k])
+            errs[k] = abs(got - ref) / max(1.0, abs(ref))
+        for k in ("g1", "g2", "g3", "gs"):
+            errs[k] = rel_l2(out[k].cpu(), golden["step_" + k])
+        print("bf16 step errors", errs)
+        print("mel L1 vs reference (bf16):", float((out["g3"].cpu() - torch.from_numpy(golden["step_g3"])).abs().mean()))
+        assert all(v < 3e-2 for v in errs.values()), errs
+        assert all(torch.isfinite(p).all() for m in tr.mods.values() for p in m.parameters())
+    finally:
+        V.set_precision("fp32")
+
+
+def test_second_step_runs_and_changes_weights():
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    try:
+        tr = Trainer(precision="bf16", dropout=True)
+        g = torch.Generator().manual_seed(0)
+        B, T = 2, 24
+        vid = torch.randn(B, 1, T, 112, 112, generator=g).cuda()
+        mel = (torch.rand(B, 1, 80, 4 * T, generator=g) * 2 - 1).cuda()
+        spec = torch.rand(B, 1, 321, 4 * T, generator=g).cuda()
+        w0 = tr.G.flat.clone()
+        l1 = tr.step(vid, mel, spec, [T, T - 5])
+        l2 = tr.step(vid, mel, spec, [T, T - 5])
+        torch.cuda.synchronize()
+        assert torch.isfinite(l2["gen_loss"]) and torch.isfinite(l2["dis_loss"])
+        assert float((tr.G.flat - w0).abs().max()) > 0
+        assert float(l2["recon"]) < float(l1["recon"]) + 0.5
+    finally:
+        V.set_precision("fp32")

@@ -74,10 +74,46 @@ class _Lib:
             else:
                 conv.append(a)
         conv.append(ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        prof = self._prof
+        if prof is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         rc = fn(*conv)
         self.launches += 1
         if rc != 0:
             raise VcaError(f"{name} failed ({rc}): {self.cdll.vca_last_error().decode()}")
+        if prof is not None:
+            e1.record()
+            flops, tag = 0, ""
+            for a in args:
+                if isinstance(a, ConvGeom):
+                    flops = 2 * a.N * a.OD * a.OH * a.OW * a.Cout * a.Cin * a.KD * a.KH * a.KW
+                    tag = "x".join(str(v) for v in a.key())
+            if name == "vca_gemm_simt":
+                flops = 2 * args[7] * args[8] * args[9] * args[10]
+            prof.append((name, tag, flops, e0, e1))
+
+    def profile_step(self, fn):
+        """Run fn() with every library call bracketed by CUDA events on the launching stream.
+        -> {entry point: {n, ms, flops, top: [(geometry, ms, TFLOP/s)]}}"""
+        self._prof = []
+        try:
+            fn()
+            torch.cuda.synchronize()
+            rows = [(n, t, f, a.elapsed_time(b)) for n, t, f, a, b in self._prof]
+        finally:
+            self._prof = None
+        agg = {}
+        for n, t, f, ms in rows:
+            d = agg.setdefault(n, {"n": 0, "ms": 0.0, "flops": 0, "by_geom": {}})
+            d["n"] += 1; d["ms"] += ms; d["flops"] += f
+            if t:
+                g = d["by_geom"].setdefault(t, [0, 0.0, 0])
+                g[0] += 1; g[1] += ms; g[2] += f
+        for d in agg.values():
+            top = sorted(d.pop("by_geom").items(), key=lambda kv: -kv[1][1])[:6]
+            d["top"] = [(k, v[0], round(v[1], 3), round(v[2] / max(v[1], 1e-9) / 1e9, 2)) for k, v in top]
+        return agg
 
     def query(self, name, *args):
         fn = getattr(self.cdll, name)

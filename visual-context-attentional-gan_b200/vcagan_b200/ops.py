@@ -9,6 +9,7 @@ Internal activation layout is channels-last: (N, H, W, C) or (N, D, H, W, C), co
 torch is used for memory, streams, views/permutes/cat (data movement) only.
 """
 import math
+import weakref
 from typing import Optional, Tuple
 
 import torch
@@ -80,8 +81,10 @@ def _packed(w: torch.Tensor, dtype: torch.dtype):
     cacheable = isinstance(base, torch.nn.Parameter)
     key = (w.data_ptr(), tuple(w.shape), dtype)
     if cacheable:
+        ep = getattr(base, "_vca_epoch", None)
+        tag = (base._version, ep[0] if ep is not None else 0)
         hit = _pack_cache.get(key)
-        if hit is not None and hit[0] == base._version:
+        if hit is not None and hit[0] == tag and hit[3]() is base:   # same live Parameter object, not a recycled address
             return hit[1], hit[2]
     wc = _c(w.detach())
     if wc.dtype != torch.float32:
@@ -92,7 +95,7 @@ def _packed(w: torch.Tensor, dtype: torch.dtype):
     wd = torch.empty((taps, cout, cin), dtype=dtype, device=w.device)
     lib().call("vca_pack_conv_weight", BF16 if dtype == torch.bfloat16 else F32, wc, wf, wd, cout, cin, taps)
     if cacheable:
-        _pack_cache[key] = (base._version, wf, wd)
+        _pack_cache[key] = (tag, wf, wd, weakref.ref(base))
     return wf, wd
 
 

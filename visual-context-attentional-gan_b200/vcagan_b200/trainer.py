@@ -1,0 +1,185 @@
+"""The G+D training step of the reference (train.py:166-237; LRS variant train_LRS.py:179-243) on the B200-native
+modules, with flat parameter/gradient buffers, a fused Adam(amsgrad) kernel and one-process-per-GPU data
+parallelism (sum all-reduce of the flat gradient buffers over NCCL/NVLink; BatchNorm statistics stay per replica,
+which is exactly what the reference's nn.DataParallel computes -- SURVEY.md 2.2 / 8e).
+
+Schedule kept from the reference: D phase (real + R1 on the unconditional logits with create_graph, fake on
+detached mels, sync loss with NON-detached phon so the visual front-end CNN receives its gradient), D optimizer
+step, then the G phase against the *updated* discriminators; v_front gradients of both phases are summed before
+the single G optimizer step.  Exact savings taken: D weight gradients are not
+computed in the G phase (the reference computes and discards them, train.py:235-236).
+"""
+import math
+from typing import Dict, Iterable, List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import models as M
+from . import ops
+from ._lib import lib
+
+DENORM_SCALE = -math.log(1e-5) / 2.0   # |d denormalize / d mel|, src/data/vid_aud_grid.py:238-240
+
+
+class FlatGroup:
+    """Re-homes the parameters of several modules into one flat fp32 buffer (and their .grad into another) so the
+    optimizer is one kernel launch and the data-parallel exchange is one (bucketed) all-reduce."""
+
+    def __init__(self, modules: Iterable[nn.Module]):
+        self.params: List[nn.Parameter] = [p for m in modules for p in m.parameters()]
+        self.epoch = [0]   # bumped by FusedAdam.step; part of the packed-weight cache tag (ops._packed)
+        dev = self.params[0].device
+        self.sizes = [p.numel() for p in self.params]
+        # 16-byte align every segment
+        self.offsets, off = [], 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + 3) // 4 * 4
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        for p, o, n in zip(self.params, self.offsets, self.sizes):
+            self.flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = self.flat[o:o + n].view(p.shape)
+            p.grad = self.grad[o:o + n].view(p.shape)
+            p._vca_epoch = self.epoch
+
+    def zero_grad(self):
+        self.grad.zero_()
+        for p, o, n in zip(self.params, self.offsets, self.sizes):
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + 4 * o:
+                p.grad = self.grad[o:o + n].view(p.shape)
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas=(0.9,0.999), eps=1e-8, weight_decay (coupled L2), amsgrad) as ONE CUDA kernel over
+    the flat buffer (vca_adam_step).  train.py:82-83 uses amsgrad=True, train_LRS.py:97-98 amsgrad=False."""
+
+    def __init__(self, group: FlatGroup, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, amsgrad=True):
+        self.g, self.lr, self.betas, self.eps, self.wd = group, lr, betas, eps, weight_decay
+        self.m = torch.zeros_like(group.flat)
+        self.v = torch.zeros_like(group.flat)
+        self.vmax = torch.zeros_like(group.flat) if amsgrad else None
+        self.t = 0
+
+    def zero_grad(self):
+        self.g.zero_grad()
+
+    def step(self, grad_scale: float = 1.0):
+        self.t += 1
+        lib().call("vca_adam_step", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr, self.betas[0],
+                   self.betas[1], self.eps, self.wd, self.t, grad_scale)
+        self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
+
+
+def bilinear_down(mel: torch.Tensor, factor: int) -> torch.Tensor:
+    """F.interpolate(mel, scale_factor=1/factor, mode='bilinear') for factor 2 or 4 on (B,1,H,W) (train.py:170-171):
+    align_corners=False makes it the mean of the 2x2 pixels at rows/cols {2d,2d+1} (x0.5) or {4d+1,4d+2} (x0.25)."""
+    x = mel.permute(0, 2, 3, 1)                       # channels-last view (C = 1)
+    if factor == 2:
+        y = ops.avg_pool2(x.contiguous())
+    elif factor == 4:
+        y = ops.avg_pool2(x[:, 1:, 1:, :].contiguous())[:, ::2, ::2, :]
+    else:
+        raise ValueError(factor)
+    return y.permute(0, 3, 1, 2).contiguous()
+
+
+class Trainer:
+    def __init__(self, precision="bf16", lr=1e-4, weight_decay=1e-5, lrs=False, temp=1.0, device="cuda",
+                 state: Optional[Dict[str, dict]] = None, dropout=True, process_group=None):
+        ops.set_precision(precision)
+        self.lrs = lrs
+        self.device = torch.device(device)
+        self.mods = dict(v_front=M.Visual_front(1), gen=M.Decoder(), post=M.Postnet(), dis1=M.Discriminator(phase='1'),
+                         dis2=M.Discriminator(phase='2'), dis3=M.Discriminator(phase='3'), s_dis=M.sync_Discriminator(temp))
+        if state is not None:
+            for k, m in self.mods.items():
+                m.load_state_dict(state[k])
+        for m in self.mods.values():
+            m.to(self.device).train()
+        if not dropout:
+            self.mods["v_front"].dropout.p = 0.0
+            self.mods["v_front"].sentence_encoder.dropout = 0.0
+        self.G = FlatGroup([self.mods[k] for k in ("v_front", "gen", "post")])
+        self.D = FlatGroup([self.mods[k] for k in ("dis1", "dis2", "dis3", "s_dis")])
+        self.g_opt = FusedAdam(self.G, lr, weight_decay=weight_decay, amsgrad=not lrs)
+        self.d_opt = FusedAdam(self.D, lr, weight_decay=weight_decay, amsgrad=not lrs)
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+
+    # -- data-parallel exchange ---------------------------------------------------------------------------------
+    def _allreduce(self, group: FlatGroup, bucket_elems: int = 8 << 20):
+        if self.world == 1:
+            return
+        cur = torch.cuda.current_stream()
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            for s in range(0, group.numel, bucket_elems):
+                torch.distributed.all_reduce(group.grad[s:s + bucket_elems], group=self.pg)
+        cur.wait_stream(self.comm_stream)
+
+    # -- one step -------------------------------------------------------------------------------------------------
+    def step(self, vid, mel, spec, vid_len, noise=None):
+        """vid (B,1,T,112,112), mel (B,1,80,4T), spec (B,1,321,4T) device fp32; vid_len int32 device tensor or list."""
+        m = self.mods
+        v_front, gen, post = m["v_front"], m["gen"], m["post"]
+        dis = (m["dis1"], m["dis2"], m["dis3"])
+        s_dis = m["s_dis"]
+        gen.fixed_noise = noise
+        self.G.zero_grad()                                                # train.py:168
+        mel1, mel2 = bilinear_down(mel, 4), bilinear_down(mel, 2)          # train.py:170-171
+        phon, sent = v_front(vid)
+        g = gen(sent, phon, vid_len)                                       # g1, g2, g3
+        T = phon.size(1)
+        sdet = sent.detach()
+        reals = [t.detach().requires_grad_(True) for t in (mel1, mel2, mel)]
+        # ---------------- D phase ----------------
+        ur, cr, gp = [], [], []
+        for d, x in zip(dis, reals):
+            u, c = d(x, sdet, T)
+            ur.append(u); cr.append(c)
+        sync_loss = s_dis(phon, reals[2]).mean()                           # phon NOT detached (train.py:186)
+        for u, x in zip(ur, reals):
+            gr = torch.autograd.grad(u.sum(), x, create_graph=True)[0]     # R1 (train.py:188-194)
+            gp.append(ops.sum_sq(gr, 1.0 / gr.size(0)))
+        uf, cf = [], []
+        for d, x in zip(dis, g):
+            u, c = d(x.detach(), sdet, T)
+            uf.append(u); cf.append(c)
+        real_loss = sum(M.gan_loss(x, True) for x in ur + cr) / 3 + sum(gp) / 3
+        fake_loss = sum(M.gan_loss(x, False) for x in uf + cf) / 3
+        dis_loss = real_loss + fake_loss + (0.5 if self.lrs else 1.0) * sync_loss
+        self.d_opt.zero_grad()
+        dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
+        self._allreduce(self.D)
+        self.d_opt.step(1.0 / self.world)
+        # ---------------- G phase ----------------
+        gs = post(g[2])
+        ug, cg = [], []
+        for d, x in zip(dis, g):
+            u, c = d(x, sdet, T)
+            ug.append(u); cg.append(c)
+        g_sync = s_dis(phon.detach(), g[2], True).mean()
+        g_adv = sum(M.gan_loss(x, True) for x in ug + cg) / 3
+        k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
+        recon = (ops.l1_mean(g[0], mel1, k) + ops.l1_mean(g[1], mel2, k) + ops.l1_mean(g[2], mel, k)) / 3 + ops.l1_mean(gs, spec)
+        gen_loss = g_adv + g_sync + 50.0 * recon
+        gen_loss.backward(inputs=self.G.params)                            # D weight grads skipped (discarded in ref)
+        self._allreduce(self.G)
+        self.g_opt.step(1.0 / self.world)
+        gen.fixed_noise = None
+        return dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
+                    fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp]), gen_loss=gen_loss.detach(),
+                    g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(), g2=g[1].detach(), g3=g[2].detach(),
+                    gs=gs.detach(), r1_grad3=None)
+
+    def _vf_cnn_params(self):
+        vf = self.mods["v_front"]
+        return list(vf.frontend.parameters()) + list(vf.resnet.parameters())
+
+    def state_dicts(self):
+        """checkpoint layout of train.py:303-309"""
+        return {f"{k}_state_dict": m.state_dict() for k, m in self.mods.items()}
