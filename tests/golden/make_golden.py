@@ -71,37 +71,13 @@ class FixedNoise:
     def __exit__(self, *a): torch.randn = self.orig
 
 
-def main():
-    out = {}
-    vid, mel, spec, noise = gen_inputs()
-    mods = build()
-    spec_json = {k: {n: [list(t.shape), str(t.dtype).replace("torch.", "")] for n, t in m.state_dict().items()}
-                 for k, m in mods.items()}
-    json.dump(spec_json, open(os.path.join(HERE, "state_spec.json"), "w"), indent=0, sort_keys=True)
-
-    # ---- module forwards, eval mode ----
-    for m in mods.values():
-        m.eval()
-    with torch.no_grad():
-        phon, sent = mods["v_front"](vid)
-        with FixedNoise(noise):
-            g1, g2, g3 = mods["gen"](sent, phon, LENS)
-        gs = mods["post"](g3)
-        out.update(eval_phon=phon, eval_sent=sent, eval_g1=g1, eval_g2=g2, eval_g3=g3, eval_gs=gs)
-        mel1 = torch.nn.functional.interpolate(mel, scale_factor=0.25, mode="bilinear")
-        mel2 = torch.nn.functional.interpolate(mel, scale_factor=0.5, mode="bilinear")
-        for i, (d, x) in enumerate(((mods["dis1"], mel1), (mods["dis2"], mel2), (mods["dis3"], mel)), 1):
-            u, c = d(x, sent, T)
-            out[f"eval_d{i}_u"], out[f"eval_d{i}_c"] = u, c
-        out["eval_sync_nce"] = mods["s_dis"](phon, mel)
-        out["eval_sync_cos"] = mods["s_dis"](phon, g3, True)
-    out["known_gan_loss0"] = gan_loss(torch.zeros(4, 1), True)
-    out["known_final_length"] = torch.tensor([final_length(t) for t in (40, 50, 75, 160, 250)])
-
-    # ---- one full training step exactly as train.py:166-237 (fresh modules, train mode) ----
+def ref_step(out, vid, mel, spec, noise, dtype, pre):
+    """train.py:166-237 verbatim on the reference modules (dropout off, noise injected), in `dtype`."""
     mods = build()
     for m in mods.values():
         m.train()
+        m.to(dtype)
+    vid, mel, spec, noise = (t.to(dtype) for t in (vid, mel, spec, noise))
     v_front, gen, post = mods["v_front"], mods["gen"], mods["post"]
     dis1, dis2, dis3, s_dis = mods["dis1"], mods["dis2"], mods["dis3"], mods["s_dis"]
     g_params = [{'params': v_front.parameters()}, {'params': gen.parameters()}, {'params': post.parameters()}]
@@ -160,21 +136,76 @@ def main():
     gen_loss.backward()
     g_gn = gnorms(("v_front", "gen", "post"))
     g_opt.step()
-    out.update(step_dis_loss=dis_loss, step_sync_loss=sync_loss, step_real_loss=real_loss, step_fake_loss=fake_loss,
-               step_grad_pen=torch.stack([gp1, gp2, gp3]), step_gen_loss=gen_loss, step_g_sync=g_sync, step_recon=recon,
-               step_g1=g1, step_g2=g2, step_g3=g3, step_gs=gs, step_phon=phon, step_sent=sent,
-               step_r1_grad3=gr3, step_r1_grad1=gr1)
-    names = sorted(d_gn); out["step_d_grad_norms"] = torch.tensor([d_gn[n] for n in names])
-    names_v = sorted(vf_d_gn); out["step_vf_d_grad_norms"] = torch.tensor([vf_d_gn[n] for n in names_v])
-    names_g = sorted(g_gn); out["step_g_grad_norms"] = torch.tensor([g_gn[n] for n in names_g])
+    res = dict(dis_loss=dis_loss, sync_loss=sync_loss, real_loss=real_loss, fake_loss=fake_loss,
+               grad_pen=torch.stack([gp1, gp2, gp3]), gen_loss=gen_loss, g_sync=g_sync, recon=recon,
+               g1=g1, g2=g2, g3=g3, gs=gs, phon=phon, sent=sent, r1_grad3=gr3, r1_grad1=gr1)
+    out.update({pre + k: v for k, v in res.items()})
+    names = sorted(d_gn); out[pre + "d_grad_norms"] = torch.tensor([d_gn[n] for n in names])
+    names_v = sorted(vf_d_gn); out[pre + "vf_d_grad_norms"] = torch.tensor([vf_d_gn[n] for n in names_v])
+    names_g = sorted(g_gn); out[pre + "g_grad_norms"] = torch.tensor([g_gn[n] for n in names_g])
     json.dump(dict(d=names, vf_d=names_v, g=names_g), open(os.path.join(HERE, "grad_norm_names.json"), "w"))
     # post-step parameter checksums (sum and abs-sum of every parameter after both Adam steps)
     chk = {f"{k}.{n}": [float(p.double().sum()), float(p.double().abs().sum())]
            for k, m in mods.items() for n, p in m.named_parameters()}
-    cn = sorted(chk); out["step_param_checksums"] = torch.tensor([chk[n] for n in cn], dtype=torch.float64)
+    cn = sorted(chk); out[pre + "param_checksums"] = torch.tensor([chk[n] for n in cn], dtype=torch.float64)
     bn = {f"{k}.{n}": float(b.double().sum()) for k, m in mods.items() for n, b in m.named_buffers()}
-    bnn = sorted(bn); out["step_buffer_sums"] = torch.tensor([bn[n] for n in bnn], dtype=torch.float64)
+    bnn = sorted(bn); out[pre + "buffer_sums"] = torch.tensor([bn[n] for n in bnn], dtype=torch.float64)
     json.dump(dict(params=cn, buffers=bnn), open(os.path.join(HERE, "checksum_names.json"), "w"))
+
+
+
+def main():
+    out = {}
+    vid, mel, spec, noise = gen_inputs()
+    mods = build()
+    spec_json = {k: {n: [list(t.shape), str(t.dtype).replace("torch.", "")] for n, t in m.state_dict().items()}
+                 for k, m in mods.items()}
+    json.dump(spec_json, open(os.path.join(HERE, "state_spec.json"), "w"), indent=0, sort_keys=True)
+
+    # ---- module forwards, eval mode ----
+    for m in mods.values():
+        m.eval()
+    with torch.no_grad():
+        phon, sent = mods["v_front"](vid)
+        with FixedNoise(noise):
+            g1, g2, g3 = mods["gen"](sent, phon, LENS)
+        gs = mods["post"](g3)
+        out.update(eval_phon=phon, eval_sent=sent, eval_g1=g1, eval_g2=g2, eval_g3=g3, eval_gs=gs)
+        mel1 = torch.nn.functional.interpolate(mel, scale_factor=0.25, mode="bilinear")
+        mel2 = torch.nn.functional.interpolate(mel, scale_factor=0.5, mode="bilinear")
+        for i, (d, x) in enumerate(((mods["dis1"], mel1), (mods["dis2"], mel2), (mods["dis3"], mel)), 1):
+            u, c = d(x, sent, T)
+            out[f"eval_d{i}_u"], out[f"eval_d{i}_c"] = u, c
+        out["eval_sync_nce"] = mods["s_dis"](phon, mel)
+        out["eval_sync_cos"] = mods["s_dis"](phon, g3, True)
+    out["known_gan_loss0"] = gan_loss(torch.zeros(4, 1), True)
+    out["known_final_length"] = torch.tensor([final_length(t) for t in (40, 50, 75, 160, 250)])
+
+    # ---- one full training step exactly as train.py:166-237 (fresh modules, train mode), fp32 and fp64 ----
+    ref_step(out, vid, mel, spec, noise, torch.float32, "step_")
+    ref_step(out, vid, mel, spec, noise, torch.float64, "step64_")
+
+    # ---- what bf16 autocast does to the unmodified reference on the same inputs (the yardstick of the bf16 bound) ----
+    mods = build()
+    for m in mods.values():
+        m.train()
+    with torch.no_grad():
+        p32, s32 = mods["v_front"](vid)
+        with FixedNoise(noise):
+            g32 = mods["gen"](s32, p32, torch.tensor(LENS))
+        gs32 = mods["post"](g32[2])
+    mods = build()
+    for m in mods.values():
+        m.train()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        pa, sa = mods["v_front"](vid)
+        with FixedNoise(noise):
+            ga = mods["gen"](sa.float(), pa.float(), torch.tensor(LENS))
+        gsa = mods["post"](ga[2].float())
+    rel = lambda a, b: float((a.float() - b).norm() / b.norm())
+    out["autocast_bf16_train_errs"] = torch.tensor([rel(pa, p32), rel(sa, s32), rel(ga[0], g32[0]), rel(ga[1], g32[1]),
+                                                    rel(ga[2], g32[2]), rel(gsa, gs32)])
+    out["autocast_bf16_train_mel_l1"] = (ga[2].float() - g32[2]).abs().mean()
 
     # ---- STFT / Griffin-Lim (src/data/stft.py, audio_processing.py) ----
     stft = STFT(640, 160, 640)

@@ -1,8 +1,13 @@
 """Module-level parity: each B200-native module (reference class name / state_dict keys, CUDA kernels through the
 C ABI) against the CPU oracle on identical weights and inputs, forward and parameter gradients, plus the committed
-golden vectors produced by the unmodified reference.  fp32 mode: <= 1e-4 relative (north-star tolerance; 3e-4 on
-gradients that pass through train-mode BatchNorm statistics of a B=2 batch, which amplify rounding).
-bf16 mode: stated bound 3e-2 relative L2 on mels / features."""
+golden vectors produced by the unmodified reference.
+
+Tolerances.  Outputs / losses / eval-mode: <= 1e-4 relative L2 vs the fp32 oracle (north-star fp32 tolerance).
+Gradients through train-mode BatchNorm of a B=2, T=20 batch are ill-conditioned in fp32: the fp32 *reference itself*
+sits 1e-3..5e-3 away from an fp64 run of the same algorithm (tests/diag_grad_errors.py prints the table).  For
+those the truth is the oracle run in fp64 and the bar is  err(ours, fp64) <= max(1e-4, 3 * err(fp32 oracle, fp64))
+per parameter -- i.e. we must be as close to the exact gradient as the reference's own fp32 arithmetic is.
+bf16 mode (eval forward): <= 3e-2 relative L2 on features / mels."""
 import pytest
 import torch
 
@@ -35,17 +40,27 @@ def build(V, spec, name, train):
     return m
 
 
-def grads_close(mod, sd, tol, skip=()):
+def to64(sd):
+    return {k: (v.detach().double().requires_grad_(v.requires_grad) if v.is_floating_point() else v.clone()) for k, v in sd.items()}
+
+
+def grads_close(mod, sd, tol, sd64=None):
+    """sd: fp32 oracle state after backward; sd64: the same oracle in fp64 (truth) or None."""
     bad = []
+    gmax = max(float(v.grad.norm()) for v in (sd64 or sd).values() if v.is_floating_point() and v.grad is not None)
     for n, p in mod.named_parameters():
         ref = sd[n].grad
         if ref is None:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
             continue
         assert p.grad is not None, n
-        e = rel_l2(p.grad.cpu(), ref)
-        if e > tol and float(ref.norm()) > 1e-7 and n not in skip:
-            bad.append((n, e))
+        if sd64 is None:
+            e, bound = rel_l2(p.grad.cpu(), ref), tol
+        else:
+            t = sd64[n].grad
+            e, bound = rel_l2(p.grad.cpu(), t), max(tol, 3.0 * rel_l2(ref, t))
+        if e > bound and float(ref.norm()) > 1e-6 * gmax:
+            bad.append((n, e, bound))
     assert not bad, bad[:10]
 
 
@@ -55,6 +70,7 @@ def test_visual_front(V, state_spec, golden, train):
     vid, mel, spec, noise = golden_inputs()
     sd = make_state(state_spec, "v_front", requires_grad=True)
     phon_r, sent_r = O.visual_front(sd, vid, train)
+    sd64 = to64(sd) if train else None
     m = build(V, state_spec, "v_front", train)
     phon, sent = m(vid.cuda())
     assert phon.shape == (2, 20, 512) and sent.shape == (2, 512, 20)
@@ -67,8 +83,10 @@ def test_visual_front(V, state_spec, golden, train):
     g = torch.Generator().manual_seed(2)
     dp, ds = torch.randn(phon_r.shape, generator=g), torch.randn(sent_r.shape, generator=g)
     ((phon_r * dp).sum() + (sent_r * ds).sum()).backward()
+    p64, s64 = O.visual_front(sd64, vid.double(), True)
+    ((p64 * dp.double()).sum() + (s64 * ds.double()).sum()).backward()
     ((phon * dp.cuda()).sum() + (sent * ds.cuda()).sum()).backward()
-    grads_close(m, sd, GTOL)
+    grads_close(m, sd, TOL, sd64)
     for n, b in m.named_buffers():
         if b.is_floating_point():
             assert rel_l2(b.cpu(), sd[n]) < 1e-4, n
@@ -100,11 +118,16 @@ def test_decoder_postnet(V, state_spec, golden, train):
     g = torch.Generator().manual_seed(4)
     ws = [torch.randn(t.shape, generator=g) for t in (g1r, g2r, g3r, gsr)]
     sum((t * w).sum() for t, w in zip((g1r, g2r, g3r, gsr), ws)).backward()
+    sd64, sp64 = to64(sd), to64(sp)
+    s64 = sent.double().requires_grad_(True); p64 = phon.double().requires_grad_(True)
+    o64 = O.decoder(sd64, s64, p64, [20, 13], noise.double(), True)
+    o64 = (*o64, O.postnet(sp64, o64[2], True))
+    sum((t * w.double()).sum() for t, w in zip(o64, ws)).backward()
     sum((t * w.cuda()).sum() for t, w in zip((g1, g2, g3, gs), ws)).backward()
-    grads_close(m, sd, GTOL)
-    grads_close(p, sp, GTOL)
-    assert rel_l2(sent_d.grad.cpu(), sent_r.grad) < GTOL
-    assert rel_l2(phon_d.grad.cpu(), phon_r.grad) < GTOL
+    grads_close(m, sd, TOL, sd64)
+    grads_close(p, sp, TOL, sp64)
+    assert rel_l2(sent_d.grad.cpu(), s64.grad) < max(TOL, 3 * rel_l2(sent_r.grad, s64.grad))
+    assert rel_l2(phon_d.grad.cpu(), p64.grad) < max(TOL, 3 * rel_l2(phon_r.grad, p64.grad))
 
 
 def test_masked_keys_do_not_matter(V, state_spec):

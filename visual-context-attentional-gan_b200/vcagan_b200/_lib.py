@@ -59,6 +59,7 @@ class _Lib:
         self.cdll = ctypes.CDLL(LIB_PATH)
         self.protos = parse_header()
         self.launches = 0
+        self._prof = None
         for name, (res, args) in self.protos.items():
             fn = getattr(self.cdll, name)
             fn.restype, fn.argtypes = res, args
