@@ -64,7 +64,7 @@ int vca_lrelu_bwd(int dtype, const void* dy, const void* x, void* dx, long long 
 int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t stream);
 int vca_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, long long n, cudaStream_t stream);
 int vca_axpby(int dtype, const void* a, const void* b, void* out, long long n, float alpha, float beta, cudaStream_t stream);
-int vca_colsum(int dtype, const void* x, long long R, int C, float* out, cudaStream_t stream);
+int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, cudaStream_t stream);
 int vca_cast(int dt_in, int dt_out, const void* x, void* y, long long n, cudaStream_t stream);
 int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t stream);
 
@@ -75,11 +75,16 @@ int vca_pool2x2_sum(int dtype, const void* x, void* y, int NF, int H, int W, int
 int vca_expand2x2(int dtype, const void* x, void* y, int NF, int IH, int IW, int C, int H, int W, float scale, cudaStream_t stream);
 int vca_spatial_sum(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t stream);
 int vca_spatial_bcast(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t stream);
+/* layout transforms that put stride-2 convs (resnet.py:33, generator.py:323-327) and the Cin=1 stem (visual_front.py:11) on the tcgen05 path */
+int vca_s2d(int dtype, const void* x, void* y, int NF, int H, int W, int C, int H2, int W2, cudaStream_t stream);
+int vca_d2s(int dtype, const void* y, void* x, int NF, int H, int W, int C, int H2, int W2, cudaStream_t stream);
+int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF, int H, int W, cudaStream_t stream);
 
 /* ---- GRU gates (visual_front.py:20,33-34), attention softmax (generator.py:161-164), sync losses
  *      (generator.py:347-359), gan_loss (generator.py:363-366), L1 (train.py:226-229), Adam (train.py:82-83) - */
 int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const float* hprev, float* hnext, float* out, float* gates, int ndir, int T, int B, int H, int step, cudaStream_t stream);
-int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh, int ndir, int T, int B, int H, int step, cudaStream_t stream);
+int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh, float* dgh_cur, int ndir, int T, int B, int H, int step, cudaStream_t stream);
+int vca_skinny_gemm(const float* in, const float* wt, float* out, int Z, int Bn, int N, int K, float beta, cudaStream_t stream);
 int vca_masked_softmax_fwd(const float* x, float* p, const int* lens, int Z, int R, int S, cudaStream_t stream);
 int vca_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int S, cudaStream_t stream);
 int vca_l2norm_fwd(const float* x, float* y, float* norms, int rows, int D, float eps, cudaStream_t stream);

@@ -164,23 +164,68 @@ def test_conv_tc_bf16(V, case):
         V.set_precision("fp32")
 
 
+@pytest.mark.parametrize("case", [(4, 64, 28, 28, 128, 3), (3, 128, 7, 7, 256, 3), (2, 128, 40, 30, 256, 3), (3, 64, 28, 28, 128, 1),
+                                  (2, 256, 7, 7, 512, 1)])
+def test_conv_stride2_tc_bf16(V, case):
+    """stride-2 convs (resnet.py:33 / downsample, generator.py:326) via space-to-depth / slicing on the tcgen05 path"""
+    N, Cin, H, W, Cout, k = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float().requires_grad_(True)
+    y = F.conv2d(x, w, None, 2, k // 2)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    V.set_precision("bf16")
+    try:
+        xd = cl(x.detach()).cuda().bfloat16().requires_grad_(True)
+        wd = w.detach().cuda().requires_grad_(True)
+        yd = V.ops.conv(xd, wd, None, (2, 2), (k // 2, k // 2))
+        assert tuple(yd.shape) == (N, y.shape[2], y.shape[3], Cout)
+        yd.backward(cl(dy).cuda().bfloat16())
+        e = dict(fwd=rel_l2(nchw(yd.detach().float().cpu()), y), dgrad=rel_l2(nchw(xd.grad.float().cpu()), x.grad),
+                 wgrad=rel_l2(wd.grad.cpu(), w.grad))
+        print("s2 case", case, e)
+        assert max(e.values()) < BF16_TOL, e
+    finally:
+        V.set_precision("fp32")
+
+
+def test_stem_conv_tc_bf16(V):
+    """Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (visual_front.py:11) as im2col + (5,1) conv on the tcgen05 path"""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 1, 6, 24, 20, generator=g).bfloat16().float()
+    w = (torch.randn(64, 1, 5, 7, 7, generator=g) / 15).bfloat16().float().requires_grad_(True)
+    y = F.conv3d(x, w, None, (1, 2, 2), (2, 3, 3))
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    V.set_precision("bf16")
+    try:
+        wd = w.detach().cuda().requires_grad_(True)
+        yd = V.ops.stem_conv(x.cuda(), wd)
+        yd.backward(cl(dy).cuda().bfloat16())
+        assert rel_l2(nchw(yd.detach().float().cpu()), y) < BF16_TOL
+        assert rel_l2(wd.grad.cpu(), w.grad) < BF16_TOL
+    finally:
+        V.set_precision("fp32")
+
+
 def test_bn_act_pool(V):
     g = torch.Generator().manual_seed(5)
     V.set_precision("fp32")
     O = V.ops
     for act in ("prelu", "lrelu", "relu", "none"):
-        x = torch.randn(3, 10, 6, 7, generator=g, requires_grad=True)
-        res = torch.randn(3, 10, 6, 7, generator=g, requires_grad=True)
-        bn = torch.nn.BatchNorm2d(10)
-        bn.weight.data = 1 + 0.2 * torch.randn(10, generator=g); bn.bias.data = 0.1 * torch.randn(10, generator=g)
-        pw = (0.25 + 0.1 * torch.randn(10, generator=g)).requires_grad_(True)
+        x = torch.randn(3, 12, 6, 7, generator=g, requires_grad=True)
+        res = torch.randn(3, 12, 6, 7, generator=g, requires_grad=True)
+        bn = torch.nn.BatchNorm2d(12)
+        bn.weight.data = 1 + 0.2 * torch.randn(12, generator=g); bn.bias.data = 0.1 * torch.randn(12, generator=g)
+        pw = (0.25 + 0.1 * torch.randn(12, generator=g)).requires_grad_(True)
         def actf(v):
             return {"prelu": lambda: F.prelu(v, pw), "lrelu": lambda: F.leaky_relu(v, 0.2), "relu": lambda: F.relu(v),
                     "none": lambda: v}[act]()
         y = actf(bn(x) + res)
         dy = torch.randn(y.shape, generator=g)
         y.backward(dy)
-        bnd = torch.nn.BatchNorm2d(10).cuda()
+        bnd = torch.nn.BatchNorm2d(12).cuda()
         bnd.weight.data = bn.weight.data.clone().cuda(); bnd.bias.data = bn.bias.data.clone().cuda()
         xd = cl(x.detach()).cuda().requires_grad_(True); rd = cl(res.detach()).cuda().requires_grad_(True)
         pwd = pw.detach().cuda().requires_grad_(True)
@@ -199,7 +244,7 @@ def test_bn_act_pool(V):
         assert int(bnd.num_batches_tracked) == 1
     # eval mode
     bn.eval(); bnd.eval()
-    x = torch.randn(2, 10, 4, 5, generator=g)
+    x = torch.randn(2, 12, 4, 5, generator=g)
     assert rel_l2(nchw(O.bn_act(cl(x).cuda(), bnd, O.ACT_LRELU, 0.2).cpu()), F.leaky_relu(bn(x), 0.2)) < FP32_TOL
     # pools
     x = torch.randn(2, 6, 9, 11, generator=g, requires_grad=True)

@@ -1,42 +1,69 @@
-// BatchNorm (+ residual) (+ activation) on channels-last tensors viewed as a [R, C] matrix, plus the
-// stand-alone activations.  HBM-bound: every kernel is a single coalesced pass (threads run along C).
+// BatchNorm (+ residual) (+ activation) on channels-last tensors viewed as a [R, C] matrix, plus the stand-alone
+// activations.  HBM-bound: every kernel is a single coalesced pass with 128-bit accesses (threads own a fixed
+// group of 4/8 channels, so per-channel constants live in registers and there is no index arithmetic per
+// element); per-channel reductions accumulate in fp64 (exact enough to beat the fp32 CPU reference, see
+// tests/diag_grad_errors.py) and are combined with one fp64 atomic per channel per CTA.
 // Reference sites: visual_front.py:12-13, resnet.py:34-63, generator.py:105-126,179,209-225,325-329.
-#include "common.cuh"
+#include "vec.cuh"
 
 namespace {
 
 enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2, ACT_RELU = 3 };
+constexpr int MAX_ROW_BLOCKS = 148 * 4;
 
-// Thread layout for column reductions: blockDim = (CX, RY); thread x walks channels c = bx*CX + x, rows strided.
-constexpr int CX = 32, RY = 8, ROWS_PER_CTA = 256;
+__device__ __forceinline__ float act_fwd(float v, int act, float s) {
+  if (act == ACT_NONE) return v;
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  return v > 0.f ? v : v * s;
+}
+__device__ __forceinline__ float act_bwd(float g, float pre, int act, float s) {
+  if (act == ACT_NONE) return g;
+  if (act == ACT_RELU) return pre > 0.f ? g : 0.f;
+  return pre > 0.f ? g : g * s;
+}
 
-template <class T>
-__global__ void __launch_bounds__(CX* RY) bn_stats_kernel(const T* __restrict__ x, long long R, int C,
-                                                          double* __restrict__ sums /*[2][C]*/) {
-  __shared__ float s1[RY][CX + 1], s2[RY][CX + 1];
-  const int c = blockIdx.x * CX + threadIdx.x;
-  const long long r0 = (long long)blockIdx.y * ROWS_PER_CTA;
-  float a = 0.f, b = 0.f;
-  if (c < C) {
-    long long rend = r0 + ROWS_PER_CTA < R ? r0 + ROWS_PER_CTA : R;
-    for (long long r = r0 + threadIdx.y; r < rend; r += RY) {
-      float v = to_f(x[r * C + c]);
-      a += v; b = fmaf(v, v, b);
-    }
-  }
-  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b;
+// Reduce per-thread fp64 partials over threadIdx.y and add them to out[c] (one atomic per channel per CTA).
+template <int V>
+__device__ __forceinline__ void block_col_reduce(const double (&acc)[V], double* sh, double* out, int c0, bool active) {
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
 #pragma unroll
-    for (int i = 1; i < RY; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; }
-    atomicAdd(&sums[c], (double)a);
-    atomicAdd(&sums[C + c], (double)b);
+  for (int i = 0; i < V; ++i) sh[(ty * TX + tx) * V + i] = acc[i];
+  __syncthreads();
+  if (ty == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      double s = 0;
+      for (int y = 0; y < TY; ++y) s += sh[(y * TX + tx) * V + i];
+      atomicAdd(&out[c0 + i], s);
+    }
   }
 }
 
+template <class T>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long R, int C, double* __restrict__ sums) {
+  constexpr int V = Vec<T>::N;
+  __shared__ double sh[256 * V];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv < C / V;
+  double s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0;
+  if (active) {
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+      float v[V];
+      Vec<T>::load(x + r * C + cv * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) { s1[i] += (double)v[i]; s2[i] += (double)v[i] * (double)v[i]; }
+    }
+  }
+  block_col_reduce<V>(s1, sh, sums, cv * V, active);
+  block_col_reduce<V>(s2, sh, sums + C, cv * V, active);
+}
+
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R, int C, float eps, float momentum,
-                                   float* __restrict__ mean, float* __restrict__ invstd,
-                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+                                   float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double m = sums[c] / (double)R;
@@ -57,177 +84,226 @@ __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* 
   if (c < C) { mean[c] = rm[c]; invstd[c] = 1.f / sqrtf(rv[c] + eps); }
 }
 
-__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
-  if (act == ACT_NONE) return v;
-  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
-  return v > 0.f ? v : v * slope;  // LRELU: constant slope; PRELU: per-channel slope passed in
-}
+struct BnParams {
+  const float *mean, *invstd, *gamma, *beta, *prelu_w;
+  int act;
+  float slope;
+};
 
 // y = act( (x-mean)*invstd*gamma + beta  [+ res] )
 template <class T>
-__global__ void bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y, long long R, int C,
-                                  const float* __restrict__ mean, const float* __restrict__ invstd,
-                                  const float* __restrict__ gamma, const float* __restrict__ beta, int act, float slope,
-                                  const float* __restrict__ prelu_w) {
-  long long total = R * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    float sc = invstd[c] * gamma[c];
-    float v = (to_f(x[i]) - mean[c]) * sc + beta[c];
-    if (res) v += to_f(res[i]);
-    float s = act == ACT_PRELU ? prelu_w[c] : slope;
-    y[i] = from_f<T>(act_fwd(v, act, s));
+__global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                         long long R, int C, BnParams p) {
+  constexpr int V = Vec<T>::N;
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv >= C / V) return;
+  float mu[V], sc[V], be[V], sl[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = cv * V + i;
+    mu[i] = p.mean[c]; sc[i] = p.invstd[c] * p.gamma[c]; be[i] = p.beta[c];
+    sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
+  }
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+    const long long o = r * C + cv * V;
+    float v[V], rr[V];
+    Vec<T>::load(x + o, v);
+    if (res) Vec<T>::load(res + o, rr);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float t = (v[i] - mu[i]) * sc[i] + be[i];
+      if (res) t += rr[i];
+      v[i] = act_fwd(t, p.act, sl[i]);
+    }
+    Vec<T>::store(y + o, v);
   }
 }
 
 // per-channel sums for the backward: s[0][c] = sum dpre, s[1][c] = sum dpre*xhat, s[2][c] = sum dy*min(pre,0) (PReLU)
 template <class T>
-__global__ void __launch_bounds__(CX* RY)
-    bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res, long long R, int C,
-                             const float* __restrict__ mean, const float* __restrict__ invstd,
-                             const float* __restrict__ gamma, const float* __restrict__ beta, int act, float slope,
-                             const float* __restrict__ prelu_w, double* __restrict__ sums /*[3][C]*/) {
-  __shared__ float s1[RY][CX + 1], s2[RY][CX + 1], s3[RY][CX + 1];
-  const int c = blockIdx.x * CX + threadIdx.x;
-  const long long r0 = (long long)blockIdx.y * ROWS_PER_CTA;
-  float a = 0.f, b = 0.f, d = 0.f;
-  if (c < C) {
-    const float mu = mean[c], is = invstd[c], ga = gamma[c], be = beta[c];
-    const float s = act == ACT_PRELU ? prelu_w[c] : slope;
-    long long rend = r0 + ROWS_PER_CTA < R ? r0 + ROWS_PER_CTA : R;
-    for (long long r = r0 + threadIdx.y; r < rend; r += RY) {
-      long long i = r * C + c;
-      float xh = (to_f(x[i]) - mu) * is;
-      float pre = xh * ga + be;
-      if (res) pre += to_f(res[i]);
-      float g = to_f(dy[i]);
-      float dpre = g;
-      if (act == ACT_RELU) dpre = pre > 0.f ? g : 0.f;
-      else if (act != ACT_NONE) { dpre = pre > 0.f ? g : g * s; if (pre <= 0.f) d = fmaf(g, pre, d); }
-      a += dpre; b = fmaf(dpre, xh, b);
+__global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                                const T* __restrict__ res, long long R, int C, BnParams p,
+                                                                double* __restrict__ sums) {
+  constexpr int V = Vec<T>::N;
+  __shared__ double sh[256 * V];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv < C / V;
+  double a[V], b[V], d[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = b[i] = d[i] = 0;
+  if (active) {
+    float mu[V], is[V], ga[V], be[V], sl[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = cv * V + i;
+      mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
+      sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
+    }
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+      const long long o = r * C + cv * V;
+      float xv[V], g[V], rr[V];
+      Vec<T>::load(x + o, xv);
+      Vec<T>::load(dy + o, g);
+      if (res) Vec<T>::load(res + o, rr);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        const float xh = (xv[i] - mu[i]) * is[i];
+        float pre = xh * ga[i] + be[i];
+        if (res) pre += rr[i];
+        const float dpre = act_bwd(g[i], pre, p.act, sl[i]);
+        a[i] += (double)dpre;
+        b[i] += (double)dpre * (double)xh;
+        if (p.act == ACT_PRELU && pre <= 0.f) d[i] += (double)g[i] * (double)pre;
+      }
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a; s2[threadIdx.y][threadIdx.x] = b; s3[threadIdx.y][threadIdx.x] = d;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-#pragma unroll
-    for (int i = 1; i < RY; ++i) { a += s1[i][threadIdx.x]; b += s2[i][threadIdx.x]; d += s3[i][threadIdx.x]; }
-    atomicAdd(&sums[c], (double)a);
-    atomicAdd(&sums[C + c], (double)b);
-    atomicAdd(&sums[2 * C + c], (double)d);
-  }
+  block_col_reduce<V>(a, sh, sums, cv * V, active);
+  block_col_reduce<V>(b, sh, sums + C, cv * V, active);
+  if (p.act == ACT_PRELU) block_col_reduce<V>(d, sh, sums + 2 * C, cv * V, active);
 }
 
-// dx = gamma*invstd*(dpre - mean(dpre) - xhat*mean(dpre*xhat))   (train)   |   gamma*invstd*dpre (eval)
-// dres = dpre.  Also writes dgamma/dbeta/dprelu (one thread per channel in block 0).
+// dx = gamma*invstd*(dpre - mean(dpre) - xhat*mean(dpre*xhat))   (train)   |   gamma*invstd*dpre (eval);  dres = dpre.
 template <class T>
-__global__ void bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ res,
-                                        T* __restrict__ dx, T* __restrict__ dres, long long R, int C,
-                                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                                        const float* __restrict__ gamma, const float* __restrict__ beta, int act,
-                                        float slope, const float* __restrict__ prelu_w, const double* __restrict__ sums,
-                                        int train, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                        float* __restrict__ dprelu) {
-  long long total = R * C;
+__global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                               const T* __restrict__ res, T* __restrict__ dx,
+                                                               T* __restrict__ dres, long long R, int C, BnParams p,
+                                                               const double* __restrict__ sums, int train) {
+  constexpr int V = Vec<T>::N;
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv >= C / V) return;
+  float mu[V], is[V], ga[V], be[V], sl[V], m1[V], m2[V];
   const double invR = 1.0 / (double)R;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C);
-    const float mu = mean[c], is = invstd[c], ga = gamma[c];
-    float xh = (to_f(x[i]) - mu) * is;
-    float pre = xh * ga + beta[c];
-    if (res) pre += to_f(res[i]);
-    float g = to_f(dy[i]);
-    float s = act == ACT_PRELU ? prelu_w[c] : slope;
-    float dpre = g;
-    if (act == ACT_RELU) dpre = pre > 0.f ? g : 0.f;
-    else if (act != ACT_NONE) dpre = pre > 0.f ? g : g * s;
-    if (dres) dres[i] = from_f<T>(dpre);
-    float v = dpre;
-    if (train) v = dpre - (float)(sums[c] * invR) - xh * (float)(sums[C + c] * invR);
-    dx[i] = from_f<T>(v * ga * is);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = cv * V + i;
+    mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
+    sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
+    m1[i] = train ? (float)(sums[c] * invR) : 0.f;
+    m2[i] = train ? (float)(sums[C + c] * invR) : 0.f;
   }
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      if (dgamma) dgamma[c] = (float)sums[C + c];
-      if (dbeta) dbeta[c] = (float)sums[c];
-      if (dprelu) dprelu[c] = (float)sums[2 * C + c];
+  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+    const long long o = r * C + cv * V;
+    float xv[V], g[V], rr[V];
+    Vec<T>::load(x + o, xv);
+    Vec<T>::load(dy + o, g);
+    if (res) Vec<T>::load(res + o, rr);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float xh = (xv[i] - mu[i]) * is[i];
+      float pre = xh * ga[i] + be[i];
+      if (res) pre += rr[i];
+      const float dpre = act_bwd(g[i], pre, p.act, sl[i]);
+      g[i] = dpre;
+      xv[i] = (dpre - m1[i] - xh * m2[i]) * ga[i] * is[i];
     }
+    Vec<T>::store(dx + o, xv);
+    if (dres) Vec<T>::store(dres + o, g);
   }
 }
 
-template <class T>
-__global__ void lrelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, float slope) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = to_f(x[i]);
-    y[i] = from_f<T>(v > 0.f ? v : v * slope);
-  }
+__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, float* __restrict__ dprelu) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dgamma) dgamma[c] = (float)sums[C + c];
+  if (dbeta) dbeta[c] = (float)sums[c];
+  if (dprelu) dprelu[c] = (float)sums[2 * C + c];
 }
-// dx = dy * (x > 0 ? 1 : slope)   (also used for its own double-backward: linear in dy)
-template <class T>
-__global__ void lrelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, T* __restrict__ dx, long long n,
-                                 float slope) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float g = to_f(dy[i]);
-    dx[i] = from_f<T>(to_f(x[i]) > 0.f ? g : g * slope);
+
+// ---- flat element-wise kernels (8 elements per thread per iteration) ------------------------------------------
+struct OpLRelu { float s; __device__ float operator()(float a, float) const { return a > 0.f ? a : a * s; } };
+struct OpLReluBwd { float s; __device__ float operator()(float g, float x) const { return x > 0.f ? g : g * s; } };
+struct OpTanh { __device__ float operator()(float a, float) const { return tanhf(a); } };
+struct OpTanhBwd { __device__ float operator()(float g, float y) const { return g * (1.f - y * y); } };
+struct OpAxpby { float al, be; __device__ float operator()(float a, float b) const { return fmaf(be, b, al * a); } };
+struct OpMul { __device__ float operator()(float a, float b) const { return a * b; } };
+
+template <class TI, class TO, class Op, bool TWO>
+__global__ void __launch_bounds__(256) ew_kernel(const TI* __restrict__ a, const TI* __restrict__ b, TO* __restrict__ out,
+                                                 long long n, Op op, bool vec_ok) {
+  constexpr int E = 8;
+  const long long nv = vec_ok ? n / E : 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nv; i += (long long)gridDim.x * blockDim.x) {
+    float x[E], y[E];
+    constexpr int VI = Vec<TI>::N, VO = Vec<TO>::N;
+#pragma unroll
+    for (int k = 0; k < E / VI; ++k) Vec<TI>::load(a + i * E + k * VI, x + k * VI);
+    if (TWO) {
+#pragma unroll
+      for (int k = 0; k < E / VI; ++k) Vec<TI>::load(b + i * E + k * VI, y + k * VI);
+    }
+#pragma unroll
+    for (int k = 0; k < E; ++k) x[k] = op(x[k], TWO ? y[k] : 0.f);
+#pragma unroll
+    for (int k = 0; k < E / VO; ++k) Vec<TO>::store(out + i * E + k * VO, x + k * VO);
   }
+  for (long long i = nv * E + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f<TO>(op(to_f(a[i]), TWO ? to_f(b[i]) : 0.f));
+}
+
+template <class TI, class TO, class Op>
+int ew_launch(const void* a, const void* b, void* out, long long n, Op op, cudaStream_t s) {
+  if (n <= 0) return VCA_OK;
+  const bool vec_ok = vca_aligned16(a) && vca_aligned16(out) && (!b || vca_aligned16(b));
+  unsigned grid = vca_grid_1d(n, 256, 8);
+  if (b) ew_kernel<TI, TO, Op, true><<<grid, 256, 0, s>>>((const TI*)a, (const TI*)b, (TO*)out, n, op, vec_ok);
+  else ew_kernel<TI, TO, Op, false><<<grid, 256, 0, s>>>((const TI*)a, nullptr, (TO*)out, n, op, vec_ok);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+template <class Op>
+int ew_dispatch(int dtype, const void* a, const void* b, void* out, long long n, Op op, cudaStream_t s) {
+  return dtype == VCA_F32 ? ew_launch<float, float, Op>(a, b, out, n, op, s) : ew_launch<bf16, bf16, Op>(a, b, out, n, op, s);
+}
+
+// column sums of a [R, C] matrix into fp32 (bias gradients); scalar path handles any C
+template <class T>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x, long long R, int C, double* __restrict__ out) {
+  constexpr int V = Vec<T>::N;
+  __shared__ double sh[256 * V];
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  const bool active = cv < C / V;
+  double a[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) a[i] = 0;
+  if (active) {
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
+      float v[V];
+      Vec<T>::load(x + r * C + cv * V, v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) a[i] += (double)v[i];
+    }
+  }
+  block_col_reduce<V>(a, sh, out, cv * V, active);
 }
 template <class T>
-__global__ void tanh_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = from_f<T>(tanhf(to_f(x[i])));
-}
-template <class T>
-__global__ void tanh_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float t = to_f(y[i]);
-    dx[i] = from_f<T>(to_f(dy[i]) * (1.f - t * t));
-  }
-}
-// out = alpha*a + beta*b  (b may be null)
-template <class T>
-__global__ void axpby_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, long long n, float alpha,
-                             float beta) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    float v = alpha * to_f(a[i]);
-    if (b) v = fmaf(beta, to_f(b[i]), v);
-    out[i] = from_f<T>(v);
-  }
-}
-// column sums of a [R, C] matrix into fp32 (bias gradients): out[c] += sum_r x[r,c]  (out zeroed by caller)
-template <class T>
-__global__ void __launch_bounds__(CX* RY) colsum_kernel(const T* __restrict__ x, long long R, int C, float* __restrict__ out) {
-  __shared__ float s1[RY][CX + 1];
-  const int c = blockIdx.x * CX + threadIdx.x;
-  const long long r0 = (long long)blockIdx.y * ROWS_PER_CTA;
-  float a = 0.f;
-  if (c < C) {
-    long long rend = r0 + ROWS_PER_CTA < R ? r0 + ROWS_PER_CTA : R;
-    for (long long r = r0 + threadIdx.y; r < rend; r += RY) a += to_f(x[r * C + c]);
-  }
-  s1[threadIdx.y][threadIdx.x] = a;
+__global__ void colsum_scalar_kernel(const T* __restrict__ x, long long R, int C, double* __restrict__ out) {
+  // one warp-row per 32 channels; rows strided over blockIdx.x * blockDim.y
+  const int c = blockIdx.y * 32 + threadIdx.x;
+  double a = 0;
+  if (c < C)
+    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y)
+      a += (double)to_f(x[r * C + c]);
+  __shared__ double sh[8][33];
+  sh[threadIdx.y][threadIdx.x] = a;
   __syncthreads();
   if (threadIdx.y == 0 && c < C) {
-#pragma unroll
-    for (int i = 1; i < RY; ++i) a += s1[i][threadIdx.x];
+    for (int y = 1; y < 8; ++y) a += sh[y][threadIdx.x];
     atomicAdd(&out[c], a);
   }
 }
-
-template <class TI, class TO>
-__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    y[i] = from_f<TO>(to_f(x[i]));
+__global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)in[i];
 }
 
-inline dim3 col_grid(long long R, int C) {
-  long long gy = (R + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-  return dim3((C + CX - 1) / CX, (unsigned)(gy > 65535 ? 65535 : gy), 1);
+template <class T>
+bool vec_ok(const void* a, const void* b, const void* c, const void* d, const void* e, int C) {
+  return C % Vec<T>::N == 0 && vca_aligned16(a) && (!b || vca_aligned16(b)) && (!c || vca_aligned16(c)) &&
+         (!d || vca_aligned16(d)) && (!e || vca_aligned16(e));
 }
 
 }  // namespace
-
-#define DISPATCH_T(dtype, CALL_F32, CALL_BF16) \
-  do { if ((dtype) == VCA_F32) { CALL_F32; } else { CALL_BF16; } } while (0)
 
 extern "C" {
 
@@ -236,11 +312,16 @@ extern "C" {
 int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, float* mean,
                  float* invstd, float* running_mean, float* running_var, cudaStream_t s) {
   VCA_CHECK_ARG(x && sums && mean && invstd && R > 0 && C > 0);
-  VCA_CHECK_ARG((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA <= 65535);
+  const bool ok = dtype == VCA_F32 ? vec_ok<float>(x, 0, 0, 0, 0, C) : vec_ok<bf16>(x, 0, 0, 0, 0, C);
+  if (!ok) { vca_set_error("vca_bn_stats: C must be a multiple of %d and x 16-byte aligned", dtype == VCA_F32 ? 4 : 8); return VCA_ERR_UNSUPPORTED; }
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
-  dim3 grid = col_grid(R, C), block(CX, RY);
-  DISPATCH_T(dtype, (bn_stats_kernel<float><<<grid, block, 0, s>>>((const float*)x, R, C, sums)),
-             (bn_stats_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, R, C, sums)));
+  if (dtype == VCA_F32) {
+    RowColGrid g = row_col_grid(R, C / 4, MAX_ROW_BLOCKS);
+    bn_stats_kernel<float><<<g.grid, g.block, 0, s>>>((const float*)x, R, C, sums);
+  } else {
+    RowColGrid g = row_col_grid(R, C / 8, MAX_ROW_BLOCKS);
+    bn_stats_kernel<bf16><<<g.grid, g.block, 0, s>>>((const bf16*)x, R, C, sums);
+  }
   VCA_LAUNCH_CHECK();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var);
   VCA_LAUNCH_CHECK();
@@ -257,12 +338,16 @@ int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long
                    const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w,
                    cudaStream_t s) {
   VCA_CHECK_ARG(x && y && mean && invstd && gamma && beta && R > 0 && C > 0 && (act != ACT_PRELU || prelu_w));
-  unsigned grid = vca_grid_1d(R * C, 256, 4);
-  DISPATCH_T(dtype,
-             (bn_act_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)res, (float*)y, R, C, mean, invstd,
-                                                            gamma, beta, act, slope, prelu_w)),
-             (bn_act_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)res, (bf16*)y, R, C, mean, invstd,
-                                                           gamma, beta, act, slope, prelu_w)));
+  const bool ok = dtype == VCA_F32 ? vec_ok<float>(x, res, y, 0, 0, C) : vec_ok<bf16>(x, res, y, 0, 0, C);
+  if (!ok) { vca_set_error("vca_bn_act_fwd: C must be a multiple of %d and tensors 16-byte aligned", dtype == VCA_F32 ? 4 : 8); return VCA_ERR_UNSUPPORTED; }
+  BnParams p{mean, invstd, gamma, beta, prelu_w, act, slope};
+  if (dtype == VCA_F32) {
+    RowColGrid g = row_col_grid(R, C / 4, 148 * 8);
+    bn_act_fwd_kernel<float><<<g.grid, g.block, 0, s>>>((const float*)x, (const float*)res, (float*)y, R, C, p);
+  } else {
+    RowColGrid g = row_col_grid(R, C / 8, 148 * 8);
+    bn_act_fwd_kernel<bf16><<<g.grid, g.block, 0, s>>>((const bf16*)x, (const bf16*)res, (bf16*)y, R, C, p);
+  }
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
@@ -271,91 +356,82 @@ int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, vo
                    const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope,
                    const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu,
                    cudaStream_t s) {
-  VCA_CHECK_ARG(dy && x && dx && mean && invstd && gamma && beta && sums && R > 0 && C > 0);
-  VCA_CHECK_ARG((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA <= 65535);
+  VCA_CHECK_ARG(dy && x && dx && mean && invstd && gamma && beta && sums && R > 0 && C > 0 && (act != ACT_PRELU || prelu_w));
+  const bool ok = dtype == VCA_F32 ? vec_ok<float>(dy, x, res, dx, dres, C) : vec_ok<bf16>(dy, x, res, dx, dres, C);
+  if (!ok) { vca_set_error("vca_bn_act_bwd: C must be a multiple of %d and tensors 16-byte aligned", dtype == VCA_F32 ? 4 : 8); return VCA_ERR_UNSUPPORTED; }
   cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, s);
-  dim3 grid = col_grid(R, C), block(CX, RY);
-  DISPATCH_T(dtype,
-             (bn_act_bwd_reduce_kernel<float><<<grid, block, 0, s>>>((const float*)dy, (const float*)x, (const float*)res, R, C,
-                                                                     mean, invstd, gamma, beta, act, slope, prelu_w, sums)),
-             (bn_act_bwd_reduce_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, R, C,
-                                                                    mean, invstd, gamma, beta, act, slope, prelu_w, sums)));
+  BnParams p{mean, invstd, gamma, beta, prelu_w, act, slope};
+  if (dtype == VCA_F32) {
+    RowColGrid g = row_col_grid(R, C / 4, MAX_ROW_BLOCKS);
+    bn_act_bwd_reduce_kernel<float><<<g.grid, g.block, 0, s>>>((const float*)dy, (const float*)x, (const float*)res, R, C, p, sums);
+    VCA_LAUNCH_CHECK();
+    RowColGrid g2 = row_col_grid(R, C / 4, 148 * 8);
+    bn_act_bwd_apply_kernel<float><<<g2.grid, g2.block, 0, s>>>((const float*)dy, (const float*)x, (const float*)res, (float*)dx,
+                                                                 (float*)dres, R, C, p, sums, train);
+  } else {
+    RowColGrid g = row_col_grid(R, C / 8, MAX_ROW_BLOCKS);
+    bn_act_bwd_reduce_kernel<bf16><<<g.grid, g.block, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, R, C, p, sums);
+    VCA_LAUNCH_CHECK();
+    RowColGrid g2 = row_col_grid(R, C / 8, 148 * 8);
+    bn_act_bwd_apply_kernel<bf16><<<g2.grid, g2.block, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, (bf16*)dx,
+                                                                (bf16*)dres, R, C, p, sums, train);
+  }
   VCA_LAUNCH_CHECK();
-  unsigned g1 = vca_grid_1d(R * C, 256, 4);
-  DISPATCH_T(dtype,
-             (bn_act_bwd_apply_kernel<float><<<g1, 256, 0, s>>>((const float*)dy, (const float*)x, (const float*)res,
-                                                                (float*)dx, (float*)dres, R, C, mean, invstd, gamma, beta, act,
-                                                                slope, prelu_w, sums, train, dgamma, dbeta, dprelu)),
-             (bn_act_bwd_apply_kernel<bf16><<<g1, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)res, (bf16*)dx,
-                                                               (bf16*)dres, R, C, mean, invstd, gamma, beta, act, slope,
-                                                               prelu_w, sums, train, dgamma, dbeta, dprelu)));
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, dgamma, dbeta, act == ACT_PRELU ? dprelu : nullptr);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
 int vca_lrelu_fwd(int dtype, const void* x, void* y, long long n, float slope, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (lrelu_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, n, slope)),
-             (lrelu_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, n, slope)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+  return ew_dispatch(dtype, x, nullptr, y, n, OpLRelu{slope}, s);
 }
 int vca_lrelu_bwd(int dtype, const void* dy, const void* x, void* dx, long long n, float slope, cudaStream_t s) {
   VCA_CHECK_ARG(dy && x && dx && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (lrelu_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dy, (const float*)x, (float*)dx, n, slope)),
-             (lrelu_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (bf16*)dx, n, slope)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+  return ew_dispatch(dtype, dy, x, dx, n, OpLReluBwd{slope}, s);
 }
 int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (tanh_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, n)),
-             (tanh_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, n)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+  return ew_dispatch(dtype, x, nullptr, y, n, OpTanh{}, s);
 }
 int vca_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, long long n, cudaStream_t s) {
   VCA_CHECK_ARG(dy && y && dx && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (tanh_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dy, (const float*)y, (float*)dx, n)),
-             (tanh_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)y, (bf16*)dx, n)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+  return ew_dispatch(dtype, dy, y, dx, n, OpTanhBwd{}, s);
 }
 int vca_axpby(int dtype, const void* a, const void* b, void* out, long long n, float alpha, float beta, cudaStream_t s) {
   VCA_CHECK_ARG(a && out && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (axpby_kernel<float><<<grid, 256, 0, s>>>((const float*)a, (const float*)b, (float*)out, n, alpha, beta)),
-             (axpby_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)a, (const bf16*)b, (bf16*)out, n, alpha, beta)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+  return ew_dispatch(dtype, a, b, out, n, OpAxpby{alpha, b ? beta : 0.f}, s);
 }
-// out[c] = sum_r x[r,c]; out is zeroed here.
-int vca_colsum(int dtype, const void* x, long long R, int C, float* out, cudaStream_t s) {
-  VCA_CHECK_ARG(x && out && R > 0 && C > 0);
-  VCA_CHECK_ARG((R + ROWS_PER_CTA - 1) / ROWS_PER_CTA <= 65535);
-  cudaMemsetAsync(out, 0, sizeof(float) * C, s);
-  dim3 grid = col_grid(R, C), block(CX, RY);
-  DISPATCH_T(dtype, (colsum_kernel<float><<<grid, block, 0, s>>>((const float*)x, R, C, out)),
-             (colsum_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, R, C, out)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
+int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t s) {
+  VCA_CHECK_ARG(x && m && y && n > 0);
+  return ew_dispatch(dtype, x, m, y, n, OpMul{}, s);
 }
 int vca_cast(int dt_in, int dt_out, const void* x, void* y, long long n, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && n >= 0);
-  if (n == 0) return VCA_OK;
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  if (dt_in == VCA_F32 && dt_out == VCA_BF16) cast_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)x, (bf16*)y, n);
-  else if (dt_in == VCA_BF16 && dt_out == VCA_F32) cast_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)x, (float*)y, n);
-  else if (dt_in == VCA_F32 && dt_out == VCA_F32) cast_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, n);
-  else cast_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, n);
+  OpAxpby id{1.f, 0.f};
+  if (dt_in == VCA_F32 && dt_out == VCA_BF16) return ew_launch<float, bf16, OpAxpby>(x, nullptr, y, n, id, s);
+  if (dt_in == VCA_BF16 && dt_out == VCA_F32) return ew_launch<bf16, float, OpAxpby>(x, nullptr, y, n, id, s);
+  if (dt_in == VCA_F32) return ew_launch<float, float, OpAxpby>(x, nullptr, y, n, id, s);
+  return ew_launch<bf16, bf16, OpAxpby>(x, nullptr, y, n, id, s);
+}
+// out[c] = sum_r x[r,c] (fp32).  scratch: device double[C].
+int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, cudaStream_t s) {
+  VCA_CHECK_ARG(x && out && scratch && R > 0 && C > 0);
+  cudaMemsetAsync(scratch, 0, sizeof(double) * C, s);
+  const bool ok = dtype == VCA_F32 ? vec_ok<float>(x, 0, 0, 0, 0, C) : vec_ok<bf16>(x, 0, 0, 0, 0, C);
+  if (ok && dtype == VCA_F32) {
+    RowColGrid g = row_col_grid(R, C / 4, MAX_ROW_BLOCKS);
+    colsum_vec_kernel<float><<<g.grid, g.block, 0, s>>>((const float*)x, R, C, scratch);
+  } else if (ok) {
+    RowColGrid g = row_col_grid(R, C / 8, MAX_ROW_BLOCKS);
+    colsum_vec_kernel<bf16><<<g.grid, g.block, 0, s>>>((const bf16*)x, R, C, scratch);
+  } else {
+    long long gx = (R + 7) / 8; if (gx > MAX_ROW_BLOCKS) gx = MAX_ROW_BLOCKS;
+    dim3 grid((unsigned)gx, (unsigned)((C + 31) / 32)), block(32, 8);
+    if (dtype == VCA_F32) colsum_scalar_kernel<float><<<grid, block, 0, s>>>((const float*)x, R, C, scratch);
+    else colsum_scalar_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, R, C, scratch);
+  }
+  VCA_LAUNCH_CHECK();
+  d2f_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

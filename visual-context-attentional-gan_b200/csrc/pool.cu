@@ -1,19 +1,26 @@
-// Pooling / resampling kernels on channels-last tensors [N(frames), H, W, C]; threads run along C (coalesced).
+// Pooling / resampling kernels on channels-last tensors [N(frames), H, W, C]; each thread owns 4/8 consecutive
+// channels of one pixel (128-bit accesses, coalesced along C).
 // Reference sites: visual_front.py:14 (MaxPool3d (1,3,3)/(1,2,2)/(0,1,1)), generator.py:74,83 (avg_pool2d 2),
-// generator.py:112,121 (nearest x2), generator.py:140 / resnet.py:82 (spatial mean).
-#include "common.cuh"
+// generator.py:112,121 (nearest x2), generator.py:140 / resnet.py:82 (spatial mean), visual_front.py:11 (stem im2col).
+#include "vec.cuh"
 
 namespace {
 
+#define GRID_STRIDE(i, total) \
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
+
 // 3x3 stride-2 pad-1 max pool per frame; idx = argmax position 0..8 (first max wins, like ATen).
-template <class T>
+template <class T, class VT>
 __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int NF,
                                         int H, int W, int C, int OH, int OW) {
-  long long total = (long long)NF * OH * OW * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); long long r = i / C;
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * OH * OW * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
     int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
-    float best = -INFINITY; int bi = 0;
+    float best[V]; int bi[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bi[k] = 0; }
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       int h = oh * 2 - 1 + kh;
@@ -22,124 +29,223 @@ __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__
       for (int kw = 0; kw < 3; ++kw) {
         int w = ow * 2 - 1 + kw;
         if ((unsigned)w >= (unsigned)W) continue;
-        float v = to_f(x[(((long long)n * H + h) * W + w) * C + c]);
-        if (v > best || (v != v && !(best != best))) { best = v; bi = kh * 3 + kw; }
+        float v[V];
+        VT::load(x + (((long long)n * H + h) * W + w) * C + cv * V, v);
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if (v[k] > best[k] || (v[k] != v[k] && best[k] == best[k])) { best[k] = v[k]; bi[k] = kh * 3 + kw; }
       }
     }
-    y[i] = from_f<T>(best);
-    idx[i] = (unsigned char)bi;
+    const long long o = i * V;
+    VT::store(y + o, best);
+#pragma unroll
+    for (int k = 0; k < V; ++k) idx[o + k] = (unsigned char)bi[k];
   }
 }
 // gather form of the backward: every input pixel looks at the <=4 windows that contain it.
-template <class T>
+template <class T, class VT>
 __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, T* __restrict__ dx,
                                         int NF, int H, int W, int C, int OH, int OW) {
-  long long total = (long long)NF * H * W * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); long long r = i / C;
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * H * W * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
     int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
-    float acc = 0.f;
-    int oh_lo = h >> 1, oh_hi = (h + 1) >> 1;  // windows oh cover rows 2oh-1..2oh+1
-    int ow_lo = w >> 1, ow_hi = (w + 1) >> 1;
-    for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int oh = h >> 1; oh <= ((h + 1) >> 1); ++oh) {   // windows oh cover rows 2oh-1..2oh+1
       if (oh >= OH) continue;
-      int kh = h - (oh * 2 - 1);
-      for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      const int kh = h - (oh * 2 - 1);
+      for (int ow = w >> 1; ow <= ((w + 1) >> 1); ++ow) {
         if (ow >= OW) continue;
-        int kw = w - (ow * 2 - 1);
-        long long o = (((long long)n * OH + oh) * OW + ow) * C + c;
-        if (idx[o] == kh * 3 + kw) acc += to_f(dy[o]);
+        const int code = kh * 3 + (w - (ow * 2 - 1));
+        const long long o = (((long long)n * OH + oh) * OW + ow) * C + cv * V;
+        float g[V];
+        VT::load(dy + o, g);
+#pragma unroll
+        for (int k = 0; k < V; ++k) if (idx[o + k] == code) acc[k] += g[k];
       }
     }
-    dx[i] = from_f<T>(acc);
+    VT::store(dx + i * V, acc);
+  }
+}
+// y[oh,ow] = scale * sum of the 2x2 block (scale 0.25: avg_pool2d(x,2); scale 1: backward of nearest x2).
+template <class T, class VT>
+__global__ void pool2x2_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int H, int W, int C, int OH, int OW,
+                                   float scale) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * OH * OW * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
+    int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
+    const T* p = x + (((long long)n * H + oh * 2) * W + ow * 2) * C + cv * V;
+    float a[V], b[V], c[V], d[V];
+    VT::load(p, a); VT::load(p + C, b); VT::load(p + (long long)W * C, c); VT::load(p + (long long)W * C + C, d);
+#pragma unroll
+    for (int k = 0; k < V; ++k) a[k] = (a[k] + b[k] + c[k] + d[k]) * scale;
+    VT::store(y + i * V, a);
+  }
+}
+// y[h,w] = scale * x[h/2, w/2] when (h/2 < IH && w/2 < IW) else 0.  scale 1: nearest x2; 0.25: backward of avg pool.
+template <class T, class VT>
+__global__ void expand2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int IH, int IW, int C, int H, int W,
+                                 float scale) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * H * W * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
+    int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+    const int ih = h >> 1, iw = w >> 1;
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = 0.f;
+    if (ih < IH && iw < IW) {
+      VT::load(x + (((long long)n * IH + ih) * IW + iw) * C + cv * V, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) v[k] *= scale;
+    }
+    VT::store(y + i * V, v);
+  }
+}
+// y[n,c] = scale * sum_p x[n,p,c]
+template <class T, class VT>
+__global__ void spatial_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int P, int C, float scale) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * CV) {
+    int cv = (int)(i % CV); int n = (int)(i / CV);
+    const T* p = x + (long long)n * P * C + cv * V;
+    float a[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) a[k] = 0.f;
+    for (int q = 0; q < P; ++q) {
+      float v[V];
+      VT::load(p + (long long)q * C, v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) a[k] += v[k];
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) a[k] *= scale;
+    VT::store(y + i * V, a);
+  }
+}
+// y[n,p,c] = scale * x[n,c]
+template <class T, class VT>
+__global__ void spatial_bcast_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int P, int C, float scale) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * P * CV) {
+    int cv = (int)(i % CV); int n = (int)(i / ((long long)P * CV));
+    float v[V];
+    VT::load(x + (long long)n * C + cv * V, v);
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] *= scale;
+    VT::store(y + i * V, v);
   }
 }
 
-// avg_pool2d(x, 2) (floor): y[oh,ow] = scale * sum of the 2x2 block.  With scale=0.25 it is the forward; with
-// scale=1 it is the backward of nearest-x2 upsampling.
-template <class T>
-__global__ void pool2x2_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int H, int W, int C, int OH, int OW,
-                                   float scale) {
-  long long total = (long long)NF * OH * OW * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); long long r = i / C;
-    int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
-    const T* p = x + (((long long)n * H + oh * 2) * W + ow * 2) * C + c;
-    float v = to_f(p[0]) + to_f(p[C]) + to_f(p[(long long)W * C]) + to_f(p[(long long)W * C + C]);
-    y[i] = from_f<T>(v * scale);
+// Space-to-depth with a zero border for stride-2 3x3 / pad-1 convolutions:
+//   y[n, i, j, (pa*2+pb)*C + c] = x[n, 2i+pa-1, 2j+pb-1, c]   (0 outside), y is [NF, H2, W2, 4C].
+// A 3x3 stride-2 conv over x is then a 2x2 stride-1 conv over y (see ops.conv_s2), which runs on the tcgen05 path.
+template <class T, class VT>
+__global__ void s2d_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int H, int W, int C, int H2, int W2) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * H2 * W2 * 4 * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
+    int par = (int)(r % 4); r /= 4;
+    int j = (int)(r % W2); r /= W2; int ii = (int)(r % H2); int n = (int)(r / H2);
+    const int h = 2 * ii + (par >> 1) - 1, w = 2 * j + (par & 1) - 1;
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = 0.f;
+    if ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) VT::load(x + (((long long)n * H + h) * W + w) * C + cv * V, v);
+    VT::store(y + i * V, v);
   }
 }
-// y[h,w] = scale * x[h/2, w/2] when (h/2 < IH && w/2 < IW) else 0; output H x W (>= 2*IH, 2*IW).
-// scale=1: nearest x2 upsample; scale=0.25: backward of avg_pool2d(2) (odd trailing row/col get zero).
-template <class T>
-__global__ void expand2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int IH, int IW, int C, int H, int W,
-                                 float scale) {
-  long long total = (long long)NF * H * W * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); long long r = i / C;
+// inverse gather (the transpose of s2d): x[n,h,w,c] = y[n,(h+1)/2,(w+1)/2,(((h+1)&1)*2+((w+1)&1))*C + c]
+template <class T, class VT>
+__global__ void d2s_kernel(const T* __restrict__ y, T* __restrict__ x, int NF, int H, int W, int C, int H2, int W2) {
+  constexpr int V = VT::N;
+  const int CV = C / V;
+  GRID_STRIDE(i, (long long)NF * H * W * CV) {
+    int cv = (int)(i % CV); long long r = i / CV;
     int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
-    int ih = h >> 1, iw = w >> 1;
-    float v = 0.f;
-    if (ih < IH && iw < IW) v = scale * to_f(x[(((long long)n * IH + ih) * IW + iw) * C + c]);
-    y[i] = from_f<T>(v);
+    const int ii = (h + 1) >> 1, j = (w + 1) >> 1, par = (((h + 1) & 1) << 1) | ((w + 1) & 1);
+    float v[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) v[k] = 0.f;
+    if (ii < H2 && j < W2) VT::load(y + ((((long long)n * H2 + ii) * W2 + j) * 4 + par) * C + cv * V, v);
+    VT::store(x + i * V, v);
   }
 }
-// spatial mean: y[n,c] = scale * sum_p x[n,p,c]
+
+// im2col of the visual front-end stem over its two spatial kernel dims (visual_front.py:11: k=(5,7,7), s=(1,2,2),
+// p=(2,3,3), Cin=1): y[f, oh, ow, kh*7+kw] = x[f, 2oh-3+kh, 2ow-3+kw] for the 49 taps, channels 49..63 zero.
+// The remaining temporal 5-tap convolution (64 -> 64 channels) then runs as a (5,1) conv on the tcgen05 path.
+template <class TI, class TO>
+__global__ void stem_im2col_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long NF, int H, int W, int OH, int OW) {
+  GRID_STRIDE(i, NF * OH * OW * 8) {   // 8 channel-groups of 8
+    int cg = (int)(i & 7); long long r = i >> 3;
+    int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); long long f = r / OH;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int t = cg * 8 + k;
+      const int kh = t / 7, kw = t - kh * 7;
+      const int h = 2 * oh - 3 + kh, w = 2 * ow - 3 + kw;
+      v[k] = (t < 49 && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) ? to_f(x[(f * H + h) * W + w]) : 0.f;
+    }
+    TO* o = y + i * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = from_f<TO>(v[k]);
+  }
+}
+
 template <class T>
-__global__ void spatial_sum_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int P, int C, float scale) {
-  long long total = (long long)NF * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); int n = (int)(i / C);
-    const T* p = x + (long long)n * P * C + c;
-    float a = 0.f;
-    for (int q = 0; q < P; ++q) a += to_f(p[(long long)q * C]);
-    y[i] = from_f<T>(a * scale);
-  }
-}
-// broadcast: y[n,p,c] = scale * x[n,c]
-template <class T>
-__global__ void spatial_bcast_kernel(const T* __restrict__ x, T* __restrict__ y, int NF, int P, int C, float scale) {
-  long long total = (long long)NF * P * C;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int c = (int)(i % C); int n = (int)(i / ((long long)P * C));
-    y[i] = from_f<T>(scale * to_f(x[(long long)n * C + c]));
-  }
-}
+bool use_vec(int C, const void* a, const void* b) { return C % Vec<T>::N == 0 && vca_aligned16(a) && vca_aligned16(b); }
 
 }  // namespace
 
-#define DISPATCH_T(dtype, CALL_F32, CALL_BF16) \
-  do { if ((dtype) == VCA_F32) { CALL_F32; } else { CALL_BF16; } } while (0)
+#define POOL_DISPATCH_T(KERNEL, T, total_per_c, a_ptr, b_ptr, ...)                                             \
+  do {                                                                                                          \
+    if (use_vec<T>(C, a_ptr, b_ptr))                                                                            \
+      KERNEL<T, Vec<T>><<<vca_grid_1d((total_per_c) * (C / Vec<T>::N), 256), 256, 0, s>>>(__VA_ARGS__);         \
+    else                                                                                                        \
+      KERNEL<T, Vec1<T>><<<vca_grid_1d((total_per_c) * C, 256), 256, 0, s>>>(__VA_ARGS__);                      \
+    VCA_LAUNCH_CHECK();                                                                                         \
+  } while (0)
+
+#define TP(T, p) ((T*)(p))
+#define CTP(T, p) ((const T*)(p))
 
 extern "C" {
 
 int vca_maxpool3x3s2_fwd(int dtype, const void* x, void* y, unsigned char* idx, int NF, int H, int W, int C, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && idx && NF > 0 && H > 0 && W > 0 && C > 0);
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  unsigned grid = vca_grid_1d((long long)NF * OH * OW * C, 256, 2);
-  DISPATCH_T(dtype, (maxpool3x3s2_fwd_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, idx, NF, H, W, C, OH, OW)),
-             (maxpool3x3s2_fwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, idx, NF, H, W, C, OH, OW)));
-  VCA_LAUNCH_CHECK();
+  long long tot = (long long)NF * OH * OW;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(maxpool3x3s2_fwd_kernel, float, tot, x, y, CTP(float, x), TP(float, y), idx, NF, H, W, C, OH, OW);
+  else POOL_DISPATCH_T(maxpool3x3s2_fwd_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), idx, NF, H, W, C, OH, OW);
   return VCA_OK;
 }
 int vca_maxpool3x3s2_bwd(int dtype, const void* dy, const unsigned char* idx, void* dx, int NF, int H, int W, int C,
                          cudaStream_t s) {
   VCA_CHECK_ARG(dy && dx && idx && NF > 0 && H > 0 && W > 0 && C > 0);
   int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  unsigned grid = vca_grid_1d((long long)NF * H * W * C, 256, 2);
-  DISPATCH_T(dtype, (maxpool3x3s2_bwd_kernel<float><<<grid, 256, 0, s>>>((const float*)dy, idx, (float*)dx, NF, H, W, C, OH, OW)),
-             (maxpool3x3s2_bwd_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)dy, idx, (bf16*)dx, NF, H, W, C, OH, OW)));
-  VCA_LAUNCH_CHECK();
+  long long tot = (long long)NF * H * W;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(maxpool3x3s2_bwd_kernel, float, tot, dy, dx, CTP(float, dy), idx, TP(float, dx), NF, H, W, C, OH, OW);
+  else POOL_DISPATCH_T(maxpool3x3s2_bwd_kernel, bf16, tot, dy, dx, CTP(bf16, dy), idx, TP(bf16, dx), NF, H, W, C, OH, OW);
   return VCA_OK;
 }
 // y[NF, H/2, W/2, C] = scale * (2x2 block sums of x[NF,H,W,C])
 int vca_pool2x2_sum(int dtype, const void* x, void* y, int NF, int H, int W, int C, float scale, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && NF > 0 && H >= 2 && W >= 2 && C > 0);
   int OH = H / 2, OW = W / 2;
-  unsigned grid = vca_grid_1d((long long)NF * OH * OW * C, 256, 2);
-  DISPATCH_T(dtype, (pool2x2_sum_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, NF, H, W, C, OH, OW, scale)),
-             (pool2x2_sum_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, NF, H, W, C, OH, OW, scale)));
-  VCA_LAUNCH_CHECK();
+  long long tot = (long long)NF * OH * OW;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(pool2x2_sum_kernel, float, tot, x, y, CTP(float, x), TP(float, y), NF, H, W, C, OH, OW, scale);
+  else POOL_DISPATCH_T(pool2x2_sum_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), NF, H, W, C, OH, OW, scale);
   return VCA_OK;
 }
 // y[NF,H,W,C] = scale * x[NF,IH,IW,C] replicated 2x2 (zero where h/2>=IH or w/2>=IW)
@@ -147,25 +253,49 @@ int vca_expand2x2(int dtype, const void* x, void* y, int NF, int IH, int IW, int
                   cudaStream_t s) {
   VCA_CHECK_ARG(x && y && NF > 0 && IH > 0 && IW > 0 && C > 0 && H >= 2 * IH && W >= 2 * IW && H <= 2 * IH + 1 &&
                 W <= 2 * IW + 1);
-  unsigned grid = vca_grid_1d((long long)NF * H * W * C, 256, 2);
-  DISPATCH_T(dtype, (expand2x2_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, NF, IH, IW, C, H, W, scale)),
-             (expand2x2_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, NF, IH, IW, C, H, W, scale)));
-  VCA_LAUNCH_CHECK();
+  long long tot = (long long)NF * H * W;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(expand2x2_kernel, float, tot, x, y, CTP(float, x), TP(float, y), NF, IH, IW, C, H, W, scale);
+  else POOL_DISPATCH_T(expand2x2_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), NF, IH, IW, C, H, W, scale);
   return VCA_OK;
 }
 int vca_spatial_sum(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && NF > 0 && P > 0 && C > 0);
-  unsigned grid = vca_grid_1d((long long)NF * C, 128);
-  DISPATCH_T(dtype, (spatial_sum_kernel<float><<<grid, 128, 0, s>>>((const float*)x, (float*)y, NF, P, C, scale)),
-             (spatial_sum_kernel<bf16><<<grid, 128, 0, s>>>((const bf16*)x, (bf16*)y, NF, P, C, scale)));
-  VCA_LAUNCH_CHECK();
+  long long tot = NF;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(spatial_sum_kernel, float, tot, x, y, CTP(float, x), TP(float, y), NF, P, C, scale);
+  else POOL_DISPATCH_T(spatial_sum_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), NF, P, C, scale);
   return VCA_OK;
 }
 int vca_spatial_bcast(int dtype, const void* x, void* y, int NF, int P, int C, float scale, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && NF > 0 && P > 0 && C > 0);
-  unsigned grid = vca_grid_1d((long long)NF * P * C, 256, 2);
-  DISPATCH_T(dtype, (spatial_bcast_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, NF, P, C, scale)),
-             (spatial_bcast_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, NF, P, C, scale)));
+  long long tot = (long long)NF * P;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(spatial_bcast_kernel, float, tot, x, y, CTP(float, x), TP(float, y), NF, P, C, scale);
+  else POOL_DISPATCH_T(spatial_bcast_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), NF, P, C, scale);
+  return VCA_OK;
+}
+// x [NF,H,W,C] -> y [NF,H2,W2,4C] with H2 = OH+1, W2 = OW+1 for OH = (H-1)/2+1 (3x3/s2/p1 output size)
+int vca_s2d(int dtype, const void* x, void* y, int NF, int H, int W, int C, int H2, int W2, cudaStream_t s) {
+  VCA_CHECK_ARG(x && y && NF > 0 && H > 0 && W > 0 && C > 0 && 2 * H2 >= H + 1 && 2 * W2 >= W + 1);
+  long long tot = (long long)NF * H2 * W2 * 4;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(s2d_kernel, float, tot, x, y, CTP(float, x), TP(float, y), NF, H, W, C, H2, W2);
+  else POOL_DISPATCH_T(s2d_kernel, bf16, tot, x, y, CTP(bf16, x), TP(bf16, y), NF, H, W, C, H2, W2);
+  return VCA_OK;
+}
+int vca_d2s(int dtype, const void* y, void* x, int NF, int H, int W, int C, int H2, int W2, cudaStream_t s) {
+  VCA_CHECK_ARG(x && y && NF > 0 && H > 0 && W > 0 && C > 0 && 2 * H2 >= H + 1 && 2 * W2 >= W + 1);
+  long long tot = (long long)NF * H * W;
+  if (dtype == VCA_F32) POOL_DISPATCH_T(d2s_kernel, float, tot, y, x, CTP(float, y), TP(float, x), NF, H, W, C, H2, W2);
+  else POOL_DISPATCH_T(d2s_kernel, bf16, tot, y, x, CTP(bf16, y), TP(bf16, x), NF, H, W, C, H2, W2);
+  return VCA_OK;
+}
+// x: [NF,H,W] (Cin = 1) fp32 or bf16; y: [NF,OH,OW,64] in dt_out, OH = (H-1)/2+1.
+int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF, int H, int W, cudaStream_t s) {
+  VCA_CHECK_ARG(x && y && NF > 0 && H > 0 && W > 0);
+  int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  unsigned grid = vca_grid_1d(NF * OH * OW * 8, 256);
+  if (dt_in == VCA_F32 && dt_out == VCA_F32) stem_im2col_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, NF, H, W, OH, OW);
+  else if (dt_in == VCA_F32) stem_im2col_kernel<float, bf16><<<grid, 256, 0, s>>>((const float*)x, (bf16*)y, NF, H, W, OH, OW);
+  else if (dt_out == VCA_F32) stem_im2col_kernel<bf16, float><<<grid, 256, 0, s>>>((const bf16*)x, (float*)y, NF, H, W, OH, OW);
+  else stem_im2col_kernel<bf16, bf16><<<grid, 256, 0, s>>>((const bf16*)x, (bf16*)y, NF, H, W, OH, OW);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

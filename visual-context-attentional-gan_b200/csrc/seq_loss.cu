@@ -40,8 +40,8 @@ __global__ void gru_gate_fwd_kernel(const float* __restrict__ gi, const float* _
 // hprev_all: out tensor [T][B][ndir*H]; h_{t-1} for dir 0 is out[t-1], for dir 1 is out[t+1]; zero at the ends.
 __global__ void gru_gate_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dh_carry,
                                     const float* __restrict__ gates, const float* __restrict__ out,
-                                    float* __restrict__ dgi, float* __restrict__ dgh, int ndir, int T, int B, int H,
-                                    int step) {
+                                    float* __restrict__ dgi, float* __restrict__ dgh, float* __restrict__ dgh_cur,
+                                    int ndir, int T, int B, int H, int step) {
   long long total = (long long)ndir * B * H;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int j = (int)(i % H); long long r = i / H; int b = (int)(r % B); int d = (int)(r / B);
@@ -62,7 +62,56 @@ __global__ void gru_gate_bwd_kernel(const float* __restrict__ dout, float* __res
     long long go = (((long long)d * T + t) * B + b) * 3 * H;
     dgi[go + j] = dr_pre; dgi[go + H + j] = dz_pre; dgi[go + 2 * H + j] = dn_pre;
     dgh[go + j] = dr_pre; dgh[go + H + j] = dz_pre; dgh[go + 2 * H + j] = dn_pre * rr;
+    const long long cg = ((long long)d * B + b) * 3 * H;   // compact copy of this step's dgh for the recurrence GEMM
+    dgh_cur[cg + j] = dr_pre; dgh_cur[cg + H + j] = dz_pre; dgh_cur[cg + 2 * H + j] = dn_pre * rr;
     dh_carry[ci] = dh * zz;
+  }
+}
+
+// Skinny batched GEMM for the GRU recurrence (few rows, fp32, exact):  out[z,b,n] = beta*out[z,b,n] + sum_k in[z,b,k] * wt[z,n,k].
+// One CTA owns 8 output columns n for every row b: its 8 weight rows (8 x K) and a 32-row slab of `in` are staged
+// in shared memory (row stride K+4 floats: conflict-free 128-bit reads), threads = 8 (n) x 32 (b).
+constexpr int SK_N = 8, SK_B = 32, SK_KC = 512;
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(const float* __restrict__ in, const float* __restrict__ wt,
+                                                          float* __restrict__ out, int Bn, int N, int K, float beta) {
+  extern __shared__ float sk_smem[];
+  float* sW = sk_smem;                       // [SK_N][SK_KC]
+  float* sI = sk_smem + SK_N * SK_KC;        // [SK_B][SK_KC + 4]
+  const int z = blockIdx.y, n0 = blockIdx.x * SK_N;
+  const int jj = threadIdx.x >> 5, bb = threadIdx.x & 31;
+  const float* inz = in + (long long)z * Bn * K;
+  const float* wz = wt + (long long)z * N * K;
+  float* outz = out + (long long)z * Bn * N;
+  for (int b0 = 0; b0 < Bn; b0 += SK_B) {
+    float acc = 0.f;
+    for (int k0 = 0; k0 < K; k0 += SK_KC) {
+      const int kc = min(SK_KC, K - k0);   // multiple of 4 (checked on the host)
+      __syncthreads();
+      for (int i = threadIdx.x; i < SK_N * (kc >> 2); i += 256) {
+        const int r = i / (kc >> 2), c4 = i - r * (kc >> 2);
+        float4 v = make_float4(0, 0, 0, 0);
+        if (n0 + r < N) v = *reinterpret_cast<const float4*>(wz + (long long)(n0 + r) * K + k0 + c4 * 4);
+        *reinterpret_cast<float4*>(sW + r * SK_KC + c4 * 4) = v;
+      }
+      for (int i = threadIdx.x; i < SK_B * (kc >> 2); i += 256) {
+        const int r = i / (kc >> 2), c4 = i - r * (kc >> 2);
+        float4 v = make_float4(0, 0, 0, 0);
+        if (b0 + r < Bn) v = *reinterpret_cast<const float4*>(inz + (long long)(b0 + r) * K + k0 + c4 * 4);
+        *reinterpret_cast<float4*>(sI + r * (SK_KC + 4) + c4 * 4) = v;
+      }
+      __syncthreads();
+      const float4* w4 = reinterpret_cast<const float4*>(sW + jj * SK_KC);
+      const float4* i4 = reinterpret_cast<const float4*>(sI + bb * (SK_KC + 4));
+#pragma unroll 4
+      for (int k = 0; k < (kc >> 2); ++k) {
+        const float4 a = w4[k], h = i4[k];
+        acc = fmaf(a.x, h.x, acc); acc = fmaf(a.y, h.y, acc); acc = fmaf(a.z, h.z, acc); acc = fmaf(a.w, h.w, acc);
+      }
+    }
+    if (b0 + bb < Bn && n0 + jj < N) {
+      float* o = outz + (long long)(b0 + bb) * N + n0 + jj;
+      *o = beta != 0.f ? fmaf(beta, *o, acc) : acc;
+    }
   }
 }
 
@@ -322,11 +371,27 @@ int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const f
   return VCA_OK;
 }
 int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh,
-                     int ndir, int T, int B, int H, int step, cudaStream_t s) {
-  VCA_CHECK_ARG(dout && dh_carry && gates && out && dgi && dgh && ndir > 0 && T > 0 && B > 0 && H > 0 && step >= 0 &&
+                     float* dgh_cur, int ndir, int T, int B, int H, int step, cudaStream_t s) {
+  VCA_CHECK_ARG(dout && dh_carry && gates && out && dgi && dgh && dgh_cur && ndir > 0 && T > 0 && B > 0 && H > 0 && step >= 0 &&
                 step < T);
-  gru_gate_bwd_kernel<<<vca_grid_1d((long long)ndir * B * H, 128), 128, 0, s>>>(dout, dh_carry, gates, out, dgi, dgh, ndir, T,
+  gru_gate_bwd_kernel<<<vca_grid_1d((long long)ndir * B * H, 128), 128, 0, s>>>(dout, dh_carry, gates, out, dgi, dgh, dgh_cur, ndir, T,
                                                                                 B, H, step);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// out[z,b,n] = beta*out + sum_k in[z,b,k]*wt[z,n,k]; all fp32 contiguous; K % 4 == 0.  (GRU recurrence GEMMs.)
+int vca_skinny_gemm(const float* in, const float* wt, float* out, int Z, int Bn, int N, int K, float beta, cudaStream_t s) {
+  VCA_CHECK_ARG(in && wt && out && Z > 0 && Bn > 0 && N > 0 && K > 0 && K % 4 == 0);
+  static bool attr_set = false;
+  const size_t smem = (size_t)(SK_N * SK_KC + SK_B * (SK_KC + 4)) * sizeof(float);
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(skinny_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+      vca_set_error("cudaFuncSetAttribute(skinny_gemm_kernel) failed"); return VCA_ERR_CUDA;
+    }
+    attr_set = true;
+  }
+  dim3 grid((N + SK_N - 1) / SK_N, Z);
+  skinny_gemm_kernel<<<grid, 256, smem, s>>>(in, wt, out, Bn, N, K, beta);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
@@ -419,13 +484,4 @@ int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
-int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t s) {
-  VCA_CHECK_ARG(x && m && y && n > 0);
-  unsigned grid = vca_grid_1d(n, 256, 4);
-  DISPATCH_T(dtype, (mul_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (const float*)m, (float*)y, n)),
-             (mul_kernel<bf16><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)m, (bf16*)y, n)));
-  VCA_LAUNCH_CHECK();
-  return VCA_OK;
-}
-
 }  // extern "C"

@@ -1,0 +1,63 @@
+// 128-bit vector access helpers for the HBM-bound kernels: 4 x fp32 or 8 x bf16 per thread per access.
+#pragma once
+#include "common.cuh"
+
+template <class T> struct Vec;
+template <> struct Vec<float> {
+  static constexpr int N = 4;
+  __device__ static __forceinline__ void load(const float* p, float* v) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct Vec<bf16> {
+  static constexpr int N = 8;
+  __device__ static __forceinline__ void load(const bf16* p, float* v) {
+    const uint4 t = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[2 * i] = __uint_as_float(w[i] << 16);
+      v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(bf16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+static inline bool vca_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Launch shape for [R, C] row-major matrices processed as column-vectors of Vec<T>::N channels:
+// blockDim = (tx, ty): tx threads cover the CV = C / N column vectors (tiled by gridDim.y when CV > tx), ty rows.
+struct RowColGrid {
+  dim3 grid, block;
+};
+static inline RowColGrid row_col_grid(long long R, int CV, int max_row_blocks) {
+  int tx = 1;
+  while (tx < CV && tx < 64) tx <<= 1;
+  int ty = 256 / tx;
+  long long gx = (R + ty - 1) / ty;
+  if (gx > max_row_blocks) gx = max_row_blocks;
+  if (gx < 1) gx = 1;
+  RowColGrid g;
+  g.block = dim3(tx, ty);
+  g.grid = dim3((unsigned)gx, (unsigned)((CV + tx - 1) / tx));
+  return g;
+}
+
+// scalar "vector" so the same kernel template serves channel counts that are not a multiple of 4/8 (C = 1 mels)
+template <class T> struct Vec1 {
+  static constexpr int N = 1;
+  __device__ static __forceinline__ void load(const T* p, float* v) { v[0] = to_f(*p); }
+  __device__ static __forceinline__ void store(T* p, const float* v) { *p = from_f<T>(v[0]); }
+};

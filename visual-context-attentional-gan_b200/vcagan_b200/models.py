@@ -154,8 +154,12 @@ class Visual_front(nn.Module):
 
     def forward(self, x):
         B, _, T = x.shape[:3]
-        x = _in_cl(x)                                   # (B,T,112,112,1)
-        x = _conv(x, self.frontend[0])                  # (B,T,56,56,64)
+        c0 = self.frontend[0]
+        if (cfg.dtype == torch.bfloat16 and cfg.use_tc and self.in_channels == 1 and c0.kernel_size == (5, 7, 7)
+                and c0.stride == (1, 2, 2) and c0.padding == (2, 3, 3)):
+            x = ops.stem_conv(x, c0.weight)             # im2col(7x7) + (5,1) conv on the tcgen05 path
+        else:
+            x = _conv(_in_cl(x), c0)                    # generic exact path: (B,T,112,112,1) -> (B,T,56,56,64)
         x = ops.bn_act(x, self.frontend[1], ACT_PRELU, 0.0, self.frontend[2].weight)
         x = ops.maxpool3x3s2(x.view(B * T, x.shape[2], x.shape[3], x.shape[4]))   # (B*T,28,28,64)
         x = self.resnet(x)                              # (B*T,512)
@@ -166,7 +170,7 @@ class Visual_front(nn.Module):
         h = ops.gru_layer(phons_tb, self._gru_params(0))
         h = ops.dropout(h, float(self.sentence_encoder.dropout), self.training, gm)
         h = ops.gru_layer(h, self._gru_params(1))       # (T,B,1024)
-        s = ops.linear(h, self.fc.weight, self.fc.bias)  # (T,B,512)
+        s = ops.cast(ops.linear(ops.cast(h, cfg.dtype), self.fc.weight, self.fc.bias), torch.float32)  # (T,B,512)
         return x, s.permute(1, 2, 0).contiguous()
 
 
@@ -281,17 +285,17 @@ class AVAttention(nn.Module):
     def forward(self, ph, g, len):
         B, Fq, T, C = g.shape
         lens = _lens_tensor(len, g.device)
-        ph = ops.cast(ph, torch.float32)
-        k = ops.linear(ph, self.k.weight, self.k.bias)                       # (B,S,256)
-        v = ops.linear(ph, self.v.weight, self.v.bias)
-        gq = ops.cast(g.permute(0, 2, 3, 1).reshape(B, T, C * Fq), torch.float32)   # index c*F+f as in g.view(B,C*F,T)
-        q = ops.linear(gq, self.q.weight, self.q.bias)                       # (B,T,256)
-        att = ops.bmm(q, k.transpose(1, 2), 1.0 / math.sqrt(self.out_dim))   # (B,T,S)
+        f32 = torch.float32
+        ph = ops.cast(ph, cfg.dtype)                                         # projections run in the compute dtype
+        k = ops.cast(ops.linear(ph, self.k.weight, self.k.bias), f32)        # (B,S,256)
+        v = ops.cast(ops.linear(ph, self.v.weight, self.v.bias), f32)
+        gq = g.permute(0, 2, 3, 1).reshape(B, T, C * Fq)                     # index c*F+f as in g.view(B,C*F,T)
+        q = ops.cast(ops.linear(gq, self.q.weight, self.q.bias), f32)        # (B,T,256)
+        att = ops.bmm(q, k.transpose(1, 2), 1.0 / math.sqrt(self.out_dim))   # (B,T,S)  scores/softmax in fp32
         att = ops.masked_softmax(att, lens)
         val = ops.bmm(att, v)                                                # (B,T,256)
-        out = ops.linear(val, self.mel.weight, self.mel.bias)                # (B,T,1280)
-        out = out.view(B, T, Fq, -1).permute(0, 2, 1, 3).contiguous()        # channels-last (B,F,T,C')
-        return ops.cast(out, cfg.dtype)
+        out = ops.linear(ops.cast(val, cfg.dtype), self.mel.weight, self.mel.bias)   # (B,T,1280)
+        return out.view(B, T, Fq, -1).permute(0, 2, 1, 3).contiguous()       # channels-last (B,F,T,C')
 
 
 class Postnet(nn.Module):
@@ -450,8 +454,8 @@ class sync_Discriminator(nn.Module):
         a = ops.bn_act(_conv(a, f[3]), f[4], ACT_PRELU, 0.0, f[5].weight)
         a = self.Res_block[0](a)                                             # (B,20,S,256)
         B, Fq, S, C = a.shape
-        a = ops.cast(a.permute(0, 2, 3, 1).reshape(B, S, C * Fq), torch.float32)   # index c*F+f (generator.py:344)
-        a = ops.linear(a, self.Linear.weight, self.Linear.bias)              # (B,S,512)
+        a = a.permute(0, 2, 3, 1).reshape(B, S, C * Fq)                      # index c*F+f (generator.py:344)
+        a = ops.cast(ops.linear(a, self.Linear.weight, self.Linear.bias), torch.float32)   # (B,S,512)
         v = ops.cast(v_feat, torch.float32)
         if gen:
             return ops.CosAbsMeanFn.apply(v, a)

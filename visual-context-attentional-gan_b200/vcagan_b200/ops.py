@@ -242,7 +242,8 @@ class ColSumFn(Function):
         ctx.xshape, ctx.xdtype = tuple(x.shape), x.dtype
         C = x.shape[-1]
         out = torch.empty(C, dtype=torch.float32, device=x.device)
-        lib().call("vca_colsum", _dt(x), x, x.numel() // C, C, out)
+        scratch = torch.empty(C, dtype=torch.float64, device=x.device)
+        lib().call("vca_colsum", _dt(x), x, x.numel() // C, C, scratch, out)
         return out
 
     @staticmethod
@@ -253,8 +254,77 @@ class ColSumFn(Function):
         return SpatialBcastFn.apply(g.to(ctx.xdtype).view(1, -1), rows, 1.0).view(ctx.xshape)
 
 
+class S2DFn(Function):
+    """(N,H,W,C) -> (N,H2,W2,4C): zero-bordered space-to-depth, y[n,i,j,(pa*2+pb)*C+c] = x[n,2i+pa-1,2j+pb-1,c]."""
+
+    @staticmethod
+    def forward(ctx, x, H2, W2):
+        x = _c(x)
+        N, H, W, C = x.shape
+        ctx.hw = (H, W)
+        y = torch.empty((N, H2, W2, 4 * C), dtype=x.dtype, device=x.device)
+        lib().call("vca_s2d", _dt(x), x, y, N, H, W, C, H2, W2)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return D2SFn.apply(g, ctx.hw[0], ctx.hw[1]), None, None
+
+
+class D2SFn(Function):
+    """transpose of S2DFn: (N,H2,W2,4C) -> (N,H,W,C)."""
+
+    @staticmethod
+    def forward(ctx, y, H, W):
+        y = _c(y)
+        N, H2, W2, C4 = y.shape
+        ctx.hw2 = (H2, W2)
+        x = torch.empty((N, H, W, C4 // 4), dtype=y.dtype, device=y.device)
+        lib().call("vca_d2s", _dt(y), y, x, N, H, W, C4 // 4, H2, W2)
+        return x
+
+    @staticmethod
+    def backward(ctx, g):
+        return S2DFn.apply(g, ctx.hw2[0], ctx.hw2[1]), None, None
+
+
+def _conv3x3_s2_via_s2d(x, w, bias):
+    """3x3 / stride 2 / pad 1 conv as a 2x2 stride-1 conv over the space-to-depth input (4C channels), so that the
+    forward, dgrad and wgrad all run on the stride-1 tcgen05 kernels (resnet.py:33 with stride 2, generator.py:326).
+    W'[co, (pa*2+pb)*C + c, a, b] = w[co, c, 2a+pa, 2b+pb] (zero where the index is 3)."""
+    N, H, W, C = x.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    xs = S2DFn.apply(x, OH + 1, OW + 1)
+    Cout = w.shape[0]
+    wp = torch.nn.functional.pad(w, (0, 1, 0, 1))                      # (Cout, C, 4, 4)   [data movement]
+    w2 = wp.view(Cout, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 4 * C, 2, 2)
+    return ConvFn.apply(xs, w2, bias, (1, 1), (0, 0))
+
+
 def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
-    return ConvFn.apply(x, w, bias, tuple(stride), tuple(pad))
+    stride, pad = tuple(stride), tuple(pad)
+    if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0:
+        k = tuple(w.shape[2:])
+        if k == (3, 3) and pad == (1, 1) and x.shape[-1] >= 8:
+            return _conv3x3_s2_via_s2d(x, w, bias)
+        if k == (1, 1) and pad == (0, 0):
+            return ConvFn.apply(x[:, ::2, ::2, :].contiguous(), w, bias, (1, 1), (0, 0))   # slicing = data movement
+    return ConvFn.apply(x, w, bias, stride, pad)
+
+
+def stem_conv(vid, w):
+    """Visual front-end stem Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (visual_front.py:11) on the tcgen05 path:
+    a gather kernel unrolls the 7x7 spatial taps of the single input channel into 64 channels (49 used), the
+    remaining 5-tap temporal convolution is a (5,1) stride-1 conv over (T, 56*56).  vid: (B,1,T,H,W) fp32 -> (B,T,OH,OW,64)."""
+    B, _, T, H, W = vid.shape
+    OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    vid = _c(vid)
+    cols = torch.empty((B * T, OH, OW, 64), dtype=cfg.dtype, device=vid.device)
+    lib().call("vca_stem_im2col", _dt(vid), BF16 if cfg.dtype == torch.bfloat16 else F32, vid, cols, B * T, H, W)
+    Cout = w.shape[0]
+    w2 = torch.nn.functional.pad(w.view(Cout, 5, 49).permute(0, 2, 1), (0, 0, 0, 15)).unsqueeze(-1)   # (Cout,64,5,1)
+    y = ConvFn.apply(cols.view(B, T, OH * OW, 64), w2, None, (1, 1), (2, 0))
+    return y.view(B, T, OH, OW, Cout)
 
 
 def linear(x, w, bias=None):
@@ -810,77 +880,66 @@ def sum_sq(x, scale_=1.0):
 # ------------------------------------------------------------------------------------------------------------
 # GRU layer (bidirectional), fp32
 # ------------------------------------------------------------------------------------------------------------
-class GRULayerFn(Function):
-    """One bidirectional GRU layer: x (T,B,I) -> (T,B,2H).  Gate order r,z,n, b_hn inside the r-product
-    (torch.nn.GRU semantics, visual_front.py:20).  Weights: (w_ih, w_hh, b_ih, b_hh) for forward then reverse."""
+class GRURecurrenceFn(Function):
+    """Recurrent part of one bidirectional GRU layer (fp32, exact): gi (2,T,B,3H) = input projections incl. b_ih for
+    the forward and reverse direction -> out (T,B,2H).  Gate order r,z,n, b_hn inside the r-product (torch.nn.GRU,
+    visual_front.py:20).  Per time step: one skinny GEMM h @ W_hh^T (both directions in one launch) + one gate kernel."""
 
     @staticmethod
-    def forward(ctx, x, w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r):
-        _require_cuda(x)
-        x = _c(x.float())
-        T, B, I = x.shape
-        H = w_hh_f.shape[1]
-        dev = x.device
-        gi = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
-        x2 = x.view(T * B, I)
-        for d, (w, b) in enumerate(((w_ih_f, b_ih_f), (w_ih_r, b_ih_r))):
-            _gemm_raw(x2, w.detach().t(), gi[d].view(T * B, 3 * H), b.detach())
-        whh = torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0)   # (2,3H,H)
-        bhh = torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0)   # (2,3H)
+    def forward(ctx, gi, w_hh_f, b_hh_f, w_hh_r, b_hh_r):
+        _require_cuda(gi)
+        gi = _c(gi)
+        _, T, B, H3 = gi.shape
+        H = H3 // 3
+        dev = gi.device
+        whh = torch.stack([w_hh_f.detach(), w_hh_r.detach()], 0).contiguous()   # (2,3H,H)
+        bhh = torch.stack([b_hh_f.detach(), b_hh_r.detach()], 0).contiguous()   # (2,3H)
         out = torch.empty((T, B, 2 * H), dtype=torch.float32, device=dev)
         gates = torch.empty((2, T, B, 4 * H), dtype=torch.float32, device=dev)
-        h = torch.zeros((2, 2, B, H), dtype=torch.float32, device=dev)  # ping-pong
+        h = torch.zeros((2, 2, B, H), dtype=torch.float32, device=dev)          # ping-pong
         gh = torch.empty((2, B, 3 * H), dtype=torch.float32, device=dev)
-        whh_t = whh.transpose(1, 2)  # (2,H,3H) view
+        L = lib()
         for s in range(T):
             hp, hn = h[s & 1], h[(s + 1) & 1]
-            _gemm_raw(hp, whh_t, gh)
-            lib().call("vca_gru_gate_fwd", gi, gh, bhh, hp, hn, out, gates, 2, T, B, H, s)
-        ctx.save_for_backward(x, w_ih_f, w_ih_r, whh, out, gates)
+            L.call("vca_skinny_gemm", hp, whh, gh, 2, B, 3 * H, H, 0.0)
+            L.call("vca_gru_gate_fwd", gi, gh, bhh, hp, hn, out, gates, 2, T, B, H, s)
+        ctx.save_for_backward(whh, out, gates)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dout):
-        x, w_ih_f, w_ih_r, whh, out, gates = ctx.saved_tensors
+        whh, out, gates = ctx.saved_tensors
         dout = _c(dout.float())
-        T, B, I = x.shape
-        H = whh.shape[2]
-        dev = x.device
+        T, B, H2 = out.shape
+        H = H2 // 2
+        dev = out.device
         dgi = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
         dgh = torch.empty((2, T, B, 3 * H), dtype=torch.float32, device=dev)
         dh = torch.zeros((2, B, H), dtype=torch.float32, device=dev)
+        whh_t = whh.transpose(1, 2).contiguous()                                 # (2,H,3H): dh += dgh @ W_hh
+        cur = torch.empty((2, B, 3 * H), dtype=torch.float32, device=dev)
+        L = lib()
         for s in range(T):
-            lib().call("vca_gru_gate_bwd", dout, dh, gates, out, dgi, dgh, 2, T, B, H, s)
-            # dh += dgh[:, t_d] @ W_hh   (direction 0 is at t = T-1-s, direction 1 at t = s)
-            row = B * 3 * H
-            cur = dgh.as_strided((2, B, 3 * H), ((2 * s + 1) * row, 3 * H, 1), (T - 1 - s) * row)
-            _gemm_raw(cur, whh, dh, None, 1.0, 1.0)
-        x2 = x.view(T * B, I)
+            L.call("vca_gru_gate_bwd", dout, dh, gates, out, dgi, dgh, cur, 2, T, B, H, s)
+            L.call("vca_skinny_gemm", cur, whh_t, dh, 2, B, H, 3 * H, 1.0)
         grads = []
-        dx = torch.empty((T * B, I), dtype=torch.float32, device=dev)
-        for d, w_ih in enumerate((w_ih_f, w_ih_r)):
-            dgi_d = dgi[d].view(T * B, 3 * H)
-            dw_ih = torch.empty((3 * H, I), dtype=torch.float32, device=dev)
-            _gemm_raw(dgi_d.t(), x2, dw_ih)
-            db_ih = ColSumFn.apply(dgi_d)
-            # h_{t-1} of direction 0 is out[t-1,:, :H]; of direction 1 it is out[t+1,:, H:]
-            dw_hh = torch.empty((3 * H, H), dtype=torch.float32, device=dev)
-            if T > 1:
+        for d in range(2):
+            dw_hh = torch.zeros((3 * H, H), dtype=torch.float32, device=dev)
+            if T > 1:  # h_{t-1} of direction 0 is out[t-1,:, :H]; of direction 1 it is out[t+1,:, H:]
                 if d == 0:
-                    a = dgh[0, 1:].reshape((T - 1) * B, 3 * H)
-                    hprev = out[:T - 1, :, :H].reshape((T - 1) * B, H)
+                    a, hprev = dgh[0, 1:].reshape((T - 1) * B, 3 * H), out[:T - 1, :, :H].reshape((T - 1) * B, H)
                 else:
-                    a = dgh[1, :T - 1].reshape((T - 1) * B, 3 * H)
-                    hprev = out[1:, :, H:].reshape((T - 1) * B, H)
+                    a, hprev = dgh[1, :T - 1].reshape((T - 1) * B, 3 * H), out[1:, :, H:].reshape((T - 1) * B, H)
                 _gemm_raw(a.t(), hprev, dw_hh)
-            else:
-                dw_hh.zero_()
-            db_hh = ColSumFn.apply(dgh[d].view(T * B, 3 * H))
-            _gemm_raw(dgi_d, w_ih.detach(), dx, None, 1.0, 0.0 if d == 0 else 1.0)
-            grads += [dw_ih, dw_hh, db_ih, db_hh]
-        return (dx.view(T, B, I), *grads)
+            grads += [dw_hh, ColSumFn.apply(dgh[d].view(T * B, 3 * H))]
+        return (dgi, *grads)
 
 
 def gru_layer(x, params):
-    return GRULayerFn.apply(x, *params)
+    """One bidirectional GRU layer: x (T,B,I) fp32 -> (T,B,2H) fp32.  params = (w_ih, w_hh, b_ih, b_hh) forward then
+    reverse.  The input projections are ordinary linears (tcgen05 path in bf16 mode); the recurrence stays fp32."""
+    w_ih_f, w_hh_f, b_ih_f, b_hh_f, w_ih_r, w_hh_r, b_ih_r, b_hh_r = params
+    xc = cast(x, cfg.dtype)
+    gi = torch.stack([cast(linear(xc, w_ih_f, b_ih_f), torch.float32), cast(linear(xc, w_ih_r, b_ih_r), torch.float32)], 0)
+    return GRURecurrenceFn.apply(gi, w_hh_f, b_hh_f, w_hh_r, b_hh_r)
