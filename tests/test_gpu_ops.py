@@ -37,6 +37,7 @@ CONV_CASES = [
     (2, 12, 7, 7, 20, 1, 2, 0),
     (2, 20, 5, 9, 12, 5, 1, 0),
     (1, 70, 6, 37, 65, 3, 1, 1),
+    (2, 1, 16, 18, 16, 3, 2, 1),   # sync-discriminator stem: Cin = 1, stride 2 (dedicated Cin=1 dgrad kernel)
 ]
 
 

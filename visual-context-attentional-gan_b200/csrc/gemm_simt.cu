@@ -301,6 +301,66 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
   }
 }
 
+// dgrad of a Cin = 1 convolution (the mel inputs of the discriminators / sync discriminator: the R1 gradient and the
+// generator's adversarial gradient end here).  N = 1 makes it a per-pixel dot product of length taps*Cout, so the
+// tiled GEMM above would waste 63/64 of its tile: one thread per input pixel, weights broadcast from shared memory,
+// dY rows read with 128-bit loads.
+constexpr int CIN1_MAX_W = 8192;
+template <class T, int V>
+__global__ void __launch_bounds__(256) conv_cin1_dgrad_kernel(ConvGeom g, const T* __restrict__ dy, const T* __restrict__ wd,
+                                                              T* __restrict__ dx, long long M) {
+  __shared__ float sw[CIN1_MAX_W];
+  const int taps = g.KD * g.KH * g.KW;
+  for (int i = threadIdx.x; i < taps * g.Cout; i += blockDim.x) sw[i] = to_f(wd[i]);   // [tap][co]
+  __syncthreads();
+  for (long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x; m < M; m += (long long)gridDim.x * blockDim.x) {
+    long long mm = m;
+    const int iw = (int)(mm % g.IW); mm /= g.IW;
+    const int ih = (int)(mm % g.IH); mm /= g.IH;
+    const int id = (int)(mm % g.ID); const long long n = mm / g.ID;
+    float acc = 0.f;
+    for (int kd = 0; kd < g.KD; ++kd) {
+      const int td = id + g.pd - kd;
+      if (td < 0 || td % g.sd) continue;
+      const int od = td / g.sd;
+      if (od >= g.OD) continue;
+      for (int kh = 0; kh < g.KH; ++kh) {
+        const int th = ih + g.ph - kh;
+        if (th < 0 || th % g.sh) continue;
+        const int oh = th / g.sh;
+        if (oh >= g.OH) continue;
+        for (int kw = 0; kw < g.KW; ++kw) {
+          const int tw = iw + g.pw - kw;
+          if (tw < 0 || tw % g.sw) continue;
+          const int ow = tw / g.sw;
+          if (ow >= g.OW) continue;
+          const T* row = dy + (((n * g.OD + od) * g.OH + oh) * g.OW + ow) * (long long)g.Cout;
+          const float* wrow = sw + ((kd * g.KH + kh) * g.KW + kw) * g.Cout;
+          if (V > 1) {
+            for (int c = 0; c < g.Cout; c += V) {
+              float v[V > 1 ? V : 1];
+              if (V == 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(row + c);
+                const uint32_t u[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xffff0000u); }
+              } else {
+                const float4 t = *reinterpret_cast<const float4*>(row + c);
+                v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+              }
+#pragma unroll
+              for (int i = 0; i < V; ++i) acc = fmaf(v[i], wrow[c + i], acc);
+            }
+          } else {
+            for (int c = 0; c < g.Cout; ++c) acc = fmaf(to_f(row[c]), wrow[c], acc);
+          }
+        }
+      }
+    }
+    dx[m] = from_f<T>(acc);
+  }
+}
+
 }  // namespace
 
 static bool geom_ok(const ConvGeom& g) {
@@ -319,8 +379,17 @@ static int conv_fwd_t(const ConvGeom& g, const void* x, const void* wf, const fl
 }
 template <class T>
 static int conv_dgrad_t(const ConvGeom& g, const void* dy, const void* wd, void* dx, cudaStream_t s) {
-  ConvDgradP<T> p; p.g = g; p.dy = (const T*)dy; p.w = (const T*)wd; p.dx = (T*)dx;
   long long M = (long long)g.N * g.ID * g.IH * g.IW;
+  if (g.Cin == 1 && g.KD * g.KH * g.KW * g.Cout <= CIN1_MAX_W) {
+    constexpr int V = sizeof(T) == 2 ? 8 : 4;
+    const bool vec = g.Cout % V == 0 && ((reinterpret_cast<uintptr_t>(dy) & 15) == 0);
+    unsigned grid = vca_grid_1d(M, 256);
+    if (vec) conv_cin1_dgrad_kernel<T, V><<<grid, 256, 0, s>>>(g, (const T*)dy, (const T*)wd, (T*)dx, M);
+    else conv_cin1_dgrad_kernel<T, 1><<<grid, 256, 0, s>>>(g, (const T*)dy, (const T*)wd, (T*)dx, M);
+    VCA_LAUNCH_CHECK();
+    return VCA_OK;
+  }
+  ConvDgradP<T> p; p.g = g; p.dy = (const T*)dy; p.w = (const T*)wd; p.dx = (T*)dx;
   VCA_CHECK_ARG(M < (1ll << 31));
   p.M = (int)M; p.K = g.KD * g.KH * g.KW * g.Cout;
   return launch(p, p.M, g.Cin, 1, s);

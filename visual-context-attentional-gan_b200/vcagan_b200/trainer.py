@@ -91,6 +91,7 @@ class Trainer:
                  state: Optional[Dict[str, dict]] = None, dropout=True, process_group=None):
         ops.set_precision(precision)
         self.lrs = lrs
+        self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.device = torch.device(device)
         self.mods = dict(v_front=M.Visual_front(1), gen=M.Decoder(), post=M.Postnet(), dis1=M.Discriminator(phase='1'),
                          dis2=M.Discriminator(phase='2'), dis3=M.Discriminator(phase='3'), s_dis=M.sync_Discriminator(temp))
@@ -141,7 +142,12 @@ class Trainer:
         for d, x in zip(dis, reals):
             u, c = d(x, sdet, T)
             ur.append(u); cr.append(c)
-        sync_loss = s_dis(phon, reals[2]).mean()                           # phon NOT detached (train.py:186)
+        # phon is NOT detached in the reference (train.py:186): the sync loss sends a gradient into the visual
+        # front-end CNN during the D backward, and the G backward traverses that CNN a second time.  The CNN weights
+        # do not change in between, so we take d(dis_loss)/d(phon) here on a detached leaf and inject it into the
+        # single G-phase traversal below -- the same sum of the two gradients, one CNN backward instead of two.
+        phon_leaf = phon.detach().requires_grad_(True) if self.merge_vfront_backward else phon
+        sync_loss = s_dis(phon_leaf, reals[2]).mean()
         for u, x in zip(ur, reals):
             gr = torch.autograd.grad(u.sum(), x, create_graph=True)[0]     # R1 (train.py:188-194)
             gp.append(ops.sum_sq(gr, 1.0 / gr.size(0)))
@@ -153,7 +159,10 @@ class Trainer:
         fake_loss = sum(M.gan_loss(x, False) for x in uf + cf) / 3
         dis_loss = real_loss + fake_loss + (0.5 if self.lrs else 1.0) * sync_loss
         self.d_opt.zero_grad()
-        dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
+        if self.merge_vfront_backward:
+            dis_loss.backward(inputs=self.D.params + [phon_leaf])
+        else:
+            dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
         self._allreduce(self.D)
         self.d_opt.step(1.0 / self.world)
         # ---------------- G phase ----------------
@@ -167,7 +176,11 @@ class Trainer:
         k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
         recon = (ops.l1_mean(g[0], mel1, k) + ops.l1_mean(g[1], mel2, k) + ops.l1_mean(g[2], mel, k)) / 3 + ops.l1_mean(gs, spec)
         gen_loss = g_adv + g_sync + 50.0 * recon
-        gen_loss.backward(inputs=self.G.params)                            # D weight grads skipped (discarded in ref)
+        # D weight grads are skipped (the reference computes and discards them, train.py:235-236)
+        if self.merge_vfront_backward:
+            torch.autograd.backward([gen_loss, phon], [None, phon_leaf.grad], inputs=self.G.params)
+        else:
+            gen_loss.backward(inputs=self.G.params)
         self._allreduce(self.G)
         self.g_opt.step(1.0 / self.world)
         gen.fixed_noise = None
