@@ -46,7 +46,7 @@ def test_step_fp32_matches_reference(golden):
             assert e_mine <= max(1e-4, 3 * e_ref), (tag, e_mine, e_ref)
             big = float(torch.from_numpy(t64).max())
             bad = [(n, float(a), float(b)) for n, a, b, c in zip(names[key], mine, torch.from_numpy(t64), torch.from_numpy(r32))
-                   if float(b) > 1e-5 * big and abs(float(a) - float(b)) > max(1e-4 * float(b), 4 * abs(float(c) - float(b)) + 2e-4 * float(b))]
+                   if float(b) > 1e-5 * big and abs(float(a) - float(b)) > 5 * abs(float(c) - float(b)) + 1e-3 * float(b)]
             assert not bad, bad[:8]
         cn = json.load(open(os.path.join(GOLD, "checksum_names.json")))
         chk = torch.tensor([float(pd[n].detach().double().abs().sum()) for n in cn["params"]], dtype=torch.float64)

@@ -1,0 +1,73 @@
+#!/usr/bin/env python
+"""Micro-benchmark of the tcgen05 conv kernels on the layer shapes of the B=32, T=75 training step (CUDA events on
+the launching stream, L2 flushed between launches).  Used for the ncu captures under profiles/.
+    python tools/conv_shapes.py [--reps 5] [--only fwd|dgrad|wgrad]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "visual-context-attentional-gan_b200"))
+import torch
+import vcagan_b200 as V
+from vcagan_b200.ops import _geom, _packed
+from vcagan_b200._lib import lib
+
+SHAPES = [  # name, N, H, W, Cin, Cout, (kh,kw), (ph,pw)
+    ("gen.decode.0.conv1", 32, 20, 75, 640, 512, (5, 5), (2, 2)),
+    ("gen.decode.0.conv2", 32, 20, 75, 512, 512, (5, 5), (2, 2)),
+    ("gen.decode.2.conv2", 32, 20, 75, 256, 256, (5, 5), (2, 2)),
+    ("gen.g1.1.conv1", 32, 20, 75, 128, 128, (5, 5), (2, 2)),
+    ("gen.g2.1.conv1", 32, 40, 150, 64, 64, (5, 5), (2, 2)),
+    ("gen.g3.1.conv1", 32, 80, 300, 32, 32, (5, 5), (2, 2)),
+    ("resnet.layer1.conv", 2400, 28, 28, 64, 64, (3, 3), (1, 1)),
+    ("resnet.layer2.conv", 2400, 14, 14, 128, 128, (3, 3), (1, 1)),
+    ("resnet.layer3.conv", 2400, 7, 7, 256, 256, (3, 3), (1, 1)),
+    ("resnet.layer4.conv", 2400, 4, 4, 512, 512, (3, 3), (1, 1)),
+    ("v_front.stem(5,1)", 32, 75, 3136, 64, 64, (5, 1), (2, 0)),
+    ("dis3.cond.1", 32, 5, 18, 1024, 512, (5, 5), (2, 2)),
+    ("gru.proj(linear)", 2400, 1, 1, 1024, 1536, (1, 1), (0, 0)),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--filter", default="")
+    args = ap.parse_args()
+    V.set_precision("bf16")
+    dev = torch.device("cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rows = []
+    for name, N, H, W, Cin, Cout, k, p in SHAPES:
+        if args.filter and args.filter not in name:
+            continue
+        x = torch.randn(N, H, W, Cin, device=dev).bfloat16()
+        w = torch.nn.Parameter(torch.randn(Cout, Cin, *k, device=dev) / (Cin * k[0] * k[1]) ** 0.5)
+        g, oshape = _geom(x.shape, w.shape, (1, 1), p)
+        y = torch.empty(oshape, dtype=torch.bfloat16, device=dev)
+        dy = torch.randn(oshape, device=dev).bfloat16()
+        dx = torch.empty_like(x)
+        dw = torch.zeros_like(w)
+        wf, wd = _packed(w, torch.bfloat16)
+        flops = 2 * N * oshape[1] * oshape[2] * Cout * Cin * k[0] * k[1]
+        calls = dict(fwd=lambda: lib().call("vca_conv_fwd_tc", g, x, wd, None, y),
+                     dgrad=lambda: lib().call("vca_conv_dgrad_tc", g, dy, wf, dx),
+                     wgrad=lambda: lib().call("vca_conv_wgrad_tc", g, dy, x, dw))
+        for kind, fn in calls.items():
+            if args.only and kind != args.only:
+                continue
+            fn(); torch.cuda.synchronize()
+            ms = []
+            for _ in range(args.reps):
+                flush.zero_()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); fn(); b.record(); torch.cuda.synchronize()
+                ms.append(a.elapsed_time(b))
+            t = sorted(ms)[len(ms) // 2]
+            rows.append(dict(layer=name, kind=kind, ms=round(t, 4), tflops=round(flops / t / 1e9, 1), gflop=round(flops / 1e9, 2)))
+            print(f"{name:22s} {kind:6s} {t:8.3f} ms  {flops / t / 1e9:8.1f} TFLOP/s  ({flops / 1e9:.1f} GFLOP)", flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "conv_shapes.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
