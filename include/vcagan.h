@@ -84,6 +84,8 @@ int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF,
  *      (generator.py:347-359), gan_loss (generator.py:363-366), L1 (train.py:226-229), Adam (train.py:82-83) - */
 int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const float* hprev, float* hnext, float* out, float* gates, int ndir, int T, int B, int H, int step, cudaStream_t stream);
 int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh, float* dgh_cur, int ndir, int T, int B, int H, int step, cudaStream_t stream);
+int vca_gru_seq_fwd(const float* gi, const float* whh, const float* bhh, float* hbuf, float* out, float* gates, unsigned* bar, int ndir, int T, int B, int H, cudaStream_t stream);
+int vca_gru_seq_bwd(const float* dout, const float* whh, const float* gates, const float* out, float* dgi, float* dgh, float* dhc, float* dghc, float* dhz, unsigned* bar, int ndir, int T, int B, int H, cudaStream_t stream);
 int vca_skinny_gemm(const float* in, const float* wt, float* out, int Z, int Bn, int N, int K, float beta, cudaStream_t stream);
 int vca_masked_softmax_fwd(const float* x, float* p, const int* lens, int Z, int R, int S, cudaStream_t stream);
 int vca_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int S, cudaStream_t stream);

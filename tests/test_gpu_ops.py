@@ -266,9 +266,11 @@ def test_bn_act_pool(V):
     assert rel_l2(O.tanh(t.cuda()).cpu(), torch.tanh(t)) < 1e-6
 
 
-def test_gru_layer(V):
+@pytest.mark.parametrize("dims,persistent", [((7, 3, 20, 16), True), ((5, 40, 12, 24), True), ((7, 3, 20, 16), False)])
+def test_gru_layer(V, dims, persistent):
     g = torch.Generator().manual_seed(9)
-    T, B, I, H = 7, 3, 20, 16
+    T, B, I, H = dims
+    V.cfg.gru_persistent = persistent
     gru = torch.nn.GRU(I, H, 1, bidirectional=True)
     x = torch.randn(T, B, I, generator=g, requires_grad=True)
     y, _ = gru(x)
@@ -283,6 +285,7 @@ def test_gru_layer(V):
     assert rel_l2(xd.grad.cpu(), x.grad) < FP32_TOL
     for n, p in zip(names, ps):
         assert rel_l2(p.grad.cpu(), getattr(gru, n).grad) < 2e-4, n
+    V.cfg.gru_persistent = True
 
 
 def test_attention_and_losses(V):

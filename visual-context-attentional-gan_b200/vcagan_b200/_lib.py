@@ -94,6 +94,16 @@ class _Lib:
                 flops = 2 * args[7] * args[8] * args[9] * args[10]
             prof.append((name, tag, flops, e0, e1))
 
+    def try_call(self, name, *args):
+        """Like call(), but returns False (instead of raising) when the entry point reports VCA_ERR_UNSUPPORTED (-3)."""
+        try:
+            self.call(name, *args)
+            return True
+        except VcaError as e:
+            if "(-3)" in str(e):
+                return False
+            raise
+
     def profile_step(self, fn):
         """Run fn() with every library call bracketed by CUDA events on the launching stream.
         -> {entry point: {n, ms, flops, top: [(geometry, ms, TFLOP/s)]}}"""

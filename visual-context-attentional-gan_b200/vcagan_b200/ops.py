@@ -27,6 +27,7 @@ class Config:
     dtype = torch.float32
     use_tc = True          # use the tcgen05 kernels when dtype is bf16 and the geometry is supported
     skip_unneeded_wgrad = True
+    gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
 
 
 cfg = Config()
@@ -899,10 +900,14 @@ class GRURecurrenceFn(Function):
         h = torch.zeros((2, 2, B, H), dtype=torch.float32, device=dev)          # ping-pong
         gh = torch.empty((2, B, 3 * H), dtype=torch.float32, device=dev)
         L = lib()
-        for s in range(T):
-            hp, hn = h[s & 1], h[(s + 1) & 1]
-            L.call("vca_skinny_gemm", hp, whh, gh, 2, B, 3 * H, H, 0.0)
-            L.call("vca_gru_gate_fwd", gi, gh, bhh, hp, hn, out, gates, 2, T, B, H, s)
+        bar = torch.empty(1, dtype=torch.int32, device=dev)
+        if cfg.gru_persistent and L.try_call("vca_gru_seq_fwd", gi, whh, bhh, h, out, gates, bar, 2, T, B, H):
+            pass   # whole sequence in one cooperative launch
+        else:
+            for s in range(T):
+                hp, hn = h[s & 1], h[(s + 1) & 1]
+                L.call("vca_skinny_gemm", hp, whh, gh, 2, B, 3 * H, H, 0.0)
+                L.call("vca_gru_gate_fwd", gi, gh, bhh, hp, hn, out, gates, 2, T, B, H, s)
         ctx.save_for_backward(whh, out, gates)
         return out
 
@@ -920,9 +925,15 @@ class GRURecurrenceFn(Function):
         whh_t = whh.transpose(1, 2).contiguous()                                 # (2,H,3H): dh += dgh @ W_hh
         cur = torch.empty((2, B, 3 * H), dtype=torch.float32, device=dev)
         L = lib()
-        for s in range(T):
-            L.call("vca_gru_gate_bwd", dout, dh, gates, out, dgi, dgh, cur, 2, T, B, H, s)
-            L.call("vca_skinny_gemm", cur, whh_t, dh, 2, B, H, 3 * H, 1.0)
+        bar = torch.empty(1, dtype=torch.int32, device=dev)
+        dhc = torch.empty((2, 2, B, H), dtype=torch.float32, device=dev)
+        dhz = torch.empty((2, B, H), dtype=torch.float32, device=dev)
+        if cfg.gru_persistent and L.try_call("vca_gru_seq_bwd", dout, whh, gates, out, dgi, dgh, dhc, cur, dhz, bar, 2, T, B, H):
+            pass
+        else:
+            for s in range(T):
+                L.call("vca_gru_gate_bwd", dout, dh, gates, out, dgi, dgh, cur, 2, T, B, H, s)
+                L.call("vca_skinny_gemm", cur, whh_t, dh, 2, B, H, 3 * H, 1.0)
         grads = []
         for d in range(2):
             dw_hh = torch.zeros((3 * H, H), dtype=torch.float32, device=dev)
