@@ -35,6 +35,7 @@ typedef struct ConvGeom {
 const char* vca_last_error();
 int vca_abi_version();
 int vca_device_ok();
+int vca_set_option(const char* key, int value);
 
 /* ---- convolutions (nn.Conv1d/2d/3d: visual_front.py:11, resnet.py:5-14, generator.py:19-25,62-66,103-108,
  *      177-185,204-225,272-300,323-327) and their autograd (aten::convolution_backward) ------------------- */

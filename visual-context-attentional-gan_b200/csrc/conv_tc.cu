@@ -19,6 +19,10 @@
 #include "common.cuh"
 #include <cuda.h>
 
+// conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
+int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
+                const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
+
 namespace {
 
 constexpr int KC = 64;              // bf16 channels per K chunk = 128 B = one SWIZZLE_128B row
@@ -120,7 +124,8 @@ struct FwdParams {
   int tiles_w, tiles_h;          // tile counts along W and H (tiles along NF = gridDim.x / (tiles_w*tiles_h))
   int KH, KW, ph, pw;            // input coord = output coord + k - p
   int kchunks;                   // ceil(Kdim / 64)
-  int BN;                        // output channels per CTA (multiple of 16, <= 256)
+  int ksteps_last;               // 16-channel MMA steps in the last K chunk (4 unless Kdim % 64 != 0)
+  int BN;                      // output channels per CTA (multiple of 16, <= 256)
   int stages;
   int flip;                      // 1: weight tap index is mirrored (dgrad)
   uint32_t a_bytes, b_bytes;     // bytes the two TMA loads of one stage deliver
@@ -180,17 +185,21 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_ROWS, p.BN, 0, 0);
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0, kcur = 0; uint32_t phase = 0;
       for (int it = 0; it < iters; ++it) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
         const uint32_t b0 = smem_u32(sB + (size_t)stage * b_stage);
+        const int ksteps = (kcur == p.kchunks - 1) ? p.ksteps_last : KC / 16;   // skip the zero-padded tail of a K chunk
+        if (++kcur == p.kchunks) kcur = 0;
 #pragma unroll
         for (int k = 0; k < KC / 16; ++k) {
-          const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
-          const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
-          umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          if (k < ksteps) {
+            const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
+            const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
+            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+          }
         }
         umma_commit(&empty[stage]);  // implies tcgen05.fence::before_thread_sync
         if (++stage == S) { stage = 0; phase ^= 1; }
@@ -414,6 +423,10 @@ uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return 
 
 int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
              const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s) {
+  {
+    const int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   FwdParams p;
   p.NF = NF; p.OH = OH; p.OW = OW; p.Cout = Nout;
   choose_box(NF, OH, OW, p.tn, p.th, p.tw);
@@ -421,6 +434,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   int tiles_n = (NF + p.tn - 1) / p.tn;
   p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw; p.flip = flip;
   p.kchunks = (Kdim + KC - 1) / KC;
+  p.ksteps_last = (Kdim - (p.kchunks - 1) * KC + 15) / 16;
   int bn = Nout >= 256 ? 256 : ((Nout + 15) / 16) * 16;
   // keep >= ~1 wave of CTAs when the problem is small: halve BN
   long long ptiles = (long long)p.tiles_w * p.tiles_h * tiles_n;

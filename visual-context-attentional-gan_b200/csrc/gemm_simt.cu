@@ -31,11 +31,11 @@ __global__ void __launch_bounds__(NT) gemm_core(P p) {
   else if (tid < BM + BN) ni[tid - BM] = p.ninfo(n0 + tid - BM, z);
   __syncthreads();
 
-  float acc[4][4];
+  float acc[4][4], comp[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = comp[i][j] = 0.f;
 
   const int tx = tid & 15, ty = tid >> 4;
 
@@ -76,6 +76,14 @@ __global__ void __launch_bounds__(NT) gemm_core(P p) {
       }
     }
     __syncthreads();
+    // two-level accumulation: a fresh partial sum per K tile, folded into the running sum afterwards.  Keeps the
+    // fp32 rounding error of long reductions (K up to 16 000 taps*channels, or 1e5 pixels in wgrad) at the level of
+    // a blocked CPU summation instead of growing like sqrt(K).
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
@@ -85,8 +93,17 @@ __global__ void __launch_bounds__(NT) gemm_core(P p) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // Kahan-compensated fold of the tile partial
+        const float y = part[i][j] - comp[i][j];
+        const float t = acc[i][j] + y;
+        comp[i][j] = (t - acc[i][j]) - y;
+        acc[i][j] = t;
+      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
