@@ -104,3 +104,38 @@ def test_second_step_runs_and_changes_weights():
         assert float(l2["recon"]) < float(l1["recon"]) + 0.5
     finally:
         V.set_precision("fp32")
+
+
+def test_graph_replay_matches_eager():
+    """The CUDA-graph replay of the step (3 graphs, device-resident Adam step counters) must reproduce the eager step."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    vid, mel, sp, noise = golden_inputs()
+    lens = torch.tensor([20, 13], dtype=torch.int32).cuda()
+    try:
+        outs = []
+        for graphed in (False, True):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision="fp32", state=state, dropout=False)
+            args = (vid.cuda(), mel.cuda(), sp.cuda(), lens)
+            if graphed:
+                tr.capture(*args, warmup=2, noise=noise)
+                for _ in range(2):
+                    out = tr.replay()
+            else:
+                for _ in range(4):
+                    out = tr.step(*args, noise=noise)
+            torch.cuda.synchronize()
+            outs.append((tr.G.flat.clone(), tr.D.flat.clone(), {k: v.clone() for k, v in out.items() if torch.is_tensor(v)},
+                         tr.g_opt.t, tr.d_opt.t))
+            del tr
+        (g0, d0, o0, tg0, td0), (g1, d1, o1, tg1, td1) = outs
+        assert tg0 == tg1 == 4 and td0 == td1 == 4
+        assert rel_l2(g1.cpu(), g0.cpu()) < 1e-5 and rel_l2(d1.cpu(), d0.cpu()) < 1e-5
+        # weights moved: 4 Adam steps of lr 1e-4
+        for k in ("gen_loss", "dis_loss", "recon"):
+            assert abs(float(o0[k]) - float(o1[k])) <= 5e-4 * max(1.0, abs(float(o0[k]))), (k, float(o0[k]), float(o1[k]))
+        assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 1e-3
+    finally:
+        V.set_precision("fp32")

@@ -294,7 +294,12 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 //   p -= lr/bc1 * m / (sqrt(vmax)/sqrt(bc2) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             float* __restrict__ vmax, long long n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float gscale) {
+                            float bc1, float bc2_sqrt, float gscale, const int* __restrict__ step_dev) {
+  if (step_dev) {   // step count lives on the device (CUDA-graph replay): bias corrections computed here
+    const float t = (float)(*step_dev);
+    bc1 = 1.f - powf(b1, t);
+    bc2_sqrt = sqrtf(1.f - powf(b2, t));
+  }
   float step = lr / bc1;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float pi = p[i];
@@ -325,7 +330,8 @@ __device__ __forceinline__ float u01(unsigned x) { return ((float)(x >> 8) + 0.5
 // mode 0: standard normal (Box-Muller); mode 1: dropout keep-mask scaled by 1/(1-p) (param = p)
 template <class T>
 __global__ void rng_kernel(T* __restrict__ out, long long n, unsigned long long seed, unsigned long long offset, int mode,
-                           float param) {
+                           float param, const unsigned long long* __restrict__ ctr_dev) {
+  if (ctr_dev) offset += *ctr_dev;   // device-resident stream position (advanced by counter_add_kernel): graph-replay safe
   long long nq = (n + 3) / 4;
   for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq; q += (long long)gridDim.x * blockDim.x) {
     unsigned long long c = (unsigned long long)q + offset;
@@ -347,6 +353,9 @@ __global__ void rng_kernel(T* __restrict__ out, long long n, unsigned long long 
     for (int k = 0; k < 4; ++k) if (q * 4 + k < n) out[q * 4 + k] = from_f<T>(o[k]);
   }
 }
+
+__global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }
+__global__ void counter_add_i32_kernel(int* ctr, int inc) { *ctr += inc; }
 
 // y = x * mask  (elementwise, same dtype)
 template <class T>
@@ -471,7 +480,18 @@ int vca_adam_step(float* p, const float* g, float* m, float* v, float* vmax, lon
   float bc1 = 1.f - powf(beta1, (float)step);
   float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                                     gscale);
+                                                     gscale, nullptr);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// Same, with the step counter resident on the device: *step_dev is incremented, then used for the bias corrections.
+// This form can be captured in a CUDA graph and replayed (the host never sees the step number).
+int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, int* step_dev, float gscale, cudaStream_t s) {
+  VCA_CHECK_ARG(p && g && m && v && n > 0 && step_dev);
+  counter_add_i32_kernel<<<1, 1, 0, s>>>(step_dev, 1);
+  adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, gscale,
+                                                     step_dev);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
@@ -479,8 +499,20 @@ int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned
             cudaStream_t s) {
   VCA_CHECK_ARG(out && n > 0 && (mode == 0 || (mode == 1 && param >= 0.f && param < 1.f)));
   unsigned grid = vca_grid_1d((n + 3) / 4, 256);
-  DISPATCH_T(dtype, (rng_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, offset, mode, param)),
-             (rng_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)out, n, seed, offset, mode, param)));
+  DISPATCH_T(dtype, (rng_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, offset, mode, param, nullptr)),
+             (rng_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)out, n, seed, offset, mode, param, nullptr)));
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// Same, with the Philox stream position resident on the device (*ctr_dev, advanced here by ceil(n/4)): replaying a
+// captured graph draws fresh numbers every time.
+int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsigned long long* ctr_dev, int mode, float param,
+                cudaStream_t s) {
+  VCA_CHECK_ARG(out && ctr_dev && n > 0 && (mode == 0 || (mode == 1 && param >= 0.f && param < 1.f)));
+  unsigned grid = vca_grid_1d((n + 3) / 4, 256);
+  DISPATCH_T(dtype, (rng_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, 0ull, mode, param, ctr_dev)),
+             (rng_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)out, n, seed, 0ull, mode, param, ctr_dev)));
+  counter_add_kernel<<<1, 1, 0, s>>>(ctr_dev, (unsigned long long)((n + 3) / 4));
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

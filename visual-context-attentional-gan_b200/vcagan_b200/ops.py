@@ -523,18 +523,25 @@ class MulFn(Function):
         return MulFn.apply(g, mask), None
 
 
-_rng_state = {"seed": 0x5EED, "offset": 0}
+_rng_state = {"seed": 0x5EED, "ctr": {}}
 
 
 def manual_seed(seed: int):
-    _rng_state["seed"], _rng_state["offset"] = int(seed), 0
+    """Seed of the device Philox streams; the stream position is a device-resident counter per GPU, so draws stay
+    fresh when the step is replayed from a CUDA graph."""
+    _rng_state["seed"] = int(seed)
+    for c in _rng_state["ctr"].values():
+        c.zero_()
 
 
 def _rng(shape, dtype, device, mode, param=0.0):
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ctr = _rng_state["ctr"].get(key)
+    if ctr is None:
+        ctr = _rng_state["ctr"][key] = torch.zeros(1, dtype=torch.int64, device=device)
     out = torch.empty(shape, dtype=dtype, device=device)
-    n = out.numel()
-    lib().call("vca_rng", BF16 if dtype == torch.bfloat16 else F32, out, n, _rng_state["seed"], _rng_state["offset"], mode, float(param))
-    _rng_state["offset"] += (n + 3) // 4
+    lib().call("vca_rng_dev", BF16 if dtype == torch.bfloat16 else F32, out, out.numel(), _rng_state["seed"], ctr, mode, float(param))
     return out
 
 

@@ -61,15 +61,18 @@ class FusedAdam:
         self.m = torch.zeros_like(group.flat)
         self.v = torch.zeros_like(group.flat)
         self.vmax = torch.zeros_like(group.flat) if amsgrad else None
-        self.t = 0
+        self.t_dev = torch.zeros(1, dtype=torch.int32, device=group.flat.device)   # step count lives on the device
+
+    @property
+    def t(self):
+        return int(self.t_dev.item())
 
     def zero_grad(self):
         self.g.zero_grad()
 
     def step(self, grad_scale: float = 1.0):
-        self.t += 1
-        lib().call("vca_adam_step", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr, self.betas[0],
-                   self.betas[1], self.eps, self.wd, self.t, grad_scale)
+        lib().call("vca_adam_step_dev", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr, self.betas[0],
+                   self.betas[1], self.eps, self.wd, self.t_dev, grad_scale)
         self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
 
 
@@ -125,8 +128,16 @@ class Trainer:
     # -- one step -------------------------------------------------------------------------------------------------
     def step(self, vid, mel, spec, vid_len, noise=None):
         """vid (B,1,T,112,112), mel (B,1,80,4T), spec (B,1,321,4T) device fp32; vid_len int32 device tensor or list."""
+        self._phase_d(vid, mel, spec, vid_len, noise)
+        self._allreduce(self.D)
+        self._phase_g()
+        self._allreduce(self.G)
+        return self._phase_end()
+
+    def _phase_d(self, vid, mel, spec, vid_len, noise=None):
+        """forward of v_front + generator, the whole D phase and its backward (train.py:168-210)."""
         m = self.mods
-        v_front, gen, post = m["v_front"], m["gen"], m["post"]
+        v_front, gen = m["v_front"], m["gen"]
         dis = (m["dis1"], m["dis2"], m["dis3"])
         s_dis = m["s_dis"]
         gen.fixed_noise = noise
@@ -134,10 +145,10 @@ class Trainer:
         mel1, mel2 = bilinear_down(mel, 4), bilinear_down(mel, 2)          # train.py:170-171
         phon, sent = v_front(vid)
         g = gen(sent, phon, vid_len)                                       # g1, g2, g3
+        gen.fixed_noise = None
         T = phon.size(1)
         sdet = sent.detach()
         reals = [t.detach().requires_grad_(True) for t in (mel1, mel2, mel)]
-        # ---------------- D phase ----------------
         ur, cr, gp = [], [], []
         for d, x in zip(dis, reals):
             u, c = d(x, sdet, T)
@@ -163,31 +174,80 @@ class Trainer:
             dis_loss.backward(inputs=self.D.params + [phon_leaf])
         else:
             dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
-        self._allreduce(self.D)
+        self._st = dict(mel=mel, mel1=mel1, mel2=mel2, spec=spec, phon=phon, phon_leaf=phon_leaf, sdet=sdet, g=g, T=T,
+                        out=dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
+                                 fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp])))
+
+    def _phase_g(self):
+        """D optimizer step, then the G phase against the updated discriminators and its backward (train.py:211-236)."""
+        st, m = self._st, self.mods
+        dis = (m["dis1"], m["dis2"], m["dis3"])
+        g, sdet, T, phon = st["g"], st["sdet"], st["T"], st["phon"]
         self.d_opt.step(1.0 / self.world)
-        # ---------------- G phase ----------------
-        gs = post(g[2])
+        gs = m["post"](g[2])
         ug, cg = [], []
         for d, x in zip(dis, g):
             u, c = d(x, sdet, T)
             ug.append(u); cg.append(c)
-        g_sync = s_dis(phon.detach(), g[2], True).mean()
+        g_sync = m["s_dis"](phon.detach(), g[2], True).mean()
         g_adv = sum(M.gan_loss(x, True) for x in ug + cg) / 3
         k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
-        recon = (ops.l1_mean(g[0], mel1, k) + ops.l1_mean(g[1], mel2, k) + ops.l1_mean(g[2], mel, k)) / 3 + ops.l1_mean(gs, spec)
+        recon = (ops.l1_mean(g[0], st["mel1"], k) + ops.l1_mean(g[1], st["mel2"], k) + ops.l1_mean(g[2], st["mel"], k)) / 3 \
+            + ops.l1_mean(gs, st["spec"])
         gen_loss = g_adv + g_sync + 50.0 * recon
         # D weight grads are skipped (the reference computes and discards them, train.py:235-236)
         if self.merge_vfront_backward:
-            torch.autograd.backward([gen_loss, phon], [None, phon_leaf.grad], inputs=self.G.params)
+            torch.autograd.backward([gen_loss, phon], [None, st["phon_leaf"].grad], inputs=self.G.params)
         else:
             gen_loss.backward(inputs=self.G.params)
-        self._allreduce(self.G)
+        st["out"].update(gen_loss=gen_loss.detach(), g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(),
+                         g2=g[1].detach(), g3=g[2].detach(), gs=gs.detach())
+
+    def _phase_end(self):
         self.g_opt.step(1.0 / self.world)
-        gen.fixed_noise = None
-        return dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
-                    fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp]), gen_loss=gen_loss.detach(),
-                    g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(), g2=g[1].detach(), g3=g[2].detach(),
-                    gs=gs.detach(), r1_grad3=None)
+        out, self._st = self._st["out"], None
+        return out
+
+    # -- CUDA-graph replay of the step ----------------------------------------------------------------------------
+    def capture(self, vid, mel, spec, vid_len, warmup=3, noise=None):
+        """Capture the step into three CUDA graphs (D phase | G phase | G optimizer) sharing one memory pool; the
+        gradient all-reduces run between them.  Everything that changes from step to step lives in device memory
+        (Adam step counters, Philox stream positions, BN buffers), so `replay` needs no host-side state.
+        `vid_len` must be an int32 device tensor.  Inputs are copied into static buffers on every replay."""
+        assert torch.is_tensor(vid_len) and vid_len.is_cuda, "vid_len must be a device tensor for graph capture"
+        self._sin = [t.clone() for t in (vid, mel, spec)] + [vid_len.to(torch.int32).clone()]
+        self._snoise = None if noise is None else noise.to(self.device).clone()   # parity tests only
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.step(*self._sin, noise=self._snoise)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        ops.clear_pack_cache()            # every weight (re)pack must be recorded inside the graphs
+        pool = torch.cuda.graph_pool_handle()
+        self._graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
+        n0 = lib().launches
+        with torch.cuda.graph(self._graphs[0], pool=pool):
+            self._phase_d(*self._sin, noise=self._snoise)
+        with torch.cuda.graph(self._graphs[1], pool=pool):
+            self._phase_g()
+        with torch.cuda.graph(self._graphs[2], pool=pool):
+            self._sout = self._phase_end()
+        self.launches_per_step = lib().launches - n0
+        return self
+
+    def replay(self, vid=None, mel=None, spec=None, vid_len=None):
+        """One training step from the captured graphs; new inputs (host-pinned or device) are copied into the static buffers."""
+        for dst, src in zip(self._sin, (vid, mel, spec, vid_len)):
+            if src is not None:
+                dst.copy_(src, non_blocking=True)
+        self._graphs[0].replay()
+        self._allreduce(self.D)
+        self._graphs[1].replay()
+        self._allreduce(self.G)
+        self._graphs[2].replay()
+        return self._sout
 
     def _vf_cnn_params(self):
         vf = self.mods["v_front"]
