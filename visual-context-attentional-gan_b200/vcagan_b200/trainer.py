@@ -15,6 +15,7 @@ from typing import Dict, Iterable, List, Optional
 import torch
 import torch.nn as nn
 
+from . import dp
 from . import models as M
 from . import ops
 from ._lib import lib
@@ -121,8 +122,7 @@ class Trainer:
         cur = torch.cuda.current_stream()
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            for s in range(0, group.numel, bucket_elems):
-                torch.distributed.all_reduce(group.grad[s:s + bucket_elems], group=self.pg)
+            dp.allreduce_flat(group.grad, self.pg, bucket_elems)
         cur.wait_stream(self.comm_stream)
 
     # -- one step -------------------------------------------------------------------------------------------------
