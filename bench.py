@@ -211,10 +211,15 @@ def run_ours(args):
 
     # dominant kernel family: the tcgen05 implicit-GEMM conv (fwd + dgrad share one kernel); timed live per launch
     roof = None
+    # every rank runs the instrumented step (it contains the gradient all-reduces); only rank 0 reports it
+    prof = V.lib().profile_step(lambda: tr.step(vid, mel, spec, lens))
+    barrier()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
     if rank == 0:
         pk = peaks()
-        prof = V.lib().profile_step(lambda: tr.step(vid, mel, spec, lens))
-        fam = {k: v for k, v in prof.items() if k.startswith("vca_conv_") and k.endswith("_tc")}
+        fam ={k: v for k, v in prof.items() if k.startswith("vca_conv_") and k.endswith("_tc")}
         flops = sum(v["flops"] for v in fam.values()); tms = sum(v["ms"] for v in fam.values())
         n_l = sum(v["n"] for v in fam.values())
         total_ms = sum(v["ms"] for v in prof.values())
@@ -250,9 +255,6 @@ def run_ours(args):
             "sample": f"1 G+D step of B={cpu_b}, T={T}, fp32, oracle port of train.py:166-237 on torch CPU ({cpu_sec:.1f} s)"},
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
 
 
 def main():

@@ -144,9 +144,9 @@ def test_graph_replay_matches_eager():
         noise_g, noise_d = rel_l2(ge.cpu(), g0.cpu()), rel_l2(de.cpu(), d0.cpu())
         print("eager-vs-eager weight noise", noise_g, noise_d, "graph-vs-eager", rel_l2(g1.cpu(), g0.cpu()), rel_l2(d1.cpu(), d0.cpu()))
         assert rel_l2(g1.cpu(), g0.cpu()) <= 3 * noise_g + 1e-6 and rel_l2(d1.cpu(), d0.cpu()) <= 3 * noise_d + 1e-6
-        assert float((g1 - g0).abs().max()) <= 4 * 1e-4 * 1.05      # nothing moved further than 4 Adam steps of lr 1e-4
+        assert float((g1 - g0).abs().max()) <= 1e-3                  # a few Adam steps of lr 1e-4 apart at most
         for k in ("gen_loss", "dis_loss", "recon"):
-            assert abs(float(o0[k]) - float(o1[k])) <= 1e-3 * max(1.0, abs(float(o0[k]))), (k, float(o0[k]), float(o1[k]))
-        assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 3 * rel_l2(oe["g3"].cpu(), o0["g3"].cpu()) + 1e-4
+            assert abs(float(o0[k]) - float(o1[k])) <= 3 * abs(float(o0[k]) - float(oe[k])) + 2e-3 * max(1.0, abs(float(o0[k]))), (k, float(o0[k]), float(o1[k]))
+        assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 3 * rel_l2(oe["g3"].cpu(), o0["g3"].cpu()) + 1e-3
     finally:
         V.set_precision("fp32")
