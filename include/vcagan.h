@@ -104,6 +104,10 @@ int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned
 int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int* step_dev, float gscale, cudaStream_t stream);
 int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsigned long long* ctr_dev, int mode, float param, cudaStream_t stream);
 
+/* ---- Griffin-Lim STFT / ISTFT (src/data/stft.py:70-129, src/data/audio_processing.py:51-68) ---------------------- */
+int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float* mag_t, float* frames, float* spec_out, int B, int T, int L, cudaStream_t stream);
+int vca_gl_ola(const float* frames, float* sig_out, int B, int T, int L, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

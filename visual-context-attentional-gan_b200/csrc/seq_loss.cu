@@ -344,6 +344,9 @@ __global__ void rng_kernel(T* __restrict__ out, long long n, unsigned long long 
       __sincosf(6.2831853071795865f * u1, &s0, &c0);
       __sincosf(6.2831853071795865f * u3, &s1, &c1);
       o[0] = ra * c0; o[1] = ra * s0; o[2] = rb * c1; o[3] = rb * s1;
+    } else if (mode == 2) {   // uniform angle in (-pi, pi): Griffin-Lim initial phase (audio_processing.py:59)
+      o[0] = 6.2831853071795865f * u01(r.x) - 3.14159265358979f; o[1] = 6.2831853071795865f * u01(r.y) - 3.14159265358979f;
+      o[2] = 6.2831853071795865f * u01(r.z) - 3.14159265358979f; o[3] = 6.2831853071795865f * u01(r.w) - 3.14159265358979f;
     } else {
       float keep = 1.f / (1.f - param);
       o[0] = u01(r.x) >= param ? keep : 0.f; o[1] = u01(r.y) >= param ? keep : 0.f;
@@ -508,7 +511,7 @@ int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned
 // captured graph draws fresh numbers every time.
 int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsigned long long* ctr_dev, int mode, float param,
                 cudaStream_t s) {
-  VCA_CHECK_ARG(out && ctr_dev && n > 0 && (mode == 0 || (mode == 1 && param >= 0.f && param < 1.f)));
+  VCA_CHECK_ARG(out && ctr_dev && n > 0 && (mode == 0 || mode == 2 || (mode == 1 && param >= 0.f && param < 1.f)));
   unsigned grid = vca_grid_1d((n + 3) / 4, 256);
   DISPATCH_T(dtype, (rng_kernel<float><<<grid, 256, 0, s>>>((float*)out, n, seed, 0ull, mode, param, ctr_dev)),
              (rng_kernel<bf16><<<grid, 256, 0, s>>>((bf16*)out, n, seed, 0ull, mode, param, ctr_dev)));
