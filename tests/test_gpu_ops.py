@@ -37,8 +37,34 @@ CONV_CASES = [
     (2, 12, 7, 7, 20, 1, 2, 0),
     (2, 20, 5, 9, 12, 5, 1, 0),
     (1, 70, 6, 37, 65, 3, 1, 1),
-    (2, 1, 16, 18, 16, 3, 2, 1),   # sync-discriminator stem: Cin = 1, stride 2 (dedicated Cin=1 dgrad kernel)
+    (2, 1, 16, 18, 16, 3, 2, 1),   # sync-discriminator stem: Cin = 1, stride 2 (dedicated Cin=1 kernels)
+    (2, 24, 9, 11, 1, 1, 1, 0),    # to_mel head: Cout = 1 pointwise (dedicated kernels)
+    (3, 40, 6, 10, 48, 3, 1, 1),   # exercises the tiled weight re-pack (Cout, Cin >= 8, ragged tiles)
 ]
+
+
+@pytest.mark.parametrize("case", [(2, 1, 20, 17, 32, 5, 1, 2), (2, 1, 16, 18, 16, 3, 2, 1), (2, 32, 9, 11, 1, 1, 1, 0)])
+def test_conv_degenerate_channels_bf16(V, case):
+    """Cin = 1 stems and Cout = 1 heads in bf16 storage (conv_small.cu)"""
+    N, Cin, H, W, Cout, k, s, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float().requires_grad_(True)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float().requires_grad_(True)
+    b = torch.randn(Cout, generator=g).requires_grad_(True)
+    y = F.conv2d(x, w, b, s, p)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    V.set_precision("bf16")
+    try:
+        xd = cl(x.detach()).cuda().bfloat16().requires_grad_(True)
+        wd = w.detach().cuda().requires_grad_(True); bd = b.detach().cuda().requires_grad_(True)
+        yd = V.ops.conv(xd, wd, bd, (s, s), (p, p))
+        yd.backward(cl(dy).cuda().bfloat16())
+        e = dict(fwd=rel_l2(nchw(yd.detach().float().cpu()), y), dgrad=rel_l2(nchw(xd.grad.float().cpu()), x.grad),
+                 wgrad=rel_l2(wd.grad.cpu(), w.grad))
+        assert max(e.values()) < BF16_TOL, e
+    finally:
+        V.set_precision("fp32")
 
 
 @pytest.mark.parametrize("case", CONV_CASES)

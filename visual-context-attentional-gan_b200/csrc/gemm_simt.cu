@@ -9,6 +9,14 @@
 //   strided batched GEMM (nn.Linear, torch.bmm sites: generator.py:147-171, 336-357; GRU gates)
 #include "common.cuh"
 
+// conv_small.cu: degenerate-channel kernels (1 = handled, 0 = not applicable, < 0 error)
+int conv_cin1_fwd(int dtype, const ConvGeom& g, const void* x, const void* wf, const float* bias, void* y, cudaStream_t s);
+int conv_cin1_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
+int conv_pw1_fwd(int dtype, const ConvGeom& g, const void* x, const void* w, const float* bias, void* y, cudaStream_t s);
+int conv_pw1_dgrad(int dtype, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s);
+int conv_pw1_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
+int pack_weight_tiled(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s);
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 32, NT = 256;
@@ -388,6 +396,12 @@ static bool geom_ok(const ConvGeom& g) {
 
 template <class T>
 static int conv_fwd_t(const ConvGeom& g, const void* x, const void* wf, const float* bias, void* y, cudaStream_t s) {
+  {
+    const int dt = sizeof(T) == 4 ? VCA_F32 : VCA_BF16;
+    int r = conv_cin1_fwd(dt, g, x, wf, bias, y, s);
+    if (r == 0) r = conv_pw1_fwd(dt, g, x, wf, bias, y, s);
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   ConvFwdP<T> p; p.g = g; p.x = (const T*)x; p.w = (const T*)wf; p.bias = bias; p.y = (T*)y;
   long long M = (long long)g.N * g.OD * g.OH * g.OW;
   VCA_CHECK_ARG(M < (1ll << 31));
@@ -396,6 +410,10 @@ static int conv_fwd_t(const ConvGeom& g, const void* x, const void* wf, const fl
 }
 template <class T>
 static int conv_dgrad_t(const ConvGeom& g, const void* dy, const void* wd, void* dx, cudaStream_t s) {
+  {
+    const int r = conv_pw1_dgrad(sizeof(T) == 4 ? VCA_F32 : VCA_BF16, g, dy, wd, dx, s);
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   long long M = (long long)g.N * g.ID * g.IH * g.IW;
   if (g.Cin == 1 && g.KD * g.KH * g.KW * g.Cout <= CIN1_MAX_W) {
     constexpr int V = sizeof(T) == 2 ? 8 : 4;
@@ -413,6 +431,12 @@ static int conv_dgrad_t(const ConvGeom& g, const void* dy, const void* wd, void*
 }
 template <class T>
 static int conv_wgrad_t(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s) {
+  {
+    const int dt = sizeof(T) == 4 ? VCA_F32 : VCA_BF16;
+    int r = conv_cin1_wgrad(dt, g, dy, x, dw, s);
+    if (r == 0) r = conv_pw1_wgrad(dt, g, dy, x, dw, s);
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   ConvWgradP<T> p; p.g = g; p.dy = (const T*)dy; p.x = (const T*)x; p.dw = dw;
   long long Kp = (long long)g.N * g.OD * g.OH * g.OW;
   VCA_CHECK_ARG(Kp < (1ll << 31));
@@ -447,6 +471,10 @@ int vca_conv_wgrad_simt(int dtype, const ConvGeom* g, const void* dy, const void
 // w: fp32 parameter [Cout][Cin][taps]; wf: [taps][Cin][Cout]; wd: [taps][Cout][Cin] (either may be null).
 int vca_pack_conv_weight(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s) {
   VCA_CHECK_ARG(w && (wf || wd) && Cout > 0 && Cin > 0 && taps > 0);
+  if (Cout >= 8 && Cin >= 8) {   // tile-transpose kernel (coalesced on both sides); tiny layers use the simple one below
+    const int r = pack_weight_tiled(dtype, w, wf, wd, Cout, Cin, taps, s);
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   long long total = (long long)Cout * Cin * taps;
   unsigned grid = vca_grid_1d(total, 256);
   if (dtype == VCA_F32) pack_weight_kernel<float><<<grid, 256, 0, s>>>(w, (float*)wf, (float*)wd, Cout, Cin, taps);

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 #pragma unroll
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0;
   if (active) {
+#pragma unroll 2
     for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
       float v[V];
       Vec<T>::load(x + r * C + cv * V, v);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
     mu[i] = p.mean[c]; sc[i] = p.invstd[c] * p.gamma[c]; be[i] = p.beta[c];
     sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
   }
+#pragma unroll 2
   for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
     const long long o = r * C + cv * V;
     float v[V], rr[V];
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
       mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
       sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
     }
+#pragma unroll 2
     for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
       const long long o = r * C + cv * V;
       float xv[V], g[V], rr[V];
@@ -181,6 +184,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
     m1[i] = train ? (float)(sums[c] * invR) : 0.f;
     m2[i] = train ? (float)(sums[C + c] * invR) : 0.f;
   }
+#pragma unroll 2
   for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
     const long long o = r * C + cv * V;
     float xv[V], g[V], rr[V];
@@ -267,6 +271,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const T* __restrict__ x
 #pragma unroll
   for (int i = 0; i < V; ++i) a[i] = 0;
   if (active) {
+#pragma unroll 2
     for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
       float v[V];
       Vec<T>::load(x + r * C + cv * V, v);
