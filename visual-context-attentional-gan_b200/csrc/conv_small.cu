@@ -186,9 +186,9 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const float* __restrict
                                                          int Cout, int Cin, int taps) {
   __shared__ float s[PK_T][PK][PK + 1];
   const int co0 = blockIdx.y * PK, ci0 = blockIdx.x * PK;
-  for (int t0 = 0; t0 < taps; t0 += PK_T) {
+  {
+    const int t0 = blockIdx.z * PK_T;            // one tap chunk per CTA (grid.z) for parallelism on small layers
     const int tc = min(PK_T, taps - t0);
-    __syncthreads();
     for (int i = threadIdx.x; i < PK * PK * tc; i += blockDim.x) {
       const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
       float v = 0.f;
@@ -284,8 +284,8 @@ int conv_pw1_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, 
   return 1;
 }
 int pack_weight_tiled(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s) {
-  dim3 grid((Cin + PK - 1) / PK, (Cout + PK - 1) / PK);
-  if (grid.y > 65535u) return 0;
+  dim3 grid((Cin + PK - 1) / PK, (Cout + PK - 1) / PK, (taps + PK_T - 1) / PK_T);
+  if (grid.y > 65535u || grid.z > 65535u) return 0;
   SMALL_T(dtype, (pack_tiled_kernel<float><<<grid, 256, 0, s>>>(w, (float*)wf, (float*)wd, Cout, Cin, taps)),
           (pack_tiled_kernel<bf16><<<grid, 256, 0, s>>>(w, (bf16*)wf, (bf16*)wd, Cout, Cin, taps)));
   if (cudaGetLastError() != cudaSuccess) { vca_set_error("pack_tiled_kernel launch failed"); return VCA_ERR_CUDA; }

@@ -22,6 +22,8 @@
 // conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
                 const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
+// conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
+int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
 
 namespace {
 
@@ -501,6 +503,10 @@ int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* d
 // dw fp32 [Cout][Cin][taps], zero on entry (accumulated with red.add across pixel splits).
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t s) {
   VCA_CHECK_ARG(g && dy && x && dw && vca_conv_tc_supported(g, 2));
+  {
+    const int r = conv_wgrad_ws_try(*g, dy, x, dw, s);   // multi-tap halo-resident kernel for <= 64 input channels
+    if (r != 0) return r < 0 ? r : VCA_OK;
+  }
   WgradParams p;
   p.NF = g->N; p.OH = g->OH; p.OW = g->OW; p.Cout = g->Cout; p.Cin = g->Cin; p.taps = g->KH * g->KW;
   choose_box(g->N, g->OH, g->OW, p.tn, p.th, p.tw);

@@ -15,10 +15,12 @@
 
 using namespace tc;
 
+extern int g_wgws_mode;   // conv_tc_wgrad_ws.cu
+
 namespace {
 
 constexpr int KC = 64;
-int g_ws_mode = 1;        // 0 off, 1 auto, 2 force whenever the geometry fits
+int g_ws_mode = 1;       // 0 off, 1 auto, 2 force whenever the geometry fits
 int g_ws_base_off = 0;    // descriptor base-offset mode for shifted A windows (0: none, 1: (addr >> 7) & 7)
 
 struct WsParams {
@@ -273,6 +275,7 @@ int vca_set_option(const char* key, int value) {
   auto eq = [&](const char* s) { const char* a = k; while (*a && *s && *a == *s) { ++a; ++s; } return *a == 0 && *s == 0; };
   if (eq("ws_mode")) { g_ws_mode = value; return VCA_OK; }
   if (eq("ws_base_off")) { g_ws_base_off = value; return VCA_OK; }
+  if (eq("wgws_mode")) { g_wgws_mode = value; return VCA_OK; }
   vca_set_error("vca_set_option: unknown key %s", key);
   return VCA_ERR_ARG;
 }
