@@ -40,6 +40,25 @@ __device__ __forceinline__ void block_col_reduce(const double (&acc)[V], double*
   }
 }
 
+
+// Row loop with 4 rows of 128-bit loads in flight per thread before any arithmetic (the kernels keep ~50 registers of
+// per-channel constants, so occupancy is low and memory-level parallelism has to come from here).
+#define BN_ROW_LOOP(NT, LOADS, BODY)                                                                               \
+  {                                                                                                                \
+    const long long stride__ = (long long)gridDim.x * blockDim.y;                                                 \
+    long long r__ = (long long)blockIdx.x * blockDim.y + threadIdx.y;                                             \
+    for (; r__ + 3 * stride__ < R; r__ += 4 * stride__) {                                                         \
+      typename Vec<T>::Raw raw__[4][NT];                                                                           \
+      _Pragma("unroll") for (int u__ = 0; u__ < 4; ++u__) { const long long o = (r__ + u__ * stride__) * C + cv * V; LOADS(raw__[u__]) } \
+      _Pragma("unroll") for (int u__ = 0; u__ < 4; ++u__) { const long long o = (r__ + u__ * stride__) * C + cv * V; BODY(raw__[u__]) }  \
+    }                                                                                                              \
+    for (; r__ < R; r__ += stride__) {                                                                             \
+      typename Vec<T>::Raw raw1__[NT];                                                                             \
+      const long long o = r__ * C + cv * V;                                                                        \
+      LOADS(raw1__) BODY(raw1__)                                                                                   \
+    }                                                                                                              \
+  }
+
 template <class T>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, long long R, int C, double* __restrict__ sums) {
   constexpr int V = Vec<T>::N;
@@ -50,13 +69,14 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
 #pragma unroll
   for (int i = 0; i < V; ++i) s1[i] = s2[i] = 0;
   if (active) {
-#pragma unroll 2
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
-      float v[V];
-      Vec<T>::load(x + r * C + cv * V, v);
-#pragma unroll
-      for (int i = 0; i < V; ++i) { s1[i] += (double)v[i]; s2[i] += (double)v[i] * (double)v[i]; }
-    }
+#define ST_LOADS(RAW) RAW[0] = Vec<T>::ldraw(x + o);
+#define ST_BODY(RAW)                                                              \
+  {                                                                               \
+    float v[V];                                                                   \
+    Vec<T>::unpack(RAW[0], v);                                                    \
+    _Pragma("unroll") for (int i = 0; i < V; ++i) { s1[i] += (double)v[i]; s2[i] += (double)v[i] * (double)v[i]; } \
+  }
+    BN_ROW_LOOP(1, ST_LOADS, ST_BODY)
   }
   block_col_reduce<V>(s1, sh, sums, cv * V, active);
   block_col_reduce<V>(s2, sh, sums + C, cv * V, active);
@@ -105,20 +125,20 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
     mu[i] = p.mean[c]; sc[i] = p.invstd[c] * p.gamma[c]; be[i] = p.beta[c];
     sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
   }
-#pragma unroll 2
-  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
-    const long long o = r * C + cv * V;
-    float v[V], rr[V];
-    Vec<T>::load(x + o, v);
-    if (res) Vec<T>::load(res + o, rr);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      float t = (v[i] - mu[i]) * sc[i] + be[i];
-      if (res) t += rr[i];
-      v[i] = act_fwd(t, p.act, sl[i]);
-    }
-    Vec<T>::store(y + o, v);
+#define FW_LOADS(RAW) RAW[0] = Vec<T>::ldraw(x + o); if (res) RAW[1] = Vec<T>::ldraw(res + o);
+#define FW_BODY(RAW)                                                              \
+  {                                                                               \
+    float v[V], rr[V];                                                            \
+    Vec<T>::unpack(RAW[0], v);                                                    \
+    if (res) Vec<T>::unpack(RAW[1], rr);                                          \
+    _Pragma("unroll") for (int i = 0; i < V; ++i) {                               \
+      float t = (v[i] - mu[i]) * sc[i] + be[i];                                   \
+      if (res) t += rr[i];                                                        \
+      v[i] = act_fwd(t, p.act, sl[i]);                                            \
+    }                                                                             \
+    Vec<T>::store(y + o, v);                                                      \
   }
+  BN_ROW_LOOP(2, FW_LOADS, FW_BODY)
 }
 
 // per-channel sums for the backward: s[0][c] = sum dpre, s[1][c] = sum dpre*xhat, s[2][c] = sum dy*min(pre,0) (PReLU)
@@ -141,24 +161,23 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
       mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c];
       sl[i] = p.act == ACT_PRELU ? p.prelu_w[c] : p.slope;
     }
-#pragma unroll 2
-    for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
-      const long long o = r * C + cv * V;
-      float xv[V], g[V], rr[V];
-      Vec<T>::load(x + o, xv);
-      Vec<T>::load(dy + o, g);
-      if (res) Vec<T>::load(res + o, rr);
-#pragma unroll
-      for (int i = 0; i < V; ++i) {
-        const float xh = (xv[i] - mu[i]) * is[i];
-        float pre = xh * ga[i] + be[i];
-        if (res) pre += rr[i];
-        const float dpre = act_bwd(g[i], pre, p.act, sl[i]);
-        a[i] += (double)dpre;
-        b[i] += (double)dpre * (double)xh;
-        if (p.act == ACT_PRELU && pre <= 0.f) d[i] += (double)g[i] * (double)pre;
-      }
-    }
+#define RD_LOADS(RAW) RAW[0] = Vec<T>::ldraw(x + o); RAW[1] = Vec<T>::ldraw(dy + o); if (res) RAW[2] = Vec<T>::ldraw(res + o);
+#define RD_BODY(RAW)                                                              \
+  {                                                                               \
+    float xv[V], g[V], rr[V];                                                     \
+    Vec<T>::unpack(RAW[0], xv); Vec<T>::unpack(RAW[1], g);                        \
+    if (res) Vec<T>::unpack(RAW[2], rr);                                          \
+    _Pragma("unroll") for (int i = 0; i < V; ++i) {                               \
+      const float xh = (xv[i] - mu[i]) * is[i];                                   \
+      float pre = xh * ga[i] + be[i];                                             \
+      if (res) pre += rr[i];                                                      \
+      const float dpre = act_bwd(g[i], pre, p.act, sl[i]);                        \
+      a[i] += (double)dpre;                                                       \
+      b[i] += (double)dpre * (double)xh;                                          \
+      if (p.act == ACT_PRELU && pre <= 0.f) d[i] += (double)g[i] * (double)pre;   \
+    }                                                                             \
+  }
+    BN_ROW_LOOP(3, RD_LOADS, RD_BODY)
   }
   block_col_reduce<V>(a, sh, sums, cv * V, active);
   block_col_reduce<V>(b, sh, sums + C, cv * V, active);
@@ -184,25 +203,23 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
     m1[i] = train ? (float)(sums[c] * invR) : 0.f;
     m2[i] = train ? (float)(sums[C + c] * invR) : 0.f;
   }
-#pragma unroll 2
-  for (long long r = (long long)blockIdx.x * blockDim.y + threadIdx.y; r < R; r += (long long)gridDim.x * blockDim.y) {
-    const long long o = r * C + cv * V;
-    float xv[V], g[V], rr[V];
-    Vec<T>::load(x + o, xv);
-    Vec<T>::load(dy + o, g);
-    if (res) Vec<T>::load(res + o, rr);
-#pragma unroll
-    for (int i = 0; i < V; ++i) {
-      const float xh = (xv[i] - mu[i]) * is[i];
-      float pre = xh * ga[i] + be[i];
-      if (res) pre += rr[i];
-      const float dpre = act_bwd(g[i], pre, p.act, sl[i]);
-      g[i] = dpre;
-      xv[i] = (dpre - m1[i] - xh * m2[i]) * ga[i] * is[i];
-    }
-    Vec<T>::store(dx + o, xv);
-    if (dres) Vec<T>::store(dres + o, g);
+#define AP_BODY(RAW)                                                              \
+  {                                                                               \
+    float xv[V], g[V], rr[V];                                                     \
+    Vec<T>::unpack(RAW[0], xv); Vec<T>::unpack(RAW[1], g);                        \
+    if (res) Vec<T>::unpack(RAW[2], rr);                                          \
+    _Pragma("unroll") for (int i = 0; i < V; ++i) {                               \
+      const float xh = (xv[i] - mu[i]) * is[i];                                   \
+      float pre = xh * ga[i] + be[i];                                             \
+      if (res) pre += rr[i];                                                      \
+      const float dpre = act_bwd(g[i], pre, p.act, sl[i]);                        \
+      g[i] = dpre;                                                                \
+      xv[i] = (dpre - m1[i] - xh * m2[i]) * ga[i] * is[i];                        \
+    }                                                                             \
+    Vec<T>::store(dx + o, xv);                                                    \
+    if (dres) Vec<T>::store(dres + o, g);                                         \
   }
+  BN_ROW_LOOP(3, RD_LOADS, AP_BODY)
 }
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,

@@ -5,6 +5,9 @@
 template <class T> struct Vec;
 template <> struct Vec<float> {
   static constexpr int N = 4;
+  typedef float4 Raw;
+  __device__ static __forceinline__ Raw ldraw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  __device__ static __forceinline__ void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   __device__ static __forceinline__ void load(const float* p, float* v) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -15,6 +18,13 @@ template <> struct Vec<float> {
 };
 template <> struct Vec<bf16> {
   static constexpr int N = 8;
+  typedef uint4 Raw;
+  __device__ static __forceinline__ Raw ldraw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  __device__ static __forceinline__ void unpack(const Raw& t, float* v) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
   __device__ static __forceinline__ void load(const bf16* p, float* v) {
     const uint4 t = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
