@@ -43,7 +43,7 @@ __device__ __forceinline__ void block_col_reduce(const double (&acc)[V], double*
 
 // Row loop with 4 rows of 128-bit loads in flight per thread before any arithmetic (the kernels keep ~50 registers of
 // per-channel constants, so occupancy is low and memory-level parallelism has to come from here).
-#define BN_ROW_LOOP(NT, LOADS, BODY)                                                                               \
+#define BN_ROW_LOOP(NT, LOADS, BODY, FLUSH)                                                                              \
   {                                                                                                                \
     const long long stride__ = (long long)gridDim.x * blockDim.y;                                                 \
     long long r__ = (long long)blockIdx.x * blockDim.y + threadIdx.y;                                             \
@@ -51,11 +51,12 @@ __device__ __forceinline__ void block_col_reduce(const double (&acc)[V], double*
       typename Vec<T>::Raw raw__[4][NT];                                                                           \
       _Pragma("unroll") for (int u__ = 0; u__ < 4; ++u__) { const long long o = (r__ + u__ * stride__) * C + cv * V; LOADS(raw__[u__]) } \
       _Pragma("unroll") for (int u__ = 0; u__ < 4; ++u__) { const long long o = (r__ + u__ * stride__) * C + cv * V; BODY(raw__[u__]) }  \
+      FLUSH                                                                                                        \
     }                                                                                                              \
     for (; r__ < R; r__ += stride__) {                                                                             \
       typename Vec<T>::Raw raw1__[NT];                                                                             \
       const long long o = r__ * C + cv * V;                                                                        \
-      LOADS(raw1__) BODY(raw1__)                                                                                   \
+      LOADS(raw1__) BODY(raw1__) FLUSH                                                                             \
     }                                                                                                              \
   }
 
@@ -74,9 +75,13 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const T* __restrict__ x, 
   {                                                                               \
     float v[V];                                                                   \
     Vec<T>::unpack(RAW[0], v);                                                    \
-    _Pragma("unroll") for (int i = 0; i < V; ++i) { s1[i] += (double)v[i]; s2[i] += (double)v[i] * (double)v[i]; } \
+    _Pragma("unroll") for (int i = 0; i < V; ++i) { f1[i] += v[i]; f2[i] = fmaf(v[i], v[i], f2[i]); } \
   }
-    BN_ROW_LOOP(1, ST_LOADS, ST_BODY)
+#define ST_FLUSH _Pragma("unroll") for (int i = 0; i < V; ++i) { s1[i] += (double)f1[i]; s2[i] += (double)f2[i]; f1[i] = f2[i] = 0.f; }
+    float f1[V], f2[V];   // fp32 partials over one 4-row group, folded into the fp64 running sums (keeps the FP64 pipe idle)
+#pragma unroll
+    for (int i = 0; i < V; ++i) f1[i] = f2[i] = 0.f;
+    BN_ROW_LOOP(1, ST_LOADS, ST_BODY, ST_FLUSH)
   }
   block_col_reduce<V>(s1, sh, sums, cv * V, active);
   block_col_reduce<V>(s2, sh, sums + C, cv * V, active);
@@ -138,7 +143,7 @@ __global__ void __launch_bounds__(256) bn_act_fwd_kernel(const T* __restrict__ x
     }                                                                             \
     Vec<T>::store(y + o, v);                                                      \
   }
-  BN_ROW_LOOP(2, FW_LOADS, FW_BODY)
+  BN_ROW_LOOP(2, FW_LOADS, FW_BODY, )
 }
 
 // per-channel sums for the backward: s[0][c] = sum dpre, s[1][c] = sum dpre*xhat, s[2][c] = sum dy*min(pre,0) (PReLU)
@@ -172,12 +177,16 @@ __global__ void __launch_bounds__(256) bn_act_bwd_reduce_kernel(const T* __restr
       float pre = xh * ga[i] + be[i];                                             \
       if (res) pre += rr[i];                                                      \
       const float dpre = act_bwd(g[i], pre, p.act, sl[i]);                        \
-      a[i] += (double)dpre;                                                       \
-      b[i] += (double)dpre * (double)xh;                                          \
-      if (p.act == ACT_PRELU && pre <= 0.f) d[i] += (double)g[i] * (double)pre;   \
+      fa[i] += dpre;                                                              \
+      fb[i] = fmaf(dpre, xh, fb[i]);                                              \
+      if (p.act == ACT_PRELU && pre <= 0.f) fd[i] = fmaf(g[i], pre, fd[i]);       \
     }                                                                             \
   }
-    BN_ROW_LOOP(3, RD_LOADS, RD_BODY)
+#define RD_FLUSH _Pragma("unroll") for (int i = 0; i < V; ++i) { a[i] += (double)fa[i]; b[i] += (double)fb[i]; d[i] += (double)fd[i]; fa[i] = fb[i] = fd[i] = 0.f; }
+    float fa[V], fb[V], fd[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) fa[i] = fb[i] = fd[i] = 0.f;
+    BN_ROW_LOOP(3, RD_LOADS, RD_BODY, RD_FLUSH)
   }
   block_col_reduce<V>(a, sh, sums, cv * V, active);
   block_col_reduce<V>(b, sh, sums + C, cv * V, active);
@@ -219,7 +228,7 @@ __global__ void __launch_bounds__(256) bn_act_bwd_apply_kernel(const T* __restri
     Vec<T>::store(dx + o, xv);                                                    \
     if (dres) Vec<T>::store(dres + o, g);                                         \
   }
-  BN_ROW_LOOP(3, RD_LOADS, AP_BODY)
+  BN_ROW_LOOP(3, RD_LOADS, AP_BODY, )
 }
 
 __global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
