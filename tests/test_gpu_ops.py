@@ -292,6 +292,54 @@ def test_bn_act_pool(V):
     assert rel_l2(O.tanh(t.cuda()).cpu(), torch.tanh(t)) < 1e-6
 
 
+@pytest.mark.parametrize("C,bn_vec", [(64, 4), (64, 8), (136, 4), (136, 8)])
+def test_bn_act_bf16_large(V, C, bn_vec):
+    """bf16 BatchNorm kernels at a row count that exercises the multi-row unrolled loop and the capped one-wave grid,
+    for both channel-vector widths of the backward kernels, against fp32 math on the bf16-rounded inputs."""
+    from vcagan_b200._lib import lib
+    O = V.ops
+    g = torch.Generator().manual_seed(C + bn_vec)
+    N, H, W = 3, 150, 151 if C == 64 else 83
+    assert lib().cdll.vca_set_option(b"bn_vec", bn_vec) == 0
+    V.set_precision("bf16")
+    try:
+        for act, with_res in (("prelu", True), ("lrelu", False), ("relu", True), ("none", False)):
+            x = (0.7 + 1.5 * torch.randn(N, C, H, W, generator=g)).bfloat16().float().requires_grad_(True)
+            res = torch.randn(N, C, H, W, generator=g).bfloat16().float().requires_grad_(True) if with_res else None
+            bn = torch.nn.BatchNorm2d(C)
+            bn.weight.data = 1 + 0.2 * torch.randn(C, generator=g); bn.bias.data = 0.1 * torch.randn(C, generator=g)
+            pw = (0.25 + 0.1 * torch.randn(C, generator=g)).requires_grad_(True)
+            pre = bn(x) + res if with_res else bn(x)
+            y = {"prelu": lambda: F.prelu(pre, pw), "lrelu": lambda: F.leaky_relu(pre, 0.2), "relu": lambda: F.relu(pre),
+                 "none": lambda: pre}[act]()
+            dy = torch.randn(y.shape, generator=g).bfloat16().float()
+            y.backward(dy)
+            bnd = torch.nn.BatchNorm2d(C).cuda()
+            bnd.weight.data = bn.weight.data.clone().cuda(); bnd.bias.data = bn.bias.data.clone().cuda()
+            xd = cl(x.detach()).cuda().bfloat16().requires_grad_(True)
+            rd = cl(res.detach()).cuda().bfloat16().requires_grad_(True) if with_res else None
+            pwd = pw.detach().cuda().requires_grad_(True)
+            code = {"prelu": O.ACT_PRELU, "lrelu": O.ACT_LRELU, "relu": O.ACT_RELU, "none": O.ACT_NONE}[act]
+            yd = O.bn_act(xd, bnd, code, 0.2, pwd if act == "prelu" else None, res=rd)
+            yd.backward(cl(dy).cuda().bfloat16())
+            assert rel_l2(nchw(yd.detach().float().cpu()), y) < 5e-3, act
+            assert rel_l2(nchw(xd.grad.float().cpu()), x.grad) < 8e-3, act
+            if with_res:
+                assert rel_l2(nchw(rd.grad.float().cpu()), res.grad) < 5e-3, act
+            assert rel_l2(bnd.weight.grad.cpu(), bn.weight.grad) < 5e-3, act
+            assert rel_l2(bnd.bias.grad.cpu(), bn.bias.grad) < 5e-3, act
+            if act == "prelu":
+                assert rel_l2(pwd.grad.cpu(), pw.grad) < 5e-3
+            assert rel_l2(bnd.running_mean.cpu(), bn.running_mean) < 1e-4
+            assert rel_l2(bnd.running_var.cpu(), bn.running_var) < 1e-4
+        # column sums (bias gradients) at the same size
+        t = torch.randn(N * H * W, C, generator=g).bfloat16()
+        assert rel_l2(O.ColSumFn.apply(t.cuda()).cpu(), t.double().sum(0).float()) < 1e-4
+    finally:
+        V.set_precision("fp32")
+        lib().cdll.vca_set_option(b"bn_vec", 4)
+
+
 @pytest.mark.parametrize("dims,persistent", [((7, 3, 20, 16), True), ((5, 40, 12, 24), True), ((7, 3, 20, 16), False)])
 def test_gru_layer(V, dims, persistent):
     g = torch.Generator().manual_seed(9)

@@ -447,8 +447,14 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   p.tmem_cols = pow2_cols(bn);
   p.bias = bias; p.y = (bf16*)y;
   const size_t stage_bytes = A_STAGE_BYTES + (size_t)bn * 128;
-  int stages = (int)((100 * 1024) / stage_bytes);
-  if (stages > 6) stages = 6; if (stages < 2) stages = 2;
+  // Two CTAs per SM (100 KB each) hide each other's TMA latency on big grids.  A grid that cannot even fill the SMs
+  // once (small feature maps of the discriminator heads) gets one deep pipeline per CTA instead: a stage is only
+  // 4 MMAs (~0.15-0.3 us) while a TMA round trip is ~1.5 us.
+  const long long total_ctas = ptiles * ((Nout + bn - 1) / bn);
+  const size_t budget = total_ctas <= vca_num_sms() ? 196 * 1024 : 100 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  const int max_stages = total_ctas <= vca_num_sms() ? 12 : 6;
+  if (stages > max_stages) stages = max_stages; if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = stages * stage_bytes + 1024 + 256;
 
@@ -459,7 +465,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   rc = make_map(&tmB, wpk, 3, dB, bB); if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       vca_set_error("cudaFuncSetAttribute(conv_tc_fwd_kernel) failed"); return VCA_ERR_CUDA;
     }
     attr_set = true;
