@@ -340,11 +340,16 @@ def test_bn_act_bf16_large(V, C, bn_vec):
         lib().cdll.vca_set_option(b"bn_vec", 4)
 
 
-@pytest.mark.parametrize("dims,persistent", [((7, 3, 20, 16), True), ((5, 40, 12, 24), True), ((7, 3, 20, 16), False)])
-def test_gru_layer(V, dims, persistent):
+@pytest.mark.parametrize("dims,mode", [((7, 3, 20, 16), "cluster"), ((5, 40, 12, 24), "cluster"), ((9, 19, 64, 256), "cluster"),
+                                       ((7, 3, 20, 16), "coop"), ((5, 40, 12, 24), "coop"), ((7, 3, 20, 16), "per_step")])
+def test_gru_layer(V, dims, mode):
+    """Bidirectional GRU layer against torch.nn.GRU through the three recurrence back ends: cluster / distributed shared
+    memory kernels (gru_cluster.cu), cooperative-grid kernels (gru_persistent.cu), per-step launches."""
+    from vcagan_b200._lib import lib
     g = torch.Generator().manual_seed(9)
     T, B, I, H = dims
-    V.cfg.gru_persistent = persistent
+    V.cfg.gru_persistent = mode != "per_step"
+    assert lib().cdll.vca_set_option(b"gru_cluster", 1 if mode == "cluster" else 0) == 0
     gru = torch.nn.GRU(I, H, 1, bidirectional=True)
     x = torch.randn(T, B, I, generator=g, requires_grad=True)
     y, _ = gru(x)
@@ -360,6 +365,7 @@ def test_gru_layer(V, dims, persistent):
     for n, p in zip(names, ps):
         assert rel_l2(p.grad.cpu(), getattr(gru, n).grad) < 2e-4, n
     V.cfg.gru_persistent = True
+    lib().cdll.vca_set_option(b"gru_cluster", 1)
 
 
 def test_attention_and_losses(V):

@@ -15,8 +15,9 @@
 
 using namespace tc;
 
-extern int g_wgws_mode;
-extern int g_bn_vec;   // bn.cu   // conv_tc_wgrad_ws.cu
+extern int g_wgws_mode;     // conv_tc_wgrad_ws.cu
+extern int g_bn_vec;        // bn.cu
+extern int g_gru_cluster;   // gru_cluster.cu
 
 namespace {
 
@@ -278,6 +279,7 @@ int vca_set_option(const char* key, int value) {
   if (eq("ws_base_off")) { g_ws_base_off = value; return VCA_OK; }
   if (eq("wgws_mode")) { g_wgws_mode = value; return VCA_OK; }
   if (eq("bn_vec")) { g_bn_vec = value; return VCA_OK; }
+  if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
   vca_set_error("vca_set_option: unknown key %s", key);
   return VCA_ERR_ARG;
 }

@@ -8,6 +8,12 @@
 // the grid barrier between steps (bounded spin: a lost arrival traps instead of hanging the GPU).
 #include "common.cuh"
 
+// gru_cluster.cu: cluster / distributed-shared-memory kernels (1 = launched, 0 = not applicable, < 0 = error)
+int gru_cluster_fwd_try(const float* gi, const float* whh, const float* bhh, float* out, float* gates, int ndir, int T, int B,
+                        int H, cudaStream_t s);
+int gru_cluster_bwd_try(const float* dout, const float* whh, const float* gates, const float* out, float* dgi, float* dgh,
+                        int ndir, int T, int B, int H, cudaStream_t s);
+
 namespace {
 
 constexpr int UNITS = 8;       // hidden units (forward) / columns (backward) per CTA = warps per CTA
@@ -187,6 +193,7 @@ extern "C" {
 int vca_gru_seq_fwd(const float* gi, const float* whh, const float* bhh, float* hbuf, float* out, float* gates, unsigned* bar,
                     int ndir, int T, int B, int H, cudaStream_t s) {
   VCA_CHECK_ARG(gi && whh && bhh && hbuf && out && gates && bar && ndir > 0 && T > 0 && B > 0 && H > 0);
+  if (const int r = gru_cluster_fwd_try(gi, whh, bhh, out, gates, ndir, T, B, H, s)) return r < 0 ? r : VCA_OK;
   if (H % UNITS || H % 4) { vca_set_error("vca_gru_seq_fwd: H must be a multiple of %d", UNITS); return VCA_ERR_UNSUPPORTED; }
   const int grid = ndir * (H / UNITS);
   const size_t smem = (size_t)(3 * UNITS * H + BT * (H + 4)) * sizeof(float);
@@ -207,6 +214,7 @@ int vca_gru_seq_fwd(const float* gi, const float* whh, const float* bhh, float* 
 int vca_gru_seq_bwd(const float* dout, const float* whh, const float* gates, const float* out, float* dgi, float* dgh,
                     float* dhc, float* dghc, float* dhz, unsigned* bar, int ndir, int T, int B, int H, cudaStream_t s) {
   VCA_CHECK_ARG(dout && whh && gates && out && dgi && dgh && dhc && dghc && dhz && bar && ndir > 0 && T > 0 && B > 0 && H > 0);
+  if (const int r = gru_cluster_bwd_try(dout, whh, gates, out, dgi, dgh, ndir, T, B, H, s)) return r < 0 ? r : VCA_OK;
   if (H % UNITS || H % 4) { vca_set_error("vca_gru_seq_bwd: H must be a multiple of %d", UNITS); return VCA_ERR_UNSUPPORTED; }
   const int grid = ndir * (H / UNITS);
   const size_t smem = (size_t)(3 * UNITS * H + BT * (H + 4)) * sizeof(float);
