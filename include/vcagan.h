@@ -87,6 +87,10 @@ int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const f
 int vca_gru_gate_bwd(const float* dout, float* dh_carry, const float* gates, const float* out, float* dgi, float* dgh, float* dgh_cur, int ndir, int T, int B, int H, int step, cudaStream_t stream);
 int vca_gru_seq_fwd(const float* gi, const float* whh, const float* bhh, float* hbuf, float* out, float* gates, unsigned* bar, int ndir, int T, int B, int H, cudaStream_t stream);
 int vca_gru_seq_bwd(const float* dout, const float* whh, const float* gates, const float* out, float* dgi, float* dgh, float* dhc, float* dghc, float* dhz, unsigned* bar, int ndir, int T, int B, int H, cudaStream_t stream);
+/* Cluster plan of the GRU recurrence for batch B, hidden size H: info[6] = {CTAs per cluster (0 = cluster kernels not
+ * applicable, vca_gru_seq_* then run as cooperative grids), batch rows per cluster, clusters a bidirectional layer needs,
+ * co-resident clusters fwd, bwd, K slices of the forward matvec}. */
+int vca_gru_cluster_query(int B, int H, int* info);
 int vca_skinny_gemm(const float* in, const float* wt, float* out, int Z, int Bn, int N, int K, float beta, cudaStream_t stream);
 int vca_masked_softmax_fwd(const float* x, float* p, const int* lens, int Z, int R, int S, cudaStream_t stream);
 int vca_softmax_bwd(const float* dp, const float* p, float* dx, int rows, int S, cudaStream_t stream);

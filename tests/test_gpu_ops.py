@@ -341,6 +341,8 @@ def test_bn_act_bf16_large(V, C, bn_vec):
 
 
 @pytest.mark.parametrize("dims,mode", [((7, 3, 20, 16), "cluster"), ((5, 40, 12, 24), "cluster"), ((9, 19, 64, 256), "cluster"),
+                                       ((6, 11, 48, 512), "cluster"), ((4, 32, 32, 512), "cluster"), ((5, 19, 16, 256), "cluster12"),
+                                       ((5, 19, 16, 256), "cluster16"), ((5, 40, 12, 24), "cluster12"),
                                        ((7, 3, 20, 16), "coop"), ((5, 40, 12, 24), "coop"), ((7, 3, 20, 16), "per_step")])
 def test_gru_layer(V, dims, mode):
     """Bidirectional GRU layer against torch.nn.GRU through the three recurrence back ends: cluster / distributed shared
@@ -349,7 +351,8 @@ def test_gru_layer(V, dims, mode):
     g = torch.Generator().manual_seed(9)
     T, B, I, H = dims
     V.cfg.gru_persistent = mode != "per_step"
-    assert lib().cdll.vca_set_option(b"gru_cluster", 1 if mode == "cluster" else 0) == 0
+    assert lib().cdll.vca_set_option(b"gru_cluster", 1 if mode.startswith("cluster") else 0) == 0
+    assert lib().cdll.vca_set_option(b"gru_bs", int(mode[7:] or 0) if mode.startswith("cluster") else 0) == 0
     gru = torch.nn.GRU(I, H, 1, bidirectional=True)
     x = torch.randn(T, B, I, generator=g, requires_grad=True)
     y, _ = gru(x)
@@ -366,6 +369,7 @@ def test_gru_layer(V, dims, mode):
         assert rel_l2(p.grad.cpu(), getattr(gru, n).grad) < 2e-4, n
     V.cfg.gru_persistent = True
     lib().cdll.vca_set_option(b"gru_cluster", 1)
+    lib().cdll.vca_set_option(b"gru_bs", 0)
 
 
 def test_attention_and_losses(V):

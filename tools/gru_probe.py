@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timing of the GRU recurrence back ends at the step's shape (T=75, B=32, H=256, 2 directions).   python tools/gru_probe.py"""
+"""Timing of the GRU recurrence back ends at the step's shape (T=75, B=32, H=512, 2 directions).   python tools/gru_probe.py"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "visual-context-attentional-gan_b200"))
@@ -8,7 +8,7 @@ from vcagan_b200._lib import lib
 
 L = lib()
 dev = torch.device("cuda")
-T, B, H = 75, 32, 256
+T, B, H = 75, 32, int(sys.argv[1]) if len(sys.argv) > 1 else 512
 gi = torch.randn(2, T, B, 3 * H, device=dev)
 whh = torch.randn(2, 3 * H, H, device=dev) / 16
 bhh = torch.randn(2, 3 * H, device=dev) / 16
@@ -35,6 +35,10 @@ def run(cluster):
     return res, out, dgi, dgh
 
 
+import ctypes
+info = (ctypes.c_int * 6)()
+L.cdll.vca_gru_cluster_query(B, H, info)
+print("cluster plan: CTAs/cluster %d, batch rows/cluster %d, clusters needed %d, co-resident fwd %d bwd %d, K slices %d" % tuple(info))
 (rf, rb), o1, a1, b1 = run(1)
 (cf, cb), o0, a0, b0 = run(0)
 L.cdll.vca_set_option(b"gru_cluster", 1)

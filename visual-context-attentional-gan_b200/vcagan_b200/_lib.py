@@ -92,6 +92,8 @@ class _Lib:
                     tag = "x".join(str(v) for v in a.key())
             if name == "vca_gemm_simt":
                 flops = 2 * args[7] * args[8] * args[9] * args[10]
+            if not tag:   # non-conv entry points: the integer arguments (shapes, modes) identify the call
+                tag = "x".join(str(a) for a in args if isinstance(a, int) and not isinstance(a, bool))
             prof.append((name, tag, flops, e0, e1))
 
     def try_call(self, name, *args):
@@ -122,7 +124,7 @@ class _Lib:
                 g = d["by_geom"].setdefault(t, [0, 0.0, 0])
                 g[0] += 1; g[1] += ms; g[2] += f
         for d in agg.values():
-            top = sorted(d.pop("by_geom").items(), key=lambda kv: -kv[1][1])[:6]
+            top = sorted(d.pop("by_geom").items(), key=lambda kv: -kv[1][1])[:10]
             d["top"] = [(k, v[0], round(v[1], 3), round(v[2] / max(v[1], 1e-9) / 1e9, 2)) for k, v in top]
         return agg
 
