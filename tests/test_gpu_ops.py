@@ -40,10 +40,13 @@ CONV_CASES = [
     (2, 1, 16, 18, 16, 3, 2, 1),   # sync-discriminator stem: Cin = 1, stride 2 (dedicated Cin=1 kernels)
     (2, 24, 9, 11, 1, 1, 1, 0),    # to_mel head: Cout = 1 pointwise (dedicated kernels)
     (3, 40, 6, 10, 48, 3, 1, 1),   # exercises the tiled weight re-pack (Cout, Cin >= 8, ragged tiles)
+    (2, 1, 7, 83, 32, 5, 1, 2),    # lane = channel stem kernels (conv_c32.cu): several row segments, ragged tail
+    (2, 1, 9, 50, 32, 3, 1, 0),    # ... 3x3, no padding
 ]
 
 
-@pytest.mark.parametrize("case", [(2, 1, 20, 17, 32, 5, 1, 2), (2, 1, 16, 18, 16, 3, 2, 1), (2, 32, 9, 11, 1, 1, 1, 0)])
+@pytest.mark.parametrize("case", [(2, 1, 20, 17, 32, 5, 1, 2), (2, 1, 16, 18, 16, 3, 2, 1), (2, 32, 9, 11, 1, 1, 1, 0),
+                                  (3, 1, 7, 83, 32, 5, 1, 2), (2, 1, 9, 50, 32, 3, 1, 1)])
 def test_conv_degenerate_channels_bf16(V, case):
     """Cin = 1 stems and Cout = 1 heads in bf16 storage (conv_small.cu)"""
     N, Cin, H, W, Cout, k, s, p = case

@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const float* __restrict
 #define SMALL_T(dtype, CALL_F32, CALL_BF16) do { if ((dtype) == VCA_F32) { CALL_F32; } else { CALL_BF16; } } while (0)
 
 // 1 = handled, 0 = not applicable, <0 error
+// conv_c32.cu: lane = output channel kernels for Cin = 1 -> Cout = 32, stride 1, 5x5 / 3x3
+int conv_c32_fwd(int dtype, const ConvGeom& g, const void* x, const void* wf, const float* bias, void* y, cudaStream_t s);
+int conv_c32_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
+
 int conv_cin1_fwd(int dtype, const ConvGeom& g, const void* x, const void* wf, const float* bias, void* y, cudaStream_t s) {
+  if (const int r = conv_c32_fwd(dtype, g, x, wf, bias, y, s)) return r;
   const int taps = g.KD * g.KH * g.KW;
   if (g.Cin != 1 || g.Cout % 8 || taps * g.Cout > SMALL_MAX_W || !vca_aligned16(y)) return 0;
   const long long M = (long long)g.N * g.OD * g.OH * g.OW;
@@ -221,6 +226,7 @@ int conv_cin1_fwd(int dtype, const ConvGeom& g, const void* x, const void* wf, c
   return 1;
 }
 int conv_cin1_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s) {
+  if (const int r = conv_c32_wgrad(dtype, g, dy, x, dw, s)) return r;
   const int taps = g.KD * g.KH * g.KW;
   if (g.Cin != 1 || taps * g.Cout > 256 * WG_MAXPAIR) return 0;
   const long long M = (long long)g.N * g.OD * g.OH * g.OW;

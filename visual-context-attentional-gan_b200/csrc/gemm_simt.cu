@@ -16,6 +16,8 @@ int conv_pw1_fwd(int dtype, const ConvGeom& g, const void* x, const void* w, con
 int conv_pw1_dgrad(int dtype, const ConvGeom& g, const void* dy, const void* w, void* dx, cudaStream_t s);
 int conv_pw1_wgrad(int dtype, const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
 int pack_weight_tiled(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t s);
+// conv_c32.cu: Cin = 1 -> Cout = 32 dgrad with lane = output channel
+int conv_c32_dgrad(int dtype, const ConvGeom& g, const void* dy, const void* wd, void* dx, cudaStream_t s);
 
 namespace {
 
@@ -411,7 +413,8 @@ static int conv_fwd_t(const ConvGeom& g, const void* x, const void* wf, const fl
 template <class T>
 static int conv_dgrad_t(const ConvGeom& g, const void* dy, const void* wd, void* dx, cudaStream_t s) {
   {
-    const int r = conv_pw1_dgrad(sizeof(T) == 4 ? VCA_F32 : VCA_BF16, g, dy, wd, dx, s);
+    int r = conv_pw1_dgrad(sizeof(T) == 4 ? VCA_F32 : VCA_BF16, g, dy, wd, dx, s);
+    if (r == 0) r = conv_c32_dgrad(sizeof(T) == 4 ? VCA_F32 : VCA_BF16, g, dy, wd, dx, s);
     if (r != 0) return r < 0 ? r : VCA_OK;
   }
   long long M = (long long)g.N * g.ID * g.IH * g.IW;

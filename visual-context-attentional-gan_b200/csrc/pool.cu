@@ -38,8 +38,20 @@ __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__
     }
     const long long o = i * V;
     VT::store(y + o, best);
+    if (V == 8) {        // the 8 argmax codes as one 64-bit store
+      unsigned lo = 0, hi = 0;
 #pragma unroll
-    for (int k = 0; k < V; ++k) idx[o + k] = (unsigned char)bi[k];
+      for (int k = 0; k < 4; ++k) { lo |= (unsigned)bi[k] << (8 * k); hi |= (unsigned)bi[(4 + k) % V] << (8 * k); }
+      *reinterpret_cast<uint2*>(idx + o) = make_uint2(lo, hi);
+    } else if (V == 4) {
+      unsigned lo = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lo |= (unsigned)bi[k % V] << (8 * k);
+      *reinterpret_cast<unsigned*>(idx + o) = lo;
+    } else {
+#pragma unroll
+      for (int k = 0; k < V; ++k) idx[o + k] = (unsigned char)bi[k];
+    }
   }
 }
 // gather form of the backward: every input pixel looks at the <=4 windows that contain it.
@@ -63,8 +75,18 @@ __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const unsigned
         const long long o = (((long long)n * OH + oh) * OW + ow) * C + cv * V;
         float g[V];
         VT::load(dy + o, g);
+        if (V == 8) {
+          const uint2 c = *reinterpret_cast<const uint2*>(idx + o);
 #pragma unroll
-        for (int k = 0; k < V; ++k) if (idx[o + k] == code) acc[k] += g[k];
+          for (int k = 0; k < V; ++k) if ((int)(((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0xffu) == code) acc[k] += g[k];
+        } else if (V == 4) {
+          const unsigned c = *reinterpret_cast<const unsigned*>(idx + o);
+#pragma unroll
+          for (int k = 0; k < V; ++k) if ((int)((c >> (8 * (k & 3))) & 0xffu) == code) acc[k] += g[k];
+        } else {
+#pragma unroll
+          for (int k = 0; k < V; ++k) if (idx[o + k] == code) acc[k] += g[k];
+        }
       }
     }
     VT::store(dx + i * V, acc);
@@ -197,9 +219,9 @@ __global__ void stem_im2col_kernel(const TI* __restrict__ x, TO* __restrict__ y,
       const int h = 2 * oh - 3 + kh, w = 2 * ow - 3 + kw;
       v[k] = (t < 49 && (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) ? to_f(x[(f * H + h) * W + w]) : 0.f;
     }
-    TO* o = y + i * 8;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) o[k] = from_f<TO>(v[k]);
+    TO* o = y + i * 8;   // 8 channels = one 128-bit (bf16) / two 128-bit (fp32) stores
+    if (sizeof(TO) == 2) Vec<bf16>::store(reinterpret_cast<bf16*>(o), v);
+    else { Vec<float>::store(reinterpret_cast<float*>(o), v); Vec<float>::store(reinterpret_cast<float*>(o) + 4, v + 4); }
   }
 }
 

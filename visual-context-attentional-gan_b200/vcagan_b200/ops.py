@@ -949,7 +949,13 @@ class GRURecurrenceFn(Function):
                     a, hprev = dgh[0, 1:].reshape((T - 1) * B, 3 * H), out[:T - 1, :, :H].reshape((T - 1) * B, H)
                 else:
                     a, hprev = dgh[1, :T - 1].reshape((T - 1) * B, 3 * H), out[1:, :, H:].reshape((T - 1) * B, H)
-                _gemm_raw(a.t(), hprev, dw_hh)
+                rows = (T - 1) * B
+                g1, _ = _geom((rows, 1, 1, H), (3 * H, H, 1, 1), (1, 1), (0, 0))
+                if cfg.dtype == torch.bfloat16 and _tc_ok(g1, 2, torch.bfloat16):
+                    # bf16 mode: dW_hh = dgh^T @ h_prev as a 1x1 wgrad on the tcgen05 path (K = (T-1)*B "pixels")
+                    lib().call("vca_conv_wgrad_tc", g1, a.to(torch.bfloat16).contiguous(), hprev.to(torch.bfloat16).contiguous(), dw_hh)
+                else:
+                    _gemm_raw(a.t(), hprev, dw_hh)
             grads += [dw_hh, ColSumFn.apply(dgh[d].view(T * B, 3 * H))]
         return (dgi, *grads)
 
