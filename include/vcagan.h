@@ -65,7 +65,7 @@ int vca_lrelu_bwd(int dtype, const void* dy, const void* x, void* dx, long long 
 int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t stream);
 int vca_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, long long n, cudaStream_t stream);
 int vca_axpby(int dtype, const void* a, const void* b, void* out, long long n, float alpha, float beta, cudaStream_t stream);
-int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, cudaStream_t stream);
+int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, int accumulate, cudaStream_t stream);
 int vca_cast(int dt_in, int dt_out, const void* x, void* y, long long n, cudaStream_t stream);
 int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t stream);
 

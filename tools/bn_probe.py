@@ -44,7 +44,7 @@ for R, C, act, has_res in SHAPES:
     t_bw8 = timed(bw)
     L.cdll.vca_set_option(b"bn_vec", 4)
     t_bw = timed(bw)
-    t_cs = timed(lambda: L.call("vca_colsum", 1, x, R, C, sums, dg))
+    t_cs = timed(lambda: L.call("vca_colsum", 1, x, R, C, sums, dg, 0))
     nres = 1 if has_res else 0
     print(f"R={R:>9} C={C:>3} act={act} res={has_res} ({nb:7.1f} MB/pass)  copy {2 * nb / t_copy:7.0f} GB/s | stats {t_st:6.3f} ms {nb / t_st:6.0f} GB/s | "
           f"fwd {t_fw:6.3f} ms {(2 + nres) * nb / t_fw:6.0f} GB/s | bwd(v4) {t_bw:6.3f} ms {(5 + 3 * nres) * nb / t_bw:6.0f} GB/s (v8) {t_bw8:6.3f} ms | "

@@ -301,9 +301,9 @@ __global__ void colsum_scalar_kernel(const T* __restrict__ x, long long R, int C
     atomicAdd(&out[c], a);
   }
 }
-__global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, int n) {
+__global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, int n, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i];
+  if (i < n) out[i] = (float)in[i] + (accumulate ? out[i] : 0.f);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------
@@ -424,8 +424,8 @@ int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, vo
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
-// out[c] = sum_r x[r,c] (fp32).  scratch: device double[C].
-int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, cudaStream_t s) {
+// out[c] (+)= sum_r x[r,c] (fp32; accumulate != 0 adds to the existing contents).  scratch: device double[C].
+int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, int accumulate, cudaStream_t s) {
   VCA_CHECK_ARG(x && out && scratch && R > 0 && C > 0);
   cudaMemsetAsync(scratch, 0, sizeof(double) * C, s);
   const bool ok = dtype == VCA_F32 ? vec_ok<Vec<float>>(x, 0, 0, 0, 0, C) : vec_ok<Vec<bf16>>(x, 0, 0, 0, 0, C);
@@ -442,7 +442,7 @@ int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, fl
     else colsum_scalar_kernel<bf16><<<grid, block, 0, s>>>((const bf16*)x, R, C, scratch);
   }
   VCA_LAUNCH_CHECK();
-  d2f_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C);
+  d2f_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, out, C, accumulate);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

@@ -28,6 +28,7 @@ class Config:
     use_tc = True          # use the tcgen05 kernels when dtype is bf16 and the geometry is supported
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
+    fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
 
 
 cfg = Config()
@@ -62,6 +63,19 @@ def _needed(ctx, i: int) -> bool:
         return bool(torch._C._will_engine_execute_node(fn))
     except RuntimeError:
         return True
+
+
+def _grad_sink(p):
+    """The parameter's own fp32 .grad view inside its FlatGroup (trainer.py) when this backward pass may add into it
+    directly -- a plain backward (no create_graph) over a leaf that the trainer re-homed.  The wgrad / column-sum
+    kernels accumulate with fp32 atomics anyway, so this is exactly AccumulateGrad's `grad += g`, minus the zero-fill
+    of a temporary and the add kernel (two launches per parameter per backward)."""
+    if p is None or not cfg.fuse_grad_accum or torch.is_grad_enabled() or not getattr(p, "_vca_flat", False):
+        return None
+    g = p.grad
+    if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
+        return None
+    return g
 
 
 def _require_cuda(*ts):
@@ -155,10 +169,11 @@ def _conv_dgrad_raw(dy, w, stride, pad, xshape):
     return dx
 
 
-def _conv_wgrad_raw(x, dy, stride, pad, wshape):
+def _conv_wgrad_raw(x, dy, stride, pad, wshape, out=None):
+    """dw (fp32, parameter layout); every wgrad kernel ADDS into its destination, so `out` may be a live .grad view."""
     g, oshape = _geom(x.shape, wshape, stride, pad)
     assert tuple(dy.shape) == tuple(oshape), (dy.shape, oshape)
-    dw = torch.zeros(wshape, dtype=torch.float32, device=x.device)
+    dw = torch.zeros(wshape, dtype=torch.float32, device=x.device) if out is None else out
     if _tc_ok(g, 2, x.dtype):
         lib().call("vca_conv_wgrad_tc", g, dy, x, dw)
     else:
@@ -175,6 +190,7 @@ class ConvFn(Function):
         x = _c(x)
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
+        ctx.bias_leaf = bias if (bias is not None and bias.is_leaf) else None   # only consulted by _grad_sink
         return _conv_fwd_raw(x, w, bias, stride, pad)
 
     @staticmethod
@@ -185,9 +201,17 @@ class ConvFn(Function):
         if _needed(ctx, 0):
             dx = ConvDgradFn.apply(dy, w, ctx.stride, ctx.pad, tuple(x.shape))
         if _needed(ctx, 1):
-            dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
+            sink = _grad_sink(w)
+            if sink is not None:
+                _conv_wgrad_raw(x, dy, ctx.stride, ctx.pad, tuple(w.shape), out=sink)   # dw stays None: already accumulated
+            else:
+                dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
         if ctx.has_bias and _needed(ctx, 2):
-            db = ColSumFn.apply(dy)
+            sink = _grad_sink(ctx.bias_leaf)
+            if sink is not None:
+                _colsum_raw(dy, out=sink, accumulate=True)
+            else:
+                db = ColSumFn.apply(dy)
         return dx, dw, db, None, None
 
 
@@ -234,18 +258,23 @@ class ConvWgradFn(Function):
         return g_x, g_dy, None, None, None
 
 
+def _colsum_raw(x, out=None, accumulate=False):
+    x = _c(x)
+    C = x.shape[-1]
+    if out is None:
+        out = torch.empty(C, dtype=torch.float32, device=x.device)
+    scratch = torch.empty(C, dtype=torch.float64, device=x.device)
+    lib().call("vca_colsum", _dt(x), x, x.numel() // C, C, scratch, out, 1 if accumulate else 0)
+    return out
+
+
 class ColSumFn(Function):
     """fp32 per-channel sum over all leading dims (bias gradient)."""
 
     @staticmethod
     def forward(ctx, x):
-        x = _c(x)
         ctx.xshape, ctx.xdtype = tuple(x.shape), x.dtype
-        C = x.shape[-1]
-        out = torch.empty(C, dtype=torch.float32, device=x.device)
-        scratch = torch.empty(C, dtype=torch.float64, device=x.device)
-        lib().call("vca_colsum", _dt(x), x, x.numel() // C, C, scratch, out)
-        return out
+        return _colsum_raw(x)
 
     @staticmethod
     def backward(ctx, g):

@@ -45,6 +45,7 @@ class FlatGroup:
             p.data = self.flat[o:o + n].view(p.shape)
             p.grad = self.grad[o:o + n].view(p.shape)
             p._vca_epoch = self.epoch
+            p._vca_flat = True   # ops._grad_sink: backward kernels may accumulate straight into p.grad
 
     def zero_grad(self):
         self.grad.zero_()
