@@ -97,6 +97,8 @@ class Trainer:
         ops.set_precision(precision)
         self.lrs = lrs
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
+        self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
+        self._branch_streams = None
         self.device = torch.device(device)
         self.mods = dict(v_front=M.Visual_front(1), gen=M.Decoder(), post=M.Postnet(), dis1=M.Discriminator(phase='1'),
                          dis2=M.Discriminator(phase='2'), dis3=M.Discriminator(phase='3'), s_dis=M.sync_Discriminator(temp))
@@ -126,6 +128,37 @@ class Trainer:
             dp.allreduce_flat(group.grad, self.pg, bucket_elems)
         cur.wait_stream(self.comm_stream)
 
+    def _branches(self, fns):
+        """Run independent sub-graphs concurrently: fns[0] on the current stream, the others on side streams that fork
+        from / join back into it (in a CUDA-graph capture these become parallel branches).  The discriminators share no
+        parameters and only read common inputs, and autograd replays each branch's backward on the stream its forward
+        ran on, so the small-grid kernels of the low-resolution discriminators fill the SMs that the tails of the
+        full-resolution one leave idle -- forward and backward."""
+        if not self.parallel_branches or len(fns) < 2:
+            return [f() for f in fns]
+        if self._branch_streams is None:
+            self._branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(len(fns) - 1)]   # all are used by every fork
+        cur = torch.cuda.current_stream()
+        outs, used = [None] * len(fns), []
+        for i in range(1, len(fns)):
+            st = self._branch_streams[(i - 1) % len(self._branch_streams)]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs[i] = fns[i]()
+            used.append(st)
+        outs[0] = fns[0]()
+        for st in used:
+            cur.wait_stream(st)
+        return outs
+
+    def _join_branches(self):
+        """After a backward pass: the branch backward kernels (incl. the wgrad kernels that accumulate straight into
+        the flat .grad buffer, which autograd's own leaf-stream bookkeeping does not see) ran on the side streams."""
+        if self._branch_streams is not None:
+            cur = torch.cuda.current_stream()
+            for st in self._branch_streams:
+                cur.wait_stream(st)
+
     # -- one step -------------------------------------------------------------------------------------------------
     def step(self, vid, mel, spec, vid_len, noise=None):
         """vid (B,1,T,112,112), mel (B,1,80,4T), spec (B,1,321,4T) device fp32; vid_len int32 device tensor or list."""
@@ -150,23 +183,27 @@ class Trainer:
         T = phon.size(1)
         sdet = sent.detach()
         reals = [t.detach().requires_grad_(True) for t in (mel1, mel2, mel)]
-        ur, cr, gp = [], [], []
-        for d, x in zip(dis, reals):
-            u, c = d(x, sdet, T)
-            ur.append(u); cr.append(c)
+        g_det = [x.detach() for x in g]
+
+        def d_branch(i):
+            """discriminator i on its real and fake mel + the R1 penalty of the real pass (train.py:176-200)"""
+            def run():
+                u, c = dis[i](reals[i], sdet, T)
+                gr = torch.autograd.grad(u.sum(), reals[i], create_graph=True)[0]     # R1 (train.py:188-194)
+                pen = ops.sum_sq(gr, 1.0 / gr.size(0))
+                uf_, cf_ = dis[i](g_det[i], sdet, T)
+                return u, c, pen, uf_, cf_
+            return run
         # phon is NOT detached in the reference (train.py:186): the sync loss sends a gradient into the visual
         # front-end CNN during the D backward, and the G backward traverses that CNN a second time.  The CNN weights
         # do not change in between, so we take d(dis_loss)/d(phon) here on a detached leaf and inject it into the
         # single G-phase traversal below -- the same sum of the two gradients, one CNN backward instead of two.
         phon_leaf = phon.detach().requires_grad_(True) if self.merge_vfront_backward else phon
-        sync_loss = s_dis(phon_leaf, reals[2]).mean()
-        for u, x in zip(ur, reals):
-            gr = torch.autograd.grad(u.sum(), x, create_graph=True)[0]     # R1 (train.py:188-194)
-            gp.append(ops.sum_sq(gr, 1.0 / gr.size(0)))
-        uf, cf = [], []
-        for d, x in zip(dis, g):
-            u, c = d(x.detach(), sdet, T)
-            uf.append(u); cf.append(c)
+        res = self._branches([d_branch(2), d_branch(1), d_branch(0), lambda: s_dis(phon_leaf, reals[2]).mean()])
+        sync_loss = res[3]
+        by_d = [res[2], res[1], res[0]]                                    # back to dis1, dis2, dis3 order
+        ur, cr, gp = [r[0] for r in by_d], [r[1] for r in by_d], [r[2] for r in by_d]
+        uf, cf = [r[3] for r in by_d], [r[4] for r in by_d]
         real_loss = sum(M.gan_loss(x, True) for x in ur + cr) / 3 + sum(gp) / 3
         fake_loss = sum(M.gan_loss(x, False) for x in uf + cf) / 3
         dis_loss = real_loss + fake_loss + (0.5 if self.lrs else 1.0) * sync_loss
@@ -175,6 +212,7 @@ class Trainer:
             dis_loss.backward(inputs=self.D.params + [phon_leaf])
         else:
             dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
+        self._join_branches()
         self._st = dict(mel=mel, mel1=mel1, mel2=mel2, spec=spec, phon=phon, phon_leaf=phon_leaf, sdet=sdet, g=g, T=T,
                         out=dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
                                  fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp])))
@@ -186,11 +224,10 @@ class Trainer:
         g, sdet, T, phon = st["g"], st["sdet"], st["T"], st["phon"]
         self.d_opt.step(1.0 / self.world)
         gs = m["post"](g[2])
-        ug, cg = [], []
-        for d, x in zip(dis, g):
-            u, c = d(x, sdet, T)
-            ug.append(u); cg.append(c)
-        g_sync = m["s_dis"](phon.detach(), g[2], True).mean()
+        res = self._branches([lambda: dis[2](g[2], sdet, T), lambda: dis[1](g[1], sdet, T), lambda: dis[0](g[0], sdet, T),
+                              lambda: m["s_dis"](phon.detach(), g[2], True).mean()])
+        ug, cg = [res[2][0], res[1][0], res[0][0]], [res[2][1], res[1][1], res[0][1]]
+        g_sync = res[3]
         g_adv = sum(M.gan_loss(x, True) for x in ug + cg) / 3
         k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
         recon = (ops.l1_mean(g[0], st["mel1"], k) + ops.l1_mean(g[1], st["mel2"], k) + ops.l1_mean(g[2], st["mel"], k)) / 3 \
@@ -201,6 +238,7 @@ class Trainer:
             torch.autograd.backward([gen_loss, phon], [None, st["phon_leaf"].grad], inputs=self.G.params)
         else:
             gen_loss.backward(inputs=self.G.params)
+        self._join_branches()
         st["out"].update(gen_loss=gen_loss.detach(), g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(),
                          g2=g[1].detach(), g3=g[2].detach(), gs=gs.detach())
 
