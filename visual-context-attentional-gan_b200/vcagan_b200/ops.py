@@ -29,6 +29,9 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    param_grad_streams = ()  # side streams for those accumulations (installed by the Trainer; () = current stream)
+    _pg_next = 0
+    _pg_used = set()         # side streams with work queued since the last join
 
 
 cfg = Config()
@@ -76,6 +79,35 @@ def _grad_sink(p):
     if g is None or g.dtype != torch.float32 or not g.is_contiguous() or g.shape != p.shape:
         return None
     return g
+
+
+class _param_grad_stream:
+    """Context: run the enclosed launches on the next of cfg.param_grad_streams (round robin), ordered after everything
+    already queued on the current stream; `tensors` are kept alive for that stream (record_stream).  No-op when the
+    trainer has not installed side streams."""
+
+    def __init__(self, *tensors):
+        self.tensors = tensors
+        self.ctx = None
+
+    def __enter__(self):
+        streams = cfg.param_grad_streams
+        if not streams:
+            return self
+        cfg._pg_next = (cfg._pg_next + 1) % len(streams)
+        st = streams[cfg._pg_next]
+        cfg._pg_used.add(st)
+        st.wait_stream(torch.cuda.current_stream())
+        for t in self.tensors:
+            t.record_stream(st)
+        self.ctx = torch.cuda.stream(st)
+        self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            self.ctx.__exit__(*exc)
+        return False
 
 
 def _require_cuda(*ts):
@@ -198,20 +230,22 @@ class ConvFn(Function):
         x, w = ctx.saved_tensors
         dy = _c(dy)
         dx = dw = db = None
+        w_sink = _grad_sink(w) if _needed(ctx, 1) else None
+        b_sink = _grad_sink(ctx.bias_leaf) if (ctx.has_bias and _needed(ctx, 2)) else None
+        if w_sink is not None or b_sink is not None:
+            # Parameter gradients that land straight in the flat .grad buffer have no consumer in the autograd graph:
+            # they run on a side stream and overlap the dgrad chain (joined by Trainer._join_branches before Adam).
+            with _param_grad_stream(x, dy):
+                if w_sink is not None:
+                    _conv_wgrad_raw(x, dy, ctx.stride, ctx.pad, tuple(w.shape), out=w_sink)   # dw stays None
+                if b_sink is not None:
+                    _colsum_raw(dy, out=b_sink, accumulate=True)
         if _needed(ctx, 0):
             dx = ConvDgradFn.apply(dy, w, ctx.stride, ctx.pad, tuple(x.shape))
-        if _needed(ctx, 1):
-            sink = _grad_sink(w)
-            if sink is not None:
-                _conv_wgrad_raw(x, dy, ctx.stride, ctx.pad, tuple(w.shape), out=sink)   # dw stays None: already accumulated
-            else:
-                dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
-        if ctx.has_bias and _needed(ctx, 2):
-            sink = _grad_sink(ctx.bias_leaf)
-            if sink is not None:
-                _colsum_raw(dy, out=sink, accumulate=True)
-            else:
-                db = ColSumFn.apply(dy)
+        if _needed(ctx, 1) and w_sink is None:
+            dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
+        if ctx.has_bias and _needed(ctx, 2) and b_sink is None:
+            db = ColSumFn.apply(dy)
         return dx, dw, db, None, None
 
 

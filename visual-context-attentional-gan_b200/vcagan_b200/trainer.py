@@ -117,6 +117,10 @@ class Trainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        # weight / bias gradients that accumulate straight into the flat .grad buffer overlap the dgrad chain
+        ops.cfg.param_grad_streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(2)) if self.parallel_branches else ()
+        if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the branch streams are intentional
 
     # -- data-parallel exchange ---------------------------------------------------------------------------------
     def _allreduce(self, group: FlatGroup, bucket_elems: int = 8 << 20):
@@ -154,10 +158,13 @@ class Trainer:
     def _join_branches(self):
         """After a backward pass: the branch backward kernels (incl. the wgrad kernels that accumulate straight into
         the flat .grad buffer, which autograd's own leaf-stream bookkeeping does not see) ran on the side streams."""
+        cur = torch.cuda.current_stream()
         if self._branch_streams is not None:
-            cur = torch.cuda.current_stream()
             for st in self._branch_streams:
                 cur.wait_stream(st)
+        for st in ops.cfg._pg_used:         # parameter-gradient side streams with work since the last join
+            cur.wait_stream(st)
+        ops.cfg._pg_used.clear()
 
     # -- one step -------------------------------------------------------------------------------------------------
     def step(self, vid, mel, spec, vid_len, noise=None):
