@@ -212,6 +212,9 @@ def run_ours(args):
     # dominant kernel family: the tcgen05 implicit-GEMM conv (fwd + dgrad share one kernel); timed live per launch
     roof = None
     # every rank runs the instrumented step (it contains the gradient all-reduces); only rank 0 reports it
+    # (serialised: the concurrent stream branches are switched off so that each launch is timed alone on its stream)
+    tr.parallel_branches = False
+    V.ops.cfg.param_grad_streams = ()
     prof = V.lib().profile_step(lambda: tr.step(vid, mel, spec, lens))
     barrier()
     if world > 1:

@@ -415,24 +415,37 @@ class Discriminator(nn.Module):
                                   nn.Conv2d(dim_out, dim_out, 5, 1, 0), nn.LeakyReLU(0.2), Avgpool(), nn.Linear(dim_out, num_class))
 
     def forward(self, x, c, vid_max_length):
+        h = self.features(x, vid_max_length)
+        return self.uncond_head(h), self.cond_head(h, c, vid_max_length)
+
+    # The three stages of forward(), callable separately: only cond_head needs the sentence embedding, so the trainer
+    # can start the trunk, the unconditional head and the R1 penalty of the real pass before the visual front-end ends.
+    def features(self, x, vid_max_length):
         f_len = final_length(vid_max_length)
-        B = x.size(0)
-        cm = ops.spatial_mean(ops.cast(c, torch.float32).permute(0, 2, 1).contiguous().unsqueeze(1))   # (B,512)
         h = _in_cl(x)
         h = _conv(h, self.main[0])
         for blk in list(self.main)[1:]:
             h = blk(h)                                                       # (B,5,f_len,C)
         if h.shape[1] != 5 or h.shape[2] != f_len:
             raise ValueError(f"discriminator map {tuple(h.shape[1:3])} does not match (5, final_length={f_len})")
+        return h
+
+    def uncond_head(self, h):
         u = _conv(ops.lrelu(h), self.uncond[1])
         u = ops.cast(ops.spatial_mean(ops.lrelu(u)), torch.float32)
         u = ops.linear(u, self.uncond[4].weight, self.uncond[4].bias)
+        return u.view(h.size(0), -1)
+
+    def cond_head(self, h, c, vid_max_length):
+        f_len = final_length(vid_max_length)
+        B = h.size(0)
+        cm = ops.spatial_mean(ops.cast(c, torch.float32).permute(0, 2, 1).contiguous().unsqueeze(1))   # (B,512)
         ct = ops.cast(ops.spatial_tile(cm, 5 * f_len), cfg.dtype).view(B, 5, f_len, -1)
         k = _conv(ops.lrelu(torch.cat([h, ct], 3)), self.cond[1])
         k = _conv(ops.lrelu(k), self.cond[3])
         k = ops.cast(ops.spatial_mean(ops.lrelu(k)), torch.float32)
         k = ops.linear(k, self.cond[6].weight, self.cond[6].bias)
-        return u.view(B, -1), k.view(B, -1)
+        return k.view(B, -1)
 
 
 class sync_Discriminator(nn.Module):

@@ -140,8 +140,8 @@ class Trainer:
         full-resolution one leave idle -- forward and backward."""
         if not self.parallel_branches or len(fns) < 2:
             return [f() for f in fns]
-        if self._branch_streams is None:
-            self._branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(len(fns) - 1)]   # all are used by every fork
+        assert len(fns) == 4
+        self._ensure_branch_streams()
         cur = torch.cuda.current_stream()
         outs, used = [None] * len(fns), []
         for i in range(1, len(fns)):
@@ -153,6 +153,25 @@ class Trainer:
         outs[0] = fns[0]()
         for st in used:
             cur.wait_stream(st)
+        return outs
+
+    def _ensure_branch_streams(self):
+        if self._branch_streams is None:
+            self._branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]   # every fork uses all three
+
+    def _fork(self, fns, stream_idx):
+        """Start fns[k] on branch stream stream_idx[k] (ordered after the current stream) WITHOUT joining: the current
+        stream carries on with independent work; `_join_branches` (or the next `_branches` fork) orders it back."""
+        if not self.parallel_branches:
+            return [f() for f in fns]
+        self._ensure_branch_streams()
+        cur = torch.cuda.current_stream()
+        outs = []
+        for f, k in zip(fns, stream_idx):
+            st = self._branch_streams[k]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                outs.append(f())
         return outs
 
     def _join_branches(self):
@@ -184,20 +203,33 @@ class Trainer:
         gen.fixed_noise = noise
         self.G.zero_grad()                                                # train.py:168
         mel1, mel2 = bilinear_down(mel, 4), bilinear_down(mel, 2)          # train.py:170-171
+        T = vid.size(2)
+        reals = [t.detach().requires_grad_(True) for t in (mel1, mel2, mel)]
+
+        def real_early(i):
+            """trunk + unconditional head + R1 penalty of the real pass (train.py:176-194): needs no generator output and
+            no sentence embedding, so it runs on a branch stream underneath the visual front-end / generator forward"""
+            def run():
+                h = dis[i].features(reals[i], T)
+                u = dis[i].uncond_head(h)
+                gr = torch.autograd.grad(u.sum(), reals[i], create_graph=True)[0]     # R1 (train.py:188-194)
+                return h, u, ops.sum_sq(gr, 1.0 / gr.size(0))
+            return run
+        early = self._fork([real_early(2), real_early(1), real_early(0)], [2, 0, 1])
+        early = {2: early[0], 1: early[1], 0: early[2]}
         phon, sent = v_front(vid)
         g = gen(sent, phon, vid_len)                                       # g1, g2, g3
         gen.fixed_noise = None
-        T = phon.size(1)
+        assert phon.size(1) == T
         sdet = sent.detach()
-        reals = [t.detach().requires_grad_(True) for t in (mel1, mel2, mel)]
         g_det = [x.detach() for x in g]
+        self._join_branches()
 
         def d_branch(i):
-            """discriminator i on its real and fake mel + the R1 penalty of the real pass (train.py:176-200)"""
+            """conditional head of the real pass, then discriminator i on its fake mel (train.py:176-200)"""
             def run():
-                u, c = dis[i](reals[i], sdet, T)
-                gr = torch.autograd.grad(u.sum(), reals[i], create_graph=True)[0]     # R1 (train.py:188-194)
-                pen = ops.sum_sq(gr, 1.0 / gr.size(0))
+                h, u, pen = early[i]
+                c = dis[i].cond_head(h, sdet, T)
                 uf_, cf_ = dis[i](g_det[i], sdet, T)
                 return u, c, pen, uf_, cf_
             return run
