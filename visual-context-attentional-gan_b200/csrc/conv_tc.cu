@@ -519,7 +519,10 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
   p.tiles_w = (g->OW + p.tw - 1) / p.tw; p.tiles_h = (g->OH + p.th - 1) / p.th;
   p.num_ptiles = p.tiles_w * p.tiles_h * ((g->N + p.tn - 1) / p.tn);
   p.KW = g->KW; p.ph = g->ph; p.pw = g->pw;
+  // ci per CTA: the kernel is L2->SM bound, and a 256-wide tile re-reads the dY atoms half as often (12 instead of 16
+  // atoms per pixel tile at Cin = 512); taken when it does not pad Cin by more than a fifth.
   p.BNc = g->Cin >= 128 ? 128 : ((g->Cin + 15) / 16) * 16;
+  if (g->Cin >= 256 && ((g->Cin + 255) / 256) * 256 * 5 <= g->Cin * 6) p.BNc = 256;
   p.ci_tiles = (g->Cin + p.BNc - 1) / p.BNc;
   const int co_tiles = (g->Cout + TILE_ROWS - 1) / TILE_ROWS;
   p.a_atoms = g->Cout >= TILE_ROWS ? 2 : (g->Cout + KC - 1) / KC;   // per co tile; tail tiles rely on TMA zero fill
