@@ -155,7 +155,10 @@ TC_CASES = [
     (300, 128, 1, 1, 256, 1, 0),   # GEMM with a ragged M tile
     (2, 64, 20, 25, 128, 5, 2),    # generator-like 5x5
     (3, 192, 20, 19, 128, 5, 2),   # attconv1 channels (3 K chunks), ragged W
-    (2, 32, 12, 30, 32, 5, 2),     # Cin = 32 (half-filled K chunk)
+    (2, 32, 12, 30, 32, 5, 2),     # 32 -> 32 5x5, even W: pixel-pair merged path (ops._conv5_via_pairs)
+    (3, 32, 9, 50, 32, 5, 2),      # ... ragged tiles
+    (2, 32, 7, 25, 32, 5, 2),      # odd W: plain 32-channel path (half-filled K chunk)
+    (2, 256, 20, 19, 512, 3, 1),   # wgrad with 256-wide input-channel tiles
     (4, 256, 7, 7, 256, 3, 1),     # resnet layer3-like, multi-image box
     (5, 128, 5, 9, 128, 5, 0),     # discriminator uncond: pad 0
     (2, 96, 10, 21, 64, 5, 2),     # attconv2 channels

@@ -297,3 +297,63 @@ int pack_weight_tiled(int dtype, const float* w, void* wf, void* wd, int Cout, i
   if (cudaGetLastError() != cudaSuccess) { vca_set_error("pack_tiled_kernel launch failed"); return VCA_ERR_CUDA; }
   return 1;
 }
+
+// ---- pixel-pair merge of a small-channel convolution -----------------------------------------------------------
+// A (Cin -> Cout, KH x 5, pad 2, stride 1) convolution over [N,H,W,Cin] is the SAME linear map as a
+// (2Cin -> 2Cout, KH x 3, pad 1) convolution over the free view [N,H,W/2,2Cin] (two neighbouring pixels = one
+// 2Cin-channel pixel) with the Toeplitz-expanded weight
+//     w2[p*Cout+co][s*Cin+ci][kh][jj] = w[co][ci][kh][2jj+s-p]   (0 outside 0..4),
+// p / s = position of the output / input pixel inside its pair.  For Cin = Cout = 32 that doubles the MMA N (the
+// tensor pipe of the SS-mode kernels is bound by the A-operand read, so N = 32 caps it at 25 %) for 1.2x the MACs.
+namespace {
+__global__ void pair_expand_kernel(const float* __restrict__ w, float* __restrict__ w2, int Cout, int Cin, int KH) {
+  const long long total = 4LL * Cout * Cin * KH * 3;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int jj = (int)(r % 3); r /= 3;
+    const int kh = (int)(r % KH); r /= KH;
+    const int ci2 = (int)(r % (2 * Cin)); const int co2 = (int)(r / (2 * Cin));
+    const int p = co2 / Cout, co = co2 - p * Cout, s = ci2 / Cin, ci = ci2 - s * Cin;
+    const int kw = 2 * jj + s - p;
+    w2[i] = (kw >= 0 && kw < 5) ? w[(((long long)co * Cin + ci) * KH + kh) * 5 + kw] : 0.f;
+  }
+}
+// adjoint: dw[co][ci][kh][kw] (+)= sum over (p, s, jj) with 2jj+s-p == kw of dw2[p*Cout+co][s*Cin+ci][kh][jj]
+__global__ void pair_contract_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int Cout, int Cin, int KH,
+                                     int accumulate) {
+  const long long total = (long long)Cout * Cin * KH * 5;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int kw = (int)(r % 5); r /= 5;
+    const int kh = (int)(r % KH); r /= KH;
+    const int ci = (int)(r % Cin); const int co = (int)(r / Cin);
+    float a = 0.f;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const int t = kw + p - s;
+        if (t >= 0 && (t & 1) == 0 && t / 2 < 3)
+          a += dw2[((((long long)(p * Cout + co)) * (2 * Cin) + s * Cin + ci) * KH + kh) * 3 + t / 2];
+      }
+    dw[i] = a + (accumulate ? dw[i] : 0.f);
+  }
+}
+}  // namespace
+
+extern "C" {
+// w [Cout][Cin][KH][5] fp32 -> w2 [2Cout][2Cin][KH][3] fp32
+int vca_pair_expand_weight(const float* w, float* w2, int Cout, int Cin, int KH, cudaStream_t s) {
+  VCA_CHECK_ARG(w && w2 && Cout > 0 && Cin > 0 && KH > 0);
+  pair_expand_kernel<<<vca_grid_1d(4LL * Cout * Cin * KH * 3, 256), 256, 0, s>>>(w, w2, Cout, Cin, KH);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// dw2 [2Cout][2Cin][KH][3] -> dw [Cout][Cin][KH][5] (accumulate != 0: added to the existing contents)
+int vca_pair_contract_wgrad(const float* dw2, float* dw, int Cout, int Cin, int KH, int accumulate, cudaStream_t s) {
+  VCA_CHECK_ARG(dw2 && dw && Cout > 0 && Cin > 0 && KH > 0);
+  pair_contract_kernel<<<vca_grid_1d((long long)Cout * Cin * KH * 5, 256), 256, 0, s>>>(dw2, dw, Cout, Cin, KH, accumulate);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+}

@@ -66,29 +66,38 @@ __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const unsigned
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
-    for (int oh = h >> 1; oh <= ((h + 1) >> 1); ++oh) {   // windows oh cover rows 2oh-1..2oh+1
-      if (oh >= OH) continue;
-      const int kh = h - (oh * 2 - 1);
-      for (int ow = w >> 1; ow <= ((w + 1) >> 1); ++ow) {
-        if (ow >= OW) continue;
-        const int code = kh * 3 + (w - (ow * 2 - 1));
-        const long long o = (((long long)n * OH + oh) * OW + ow) * C + cv * V;
-        float g[V];
-        VT::load(dy + o, g);
-        if (V == 8) {
-          const uint2 c = *reinterpret_cast<const uint2*>(idx + o);
+    // windows oh cover rows 2oh-1..2oh+1: at most 2 x 2 windows contain this pixel.  All (<= 4) gradient / argmax
+    // loads are issued before any is used (the kernel is latency bound otherwise: 4 dependent L2 round trips).
+    const int ohs[2] = {h >> 1, (h + 1) >> 1}, ows[2] = {w >> 1, (w + 1) >> 1};
+    const bool vh[2] = {ohs[0] < OH, ohs[1] < OH && ohs[1] != ohs[0]}, vw[2] = {ows[0] < OW, ows[1] < OW && ows[1] != ows[0]};
+    float g[4][V];
+    unsigned long long codes[4];
 #pragma unroll
-          for (int k = 0; k < V; ++k) if ((int)(((k < 4 ? c.x : c.y) >> (8 * (k & 3))) & 0xffu) == code) acc[k] += g[k];
-        } else if (V == 4) {
-          const unsigned c = *reinterpret_cast<const unsigned*>(idx + o);
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-          for (int k = 0; k < V; ++k) if ((int)((c >> (8 * (k & 3))) & 0xffu) == code) acc[k] += g[k];
-        } else {
+      for (int b = 0; b < 2; ++b) {
+        const int q = a * 2 + b;
+        codes[q] = 0xffffffffffffffffull;                      // matches no argmax code
 #pragma unroll
-          for (int k = 0; k < V; ++k) if (idx[o + k] == code) acc[k] += g[k];
+        for (int k = 0; k < V; ++k) g[q][k] = 0.f;
+        if (vh[a] && vw[b]) {
+          const long long o = (((long long)n * OH + ohs[a]) * OW + ows[b]) * C + cv * V;
+          VT::load(dy + o, g[q]);
+          if (V == 8) codes[q] = *reinterpret_cast<const unsigned long long*>(idx + o);
+          else if (V == 4) codes[q] = *reinterpret_cast<const unsigned*>(idx + o);
+          else codes[q] = idx[o];
         }
       }
-    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int q = a * 2 + b;
+        const unsigned code = (unsigned)((h - (ohs[a] * 2 - 1)) * 3 + (w - (ows[b] * 2 - 1)));
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if ((unsigned)((codes[q] >> (8 * k)) & 0xffull) == code) acc[k] += g[q][k];
+      }
     VT::store(dx + i * V, acc);
   }
 }

@@ -89,6 +89,10 @@ class _Lib:
             for a in args:
                 if isinstance(a, ConvGeom):
                     flops = 2 * a.N * a.OD * a.OH * a.OW * a.Cout * a.Cin * a.KD * a.KH * a.KW
+                    if (a.KH, a.KW, a.ph, a.pw) == (5, 3, 2, 1):
+                        # pixel-pair merged 5x5 conv (ops._conv5_via_pairs; the model has no native 5x3 conv): count the
+                        # ALGORITHMIC work of the original (C/2 -> C/2, 5x5) layer, not the 1.2x Toeplitz-padded MACs
+                        flops = flops * 5 // 6
                     tag = "x".join(str(v) for v in a.key())
             if name == "vca_gemm_simt":
                 flops = 2 * args[7] * args[8] * args[9] * args[10]

@@ -29,6 +29,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
     param_grad_streams = ()  # side streams for those accumulations (installed by the Trainer; () = current stream)
     _pg_next = 0
     _pg_used = set()         # side streams with work queued since the last join
@@ -365,8 +366,49 @@ def _conv3x3_s2_via_s2d(x, w, bias):
     return ConvFn.apply(xs, w2, bias, (1, 1), (0, 0))
 
 
+class PairExpandFn(Function):
+    """w (Cout,Cin,KH,5) -> Toeplitz-expanded w2 (2Cout,2Cin,KH,3) of the pixel-pair merged convolution (linear)."""
+
+    @staticmethod
+    def forward(ctx, w):
+        ctx.wshape = tuple(w.shape)
+        ctx.w_leaf = w if w.is_leaf else None
+        Cout, Cin, KH, KW = w.shape
+        assert KW == 5
+        w2 = torch.empty((2 * Cout, 2 * Cin, KH, 3), dtype=torch.float32, device=w.device)
+        lib().call("vca_pair_expand_weight", _c(w.detach().float()), w2, Cout, Cin, KH)
+        return w2
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dw2):
+        Cout, Cin, KH, _ = ctx.wshape
+        sink = _grad_sink(ctx.w_leaf)
+        if sink is not None:
+            lib().call("vca_pair_contract_wgrad", _c(dw2), sink, Cout, Cin, KH, 1)
+            return None
+        dw = torch.empty(ctx.wshape, dtype=torch.float32, device=dw2.device)
+        lib().call("vca_pair_contract_wgrad", _c(dw2), dw, Cout, Cin, KH, 0)
+        return dw
+
+
+def _conv5_via_pairs(x, w, bias):
+    """(32 -> 32, KH x 5, pad 2) convolution as a (64 -> 64, KH x 3, pad 1) convolution over pixel pairs: the view
+    [N,H,W/2,64] of x costs nothing, the weight is Toeplitz-expanded (1.2x the MACs), and the tcgen05 kernels run with
+    N = 64 instead of 32 -- their tensor pipe is bound by the A-operand shared-memory read, i.e. proportional to N."""
+    N, H, W, C = x.shape
+    w2 = PairExpandFn.apply(w)
+    b2 = None if bias is None else torch.cat([bias, bias])
+    y2 = ConvFn.apply(x.view(N, H, W // 2, 2 * C), w2, b2, (1, 1), (w.shape[2] // 2, 1))
+    return y2.view(N, H, W, w.shape[0])
+
+
 def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
     stride, pad = tuple(stride), tuple(pad)
+    if (cfg.pair_merge and x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and stride == (1, 1)
+            and tuple(w.shape[1:]) == (32, 5, 5) and w.shape[0] == 32 and pad == (2, 2) and x.shape[-1] == 32
+            and x.shape[2] % 2 == 0 and x.is_contiguous()):
+        return _conv5_via_pairs(x, w, bias)
     if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0:
         k = tuple(w.shape[2:])
         if k == (3, 3) and pad == (1, 1) and x.shape[-1] >= 8:
