@@ -166,9 +166,12 @@ TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("hs", [1, 2])
 @pytest.mark.parametrize("case", TC_CASES)
-def test_conv_tc_bf16(V, case):
+def test_conv_tc_bf16(V, case, hs):
+    """hs = 2 forces the halo-resident / streamed-weights kernel (conv_tc_hs.cu) wherever its geometry fits"""
     N, Cin, H, W, Cout, k, p = case
+    assert V.lib().cdll.vca_set_option(b"hs_mode", hs) == 0
     g = torch.Generator().manual_seed(sum(case))
     x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float().requires_grad_(True)
     w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).bfloat16().float().requires_grad_(True)
@@ -195,6 +198,7 @@ def test_conv_tc_bf16(V, case):
         assert e["bias"] < BF16_TOL, e
     finally:
         V.set_precision("fp32")
+        V.lib().cdll.vca_set_option(b"hs_mode", 1)
 
 
 @pytest.mark.parametrize("case", [(4, 64, 28, 28, 128, 3), (3, 128, 7, 7, 256, 3), (2, 128, 40, 30, 256, 3), (3, 64, 28, 28, 128, 1),

@@ -22,6 +22,9 @@
 // conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
                 const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
+// conv_tc_hs.cu: halo-resident activations + streamed weights for 64..128 output channels (same return convention)
+int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
+                const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
 
@@ -426,7 +429,8 @@ uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return 
 int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
              const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s) {
   {
-    const int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
+    int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
+    if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
     if (r != 0) return r < 0 ? r : VCA_OK;
   }
   FwdParams p;

@@ -18,6 +18,7 @@ using namespace tc;
 extern int g_wgws_mode;     // conv_tc_wgrad_ws.cu
 extern int g_bn_vec;        // bn.cu
 extern int g_gru_cluster, g_gru_bs;   // gru_cluster.cu
+extern int g_hs_mode;       // conv_tc_hs.cu
 
 namespace {
 
@@ -281,6 +282,7 @@ int vca_set_option(const char* key, int value) {
   if (eq("bn_vec")) { g_bn_vec = value; return VCA_OK; }
   if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
   if (eq("gru_bs")) { g_gru_bs = value; return VCA_OK; }
+  if (eq("hs_mode")) { g_hs_mode = value; return VCA_OK; }
   vca_set_error("vca_set_option: unknown key %s", key);
   return VCA_ERR_ARG;
 }
