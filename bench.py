@@ -208,7 +208,11 @@ def run_ours(args):
         # n_e2e steps that contains the pinned-host -> device copy of every one of those steps' inputs (step 1's up
         # front, step i+1's on a copy stream underneath step i) and a device -> host read of the losses every step.
         # No L2 flush here: each step's fresh 136 MB of inputs alone exceed the 126 MB L2.
-        torch.cuda.synchronize()
+        tr.stage_inputs(vid_h, mel_h, spec_h)            # untimed warm-up of the feed path (allocates the staging buffers)
+        for i in range(2):
+            out2 = tr.replay_prefetched((vid_h, mel_h, spec_h) if i == 0 else None)
+            _ = torch.stack([out2["gen_loss"], out2["dis_loss"]]).cpu()
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         tr.stage_inputs(vid_h, mel_h, spec_h)

@@ -159,6 +159,8 @@ TC_CASES = [
     (3, 32, 9, 50, 32, 5, 2),      # ... ragged tiles
     (2, 32, 7, 25, 32, 5, 2),      # odd W: plain 32-channel path (half-filled K chunk)
     (2, 256, 20, 19, 512, 3, 1),   # wgrad with 256-wide input-channel tiles
+    (2, 128, 20, 25, 128, 5, 2),   # multi-tap wgrad with two 64-channel chunks of Cin
+    (3, 128, 14, 14, 192, 3, 1),   # ... 3x3, two output-channel tiles
     (4, 256, 7, 7, 256, 3, 1),     # resnet layer3-like, multi-image box
     (5, 128, 5, 9, 128, 5, 0),     # discriminator uncond: pad 0
     (2, 96, 10, 21, 64, 5, 2),     # attconv2 channels

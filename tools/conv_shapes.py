@@ -34,9 +34,11 @@ def main():
     ap.add_argument("--filter", default="")
     ap.add_argument("--ws", type=int, default=1, help="weights-stationary kernel: 0 off, 1 auto, 2 force")
     ap.add_argument("--hs", type=int, default=1, help="halo-resident / streamed-weights kernel: 0 off, 1 auto, 2 force")
+    ap.add_argument("--wgws", type=int, default=1, help="multi-tap wgrad kernel: 0 off, 1 auto (Cin <= 128), 2 any Cin")
     args = ap.parse_args()
     assert lib().cdll.vca_set_option(b"ws_mode", args.ws) == 0
     assert lib().cdll.vca_set_option(b"hs_mode", args.hs) == 0
+    assert lib().cdll.vca_set_option(b"wgws_mode", args.wgws) == 0
     V.set_precision("bf16")
     dev = torch.device("cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

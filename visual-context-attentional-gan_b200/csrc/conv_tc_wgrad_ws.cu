@@ -27,6 +27,7 @@ struct WgWsParams {
   int NF, OH, OW, Cout, Cin, taps;
   int KH, KW, ph, pw;
   int th, tw, P, tiles_w, tiles_h, num_tiles, tiles_per_split;
+  int ci_tiles;          // 64-channel chunks of Cin (one CTA column each)
   int G;                 // taps per group
   int groups;            // number of groups (KH when grouping along kw, 1 when grouping along kh)
   int along_kh;          // 1: group = the KH taps of a (KH,1) filter, spacing P rows; 0: group = KW taps of row kh, spacing 1
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = blockIdx.z;                                // tap group
-  const int co0 = blockIdx.y * 128;
+  const int co0 = (blockIdx.y / p.ci_tiles) * 128;
+  const int ci0 = (blockIdx.y % p.ci_tiles) * KC;
   const int t_beg = blockIdx.x * p.tiles_per_split;
   const int t_end = min(t_beg + p.tiles_per_split, p.num_tiles);
   const int iters = t_end - t_beg;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], p.x_tx_bytes + (uint32_t)(p.a_atoms * p.th) * p.a_row_tx_bytes);
           // X halo: rows oh0 - ph + kh0 ... (+ x_rows), columns ow0 - pw ... (+ P)
-          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], 0, ow0 - p.pw, oh0 - p.ph + kh0, n);
+          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], ci0, ow0 - p.pw, oh0 - p.ph + kh0, n);
           // dY: one box per image row, written at pitch P so that tile row r*P + w is pixel (oh0 + r, ow0 + w)
           for (int a = 0; a < p.a_atoms; ++a)
             for (int r = 0; r < p.th; ++r)
@@ -135,13 +137,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
       for (int g = 0; g < p.G; ++g) {
         const int tap = p.along_kh ? g * p.KW : kh0 * p.KW + g;       // (kh = g, kw = 0)  or  (kh0, kw = g)
         for (int c = 0; c < KC; c += 16) {
-          if (c >= p.Cin) break;                                      // warp-uniform
+          if (ci0 + c >= p.Cin) break;                                // warp-uniform
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * KC + c), v);
           if (co < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (c + i < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + c + i) * p.taps + tap, v[i]);
+              if (ci0 + c + i < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci0 + c + i) * p.taps + tap, v[i]);
           }
         }
       }
@@ -154,16 +156,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
 
 }  // namespace
 
-int g_wgws_mode = 1;   // 0 off, 1 auto
+int g_wgws_mode = 1;   // 0 off, 1 auto, 2 any Cin
 
 // 1 = launched, 0 = not applicable, < 0 error.  dw fp32 [Cout][Cin][taps], zero on entry.
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s) {
   if (!g_wgws_mode) return 0;
   const int taps = g.KH * g.KW;
-  if (g.Cin > KC || taps < 2 || g.KW > 5 || g.KH > 8) return 0;
+  // Cin > 64 runs as 64-channel chunks (one CTA column each): the dY tile is then re-read per chunk, but a stage still
+  // feeds G x 8 MMAs from ~50 KB, against 8 MMAs from 64 KB in conv_tc_wgrad_kernel.
+  // Measured (tools/conv_shapes.py --wgws): faster for 128 ch (408 -> 513 TF/s 5x5, 505 -> 579 3x3), 256 ch 5x5
+  // (711 -> 868) and 640 -> 512 (744 -> 857); slower where the 256-wide streaming tiles fit exactly (512 ch: 1054 vs
+  // 700) and on small maps where the pitched tile wastes rows (7x7: 610 vs 326) -- hence the rule below.
+  if (g.Cin > 4096 || taps < 2 || g.KW > 5 || g.KH > 8) return 0;
   WgWsParams p;
   p.NF = g.N; p.OH = g.OH; p.OW = g.OW; p.Cout = g.Cout; p.Cin = g.Cin; p.taps = taps;
   p.KH = g.KH; p.KW = g.KW; p.ph = g.ph; p.pw = g.pw;
+  p.ci_tiles = (g.Cin + KC - 1) / KC;
   p.along_kh = g.KW == 1;
   p.G = p.along_kh ? g.KH : g.KW;
   p.groups = p.along_kh ? 1 : g.KH;
@@ -179,6 +187,7 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
     if (util > best) { best = util; best_tw = tw; best_th = th; }
   }
   if (best_tw == 0) return 0;
+  if (g_wgws_mode == 1 && g.Cin > 2 * KC && !(best >= 0.6 && (g.Cin <= 256 || g.Cin % 256 != 0))) return 0;
   p.tw = best_tw; p.th = best_th; p.P = p.tw + g.KW - 1;
   p.tiles_w = (g.OW + p.tw - 1) / p.tw; p.tiles_h = (g.OH + p.th - 1) / p.th;
   const long long nt = (long long)g.N * p.tiles_w * p.tiles_h;
@@ -204,7 +213,7 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   p.tmem_cols = pow2_cols(p.G * KC);
   p.dw = dw;
   const int co_tiles = (g.Cout + 127) / 128;
-  const long long base_ctas = (long long)co_tiles * p.groups;
+  const long long base_ctas = (long long)co_tiles * p.ci_tiles * p.groups;
   int split = (int)(vca_num_sms() / base_ctas);   // one CTA per SM (smem-bound): never spill into a second wave
   if (split < 1) split = 1; if (split > p.num_tiles) split = p.num_tiles;
   p.tiles_per_split = (p.num_tiles + split - 1) / split;
@@ -224,7 +233,8 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
     }
     attr_set = true;
   }
-  dim3 grid((unsigned)split, (unsigned)co_tiles, (unsigned)p.groups);
+  if ((long long)co_tiles * p.ci_tiles > 65535) return 0;
+  dim3 grid((unsigned)split, (unsigned)(co_tiles * p.ci_tiles), (unsigned)p.groups);
   conv_tc_wgrad_ws_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, p);
   VCA_LAUNCH_CHECK();
   return 1;
