@@ -157,6 +157,7 @@ TC_CASES = [
     (3, 192, 20, 19, 128, 5, 2),   # attconv1 channels (3 K chunks), ragged W
     (2, 32, 12, 30, 32, 5, 2),     # 32 -> 32 5x5, even W: pixel-pair merged path (ops._conv5_via_pairs)
     (3, 32, 9, 50, 32, 5, 2),      # ... ragged tiles
+    (2, 64, 12, 30, 64, 5, 2),     # ... 64 -> 64 as 128 -> 128 over pairs
     (2, 32, 7, 25, 32, 5, 2),      # odd W: plain 32-channel path (half-filled K chunk)
     (2, 256, 20, 19, 512, 3, 1),   # wgrad with 256-wide input-channel tiles
     (2, 128, 20, 25, 128, 5, 2),   # multi-tap wgrad with two 64-channel chunks of Cin
