@@ -150,3 +150,74 @@ def test_graph_replay_matches_eager():
         assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 3 * rel_l2(oe["g3"].cpu(), o0["g3"].cpu()) + 1e-3
     finally:
         V.set_precision("fp32")
+
+
+def test_stream_branches_match_serial_step():
+    """The concurrent schedule (discriminators as stream branches, real-pass trunks under the generator forward,
+    parameter-gradient kernels on side streams) must compute what the single-stream schedule computes."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    vid, mel, sp, noise = golden_inputs()
+    lens = torch.tensor([20, 13], dtype=torch.int32).cuda()
+    try:
+        res = []
+        for par in (False, False, True):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision="fp32", state=state, dropout=False)
+            if not par:
+                tr.parallel_branches = False
+                V.ops.cfg.param_grad_streams = ()
+            tr.G.zero_grad()
+            tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)       # D phase incl. backward, no optimizer yet
+            torch.cuda.synchronize()
+            gd = tr.D.grad.clone()
+            tr._phase_g(); out = tr._phase_end()
+            torch.cuda.synchronize()
+            res.append((gd, tr.G.grad.clone(), {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
+            del tr
+        (d0, g0, o0), (de, ge, oe), (d1, g1, o1) = res
+        nd, ng = rel_l2(de.cpu(), d0.cpu()), rel_l2(ge.cpu(), g0.cpu())     # serial-vs-serial noise (fp32 atomics order)
+        print("serial-vs-serial grad noise", nd, ng, "branches-vs-serial", rel_l2(d1.cpu(), d0.cpu()), rel_l2(g1.cpu(), g0.cpu()))
+        assert rel_l2(d1.cpu(), d0.cpu()) <= 3 * nd + 1e-5
+        assert rel_l2(g1.cpu(), g0.cpu()) <= 3 * ng + 1e-5
+        for k in ("gen_loss", "dis_loss", "recon", "sync_loss"):
+            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-5 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
+    finally:
+        V.set_precision("fp32")
+
+
+def test_prefetched_feed_matches_direct_replay():
+    """Trainer.stage_inputs / replay_prefetched (next batch copied on a copy stream under the current step) must feed the
+    captured graphs the same inputs, in the same order, as replay(vid, mel, spec) does."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    vid, mel, sp, noise = golden_inputs()
+    lens = torch.tensor([20, 20], dtype=torch.int32).cuda()
+    batches = [(vid.pin_memory(), mel.pin_memory(), sp.pin_memory()),
+               ((0.5 * vid.flip(0)).pin_memory(), (-mel.flip(0)).pin_memory(), sp.flip(0).contiguous().pin_memory())]
+    try:
+        losses = []
+        for prefetched in (False, True):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision="fp32", state=state, dropout=False)
+            tr.capture(vid.cuda(), mel.cuda(), sp.cuda(), lens, warmup=1, noise=noise)
+            seq = []
+            if prefetched:
+                tr.stage_inputs(*batches[0])
+                for i in range(4):
+                    out = tr.replay_prefetched(batches[(i + 1) % 2] if i < 3 else None)
+                    seq.append((float(out["gen_loss"]), float(out["dis_loss"])))
+            else:
+                for i in range(4):
+                    out = tr.replay(*batches[i % 2])
+                    seq.append((float(out["gen_loss"]), float(out["dis_loss"])))
+            losses.append(seq)
+            del tr
+        print("direct", losses[0], "prefetched", losses[1])
+        for (ga, da), (gb, db) in zip(*losses):
+            assert abs(ga - gb) <= 2e-3 * max(1.0, abs(ga)) and abs(da - db) <= 2e-3 * max(1.0, abs(da))
+        assert abs(losses[0][0][0] - losses[0][1][0]) > 1e-3      # the two batches really differ
+    finally:
+        V.set_precision("fp32")

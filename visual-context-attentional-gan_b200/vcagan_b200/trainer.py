@@ -157,7 +157,7 @@ class Trainer:
 
     def _ensure_branch_streams(self):
         if self._branch_streams is None:
-            self._branch_streams = [torch.cuda.Stream(device=self.device) for _ in range(3)]   # every fork uses all three
+            self._branch_streams = [torch.cuda.Stream(device=self.device, priority=-1) for _ in range(3)]   # every fork uses all three
 
     def _fork(self, fns, stream_idx):
         """Start fns[k] on branch stream stream_idx[k] (ordered after the current stream) WITHOUT joining: the current
@@ -306,11 +306,15 @@ class Trainer:
         pool = torch.cuda.graph_pool_handle()
         self._graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
         n0 = lib().launches
-        with torch.cuda.graph(self._graphs[0], pool=pool):
+        # The critical path (main chain + discriminator branches) is captured on high-priority streams, the
+        # parameter-gradient side streams keep the default (lowest) priority: when both have CTAs pending, the SMs
+        # go to the chain the step is waiting for.
+        cap = torch.cuda.Stream(device=self.device, priority=-1)
+        with torch.cuda.graph(self._graphs[0], pool=pool, stream=cap):
             self._phase_d(*self._sin, noise=self._snoise)
-        with torch.cuda.graph(self._graphs[1], pool=pool):
+        with torch.cuda.graph(self._graphs[1], pool=pool, stream=cap):
             self._phase_g()
-        with torch.cuda.graph(self._graphs[2], pool=pool):
+        with torch.cuda.graph(self._graphs[2], pool=pool, stream=cap):
             self._sout = self._phase_end()
         self.launches_per_step = lib().launches - n0
         return self
