@@ -72,6 +72,11 @@ int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t st
 int vca_tanh_bwd(int dtype, const void* dy, const void* y, void* dx, long long n, cudaStream_t stream);
 int vca_axpby(int dtype, const void* a, const void* b, void* out, long long n, float alpha, float beta, cudaStream_t stream);
 int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, int accumulate, cudaStream_t stream);
+/* Row-tap combine of a KH x KW conv over channels that are constant along H (the phoneme features tiled along the mel
+ * axis, generator.py:249-250): y[b,f,t,c] = yn[b,f,t,c] + sum_{kh: 0 <= f+kh-ph < F} R[b,t,kh*C+c];  bwd: dR = the
+ * matching row sums of dy. */
+int vca_row_taps_fwd(int dtype, const void* yn, const void* R, void* y, int B, int F, int T, int C, int KH, int ph, cudaStream_t stream);
+int vca_row_taps_bwd(int dtype, const void* dy, void* dR, int B, int F, int T, int C, int KH, int ph, cudaStream_t stream);
 int vca_cast(int dt_in, int dt_out, const void* x, void* y, long long n, cudaStream_t stream);
 int vca_mul(int dtype, const void* x, const void* m, void* y, long long n, cudaStream_t stream);
 

@@ -454,3 +454,39 @@ def test_rng_moments(V):
     assert abs(float(n.mean())) < 5e-3 and abs(float(n.std()) - 1) < 5e-3
     d = V.ops.dropout(torch.ones(1 << 20, device="cuda"), 0.3, True)
     assert abs(float((d == 0).float().mean()) - 0.3) < 5e-3 and abs(float(d.max()) - 1 / 0.7) < 1e-5
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_conv_rowconst(V, prec):
+    """conv over an input whose first channels are constant along H (tiled phoneme features): the collapsed form
+    (one row + row-tap combine, ops.conv_rowconst) against the plain convolution, forward and all gradients."""
+    g = torch.Generator().manual_seed(21)
+    B, Fq, T, nc, nn_, Cout = 2, 20, 23, 64, 16, 48
+    row = torch.randn(B, nc, 1, T, generator=g)
+    xn = torch.randn(B, nn_, Fq, T, generator=g)
+    w = (torch.randn(Cout, nc + nn_, 5, 5, generator=g) / math.sqrt((nc + nn_) * 25))
+    b = torch.randn(Cout, generator=g)
+    if prec == "bf16":
+        row, xn, w = row.bfloat16().float(), xn.bfloat16().float(), w.bfloat16().float()
+    row.requires_grad_(True); xn.requires_grad_(True); w.requires_grad_(True); b.requires_grad_(True)
+    x = torch.cat([row.expand(B, nc, Fq, T), xn], 1)
+    y = F.conv2d(x, w, b, 1, 2)
+    dy = torch.randn(y.shape, generator=g)
+    if prec == "bf16":
+        dy = dy.bfloat16().float()
+    y.backward(dy)
+    V.set_precision(prec)
+    try:
+        dt = torch.bfloat16 if prec == "bf16" else torch.float32
+        rowd = row.detach().cuda().requires_grad_(True); xnd = xn.detach().cuda().requires_grad_(True)
+        wd = w.detach().cuda().requires_grad_(True); bd = b.detach().cuda().requires_grad_(True)
+        xd = torch.cat([rowd.expand(B, nc, Fq, T), xnd], 1).permute(0, 2, 3, 1).contiguous().to(dt)   # channels-last
+        yd = V.ops.conv_rowconst(xd, nc, wd, bd, (2, 2))
+        yd.backward(cl(dy).cuda().to(dt))
+        tol = BF16_TOL if prec == "bf16" else FP32_TOL
+        e = dict(fwd=rel_l2(nchw(yd.detach().float().cpu()), y), drow=rel_l2(rowd.grad.cpu(), row.grad), dxn=rel_l2(xnd.grad.cpu(), xn.grad),
+                 dw=rel_l2(wd.grad.cpu(), w.grad), db=rel_l2(bd.grad.cpu(), b.grad))
+        print("rowconst", prec, e)
+        assert max(e.values()) < tol, e
+    finally:
+        V.set_precision("fp32")

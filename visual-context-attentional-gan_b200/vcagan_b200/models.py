@@ -237,11 +237,18 @@ class GenResBlk(nn.Module):
         if self.learned_sc:
             self.conv1x1 = nn.Conv2d(dim_in, dim_out, 1, 1, 0, bias=False)
 
-    def forward(self, x):
+    def forward(self, x, const_channels=0):
+        """const_channels > 0: the caller guarantees that the first `const_channels` channels of x are constant along
+        dim 1 (the tiled phoneme features of generator.py:249-250).  BN + LeakyReLU are per-channel maps, so that still
+        holds at conv1's input and the constant part of conv1 collapses to one row (ops.conv_rowconst): an exact
+        saving the reference does not take (SURVEY appendix A #14 i)."""
         r = ops.bn_act(x, self.norm1, ACT_LRELU, 0.2)
         if self.upsample:
             r = ops.upsample2(r)
-        r = _conv(r, self.conv1)
+        if const_channels and not self.upsample and cfg.rowconst:
+            r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding))
+        else:
+            r = _conv(r, self.conv1)
         r = ops.bn_act(r, self.norm2, ACT_LRELU, 0.2)
         r = _conv(r, self.conv2)
         s = ops.upsample2(x) if self.upsample else x
@@ -376,8 +383,8 @@ class Decoder(nn.Module):
         n = self._noise(B, T, x.device)                                      # (B,20,T,128)
         xt = ops.spatial_tile(ops.cast(x.contiguous(), cfg.dtype).view(B, T * x.size(2)), 20).view(B, 20, T, x.size(2))
         h = torch.cat([xt, n], 3)                                            # (B,20,T,640)
-        for blk in self.decode:
-            h = blk(h)
+        for i, blk in enumerate(self.decode):
+            h = blk(h, const_channels=x.size(2)) if i == 0 else blk(h)       # xt is constant along the 20 mel rows
         for blk in self.g1:
             h = blk(h)
         f1 = h

@@ -29,6 +29,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
     pair_merge_channels = (32,)   # 64 -> 64 as 128 -> 128 over pairs works too but measured no faster (62.2 vs 61.8 ms/step)
     param_grad_streams = ()  # side streams for those accumulations (installed by the Trainer; () = current stream)
@@ -586,6 +587,45 @@ class AxpbyFn(Function):
 
 def add_scale(a, b, s):
     return AxpbyFn.apply(a, b, float(s), float(s))
+
+
+class RowTapsFn(Function):
+    """y[b,f,t,c] = yn[b,f,t,c] + sum_{kh: 0 <= f+kh-ph < F} R[b,0,t,kh*C+c]: adds the collapsed form of a KH x KW
+    convolution over channels that are constant along F (see csrc/row_taps.cu) to the convolution of the others."""
+
+    @staticmethod
+    def forward(ctx, yn, R, KH, ph):
+        yn, R = _c(yn), _c(R)
+        B, F_, T, C = yn.shape
+        assert tuple(R.shape) == (B, 1, T, KH * C) and R.dtype == yn.dtype, (R.shape, yn.shape)
+        ctx.dims = (B, F_, T, C, KH, ph)
+        y = torch.empty_like(yn)
+        lib().call("vca_row_taps_fwd", _dt(yn), yn, R, y, B, F_, T, C, KH, ph)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, F_, T, C, KH, ph = ctx.dims
+        dy = _c(dy)
+        dR = None
+        if ctx.needs_input_grad[1]:
+            dR = torch.empty((B, 1, T, KH * C), dtype=dy.dtype, device=dy.device)
+            lib().call("vca_row_taps_bwd", _dt(dy), dy, dR, B, F_, T, C, KH, ph)
+        return (dy if ctx.needs_input_grad[0] else None), dR, None, None
+
+
+def conv_rowconst(x, nc, w, bias, pad):
+    """conv(x, w, bias, stride 1, pad) for x (B,F,T,C) whose first `nc` channels are constant along F: those channels
+    go through ONE row (kh folded into the output channels of a 1 x KW conv) + the row-tap combine, the remaining
+    channels through the ordinary conv.  Exact up to summation order; F/KH-fold fewer MACs on the constant part."""
+    Cout, C, KH, KW = w.shape
+    rc = x[:, :1, :, :nc].contiguous()                                             # the single distinct row
+    rn = x[..., nc:].contiguous()
+    w_rows = w[:, :nc].permute(2, 0, 1, 3).reshape(KH * Cout, nc, 1, KW)            # R[kh] = conv1d(row, w[:, :nc, kh, :])
+    R = conv(rc, w_rows, None, (1, 1), (0, pad[1]))
+    yn = conv(rn, w[:, nc:].contiguous(), bias, (1, 1), pad)
+    return RowTapsFn.apply(yn, R, KH, pad[0])
 
 
 def scale(a, s):
