@@ -125,6 +125,7 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
 
 struct FwdParams {
   int NF, OH, OW, Cout;          // output tensor [NF, OH, OW, Cout]
+  int IH, IW;                    // input spatial dims (to skip taps whose whole shifted box is padding)
   int tn, th, tw;                // pixel box
   int tiles_w, tiles_h;          // tile counts along W and H (tiles along NF = gridDim.x / (tiles_w*tiles_h))
   int KH, KW, ph, pw;            // input coord = output coord + k - p
@@ -179,6 +180,8 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
         const int kc = it % p.kchunks; const int tap = it / p.kchunks;
         const int a = tap / p.KW, b = tap % p.KW;
         const int wtap = p.flip ? (p.KH - 1 - a) * p.KW + (p.KW - 1 - b) : tap;
+        const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
+        if (r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0) continue;   // the whole box is zero padding
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
         tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &tmA, &full[stage], kc * KC, ow0 + b - p.pw, oh0 + a - p.ph, n0);
@@ -190,8 +193,13 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_ROWS, p.BN, 0, 0);
-      int stage = 0, kcur = 0; uint32_t phase = 0;
+      int stage = 0, kcur = 0; uint32_t phase = 0, started = 0;
       for (int it = 0; it < iters; ++it) {
+        {   // same skip rule as the producer (dgrad onto a map much taller than dY: most filter rows see only padding)
+          const int tap = it / p.kchunks, a = tap / p.KW, b = tap % p.KW;
+          const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
+          if (r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0) continue;
+        }
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a0 = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
@@ -203,9 +211,10 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
           if (k < ksteps) {
             const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
             const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (it | k) != 0);
+            umma_bf16(tmem_base, ad, bd, idesc, (started | (uint32_t)k) != 0);
           }
         }
+        started = 1;
         umma_commit(&empty[stage]);  // implies tcgen05.fence::before_thread_sync
         if (++stage == S) { stage = 0; phase ^= 1; }
       }
@@ -414,10 +423,10 @@ int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, 
 }
 
 // choose the pixel box (tn, th, tw), tn*th*tw <= 128, that minimises the number of tiles
-void choose_box(int NF, int H, int W, int& tn, int& th, int& tw) {
+void choose_box(int NF, int H, int W, int& tn, int& th, int& tw, int max_th = 1 << 30) {
   long long best = -1; tn = th = tw = 1;
   for (int w = 1; w <= W && w <= 128; ++w) {
-    for (int h = 1; h <= H && w * h <= 128; ++h) {
+    for (int h = 1; h <= H && h <= max_th && w * h <= 128; ++h) {
       int n = 128 / (w * h); if (n > NF) n = NF; if (n < 1) n = 1;
       long long tiles = (long long)((W + w - 1) / w) * ((H + h - 1) / h) * ((NF + n - 1) / n);
       if (best < 0 || tiles < best || (tiles == best && w > tw)) { best = tiles; tn = n; th = h; tw = w; }
@@ -435,7 +444,10 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   }
   FwdParams p;
   p.NF = NF; p.OH = OH; p.OW = OW; p.Cout = Nout;
-  choose_box(NF, OH, OW, p.tn, p.th, p.tw);
+  p.IH = IH; p.IW = IW;
+  // An input shorter than the filter (dgrad of the discriminator heads: dY is 1 x 14, dX 5 x 18) means every output
+  // row sees a single filter row; one-row boxes let the kernel skip the other KH-1 (all-padding) taps.
+  choose_box(NF, OH, OW, p.tn, p.th, p.tw, IH < KH ? 1 : 1 << 30);
   p.tiles_w = (OW + p.tw - 1) / p.tw; p.tiles_h = (OH + p.th - 1) / p.th;
   int tiles_n = (NF + p.tn - 1) / p.tn;
   p.KH = KH; p.KW = KW; p.ph = ph; p.pw = pw; p.flip = flip;
