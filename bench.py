@@ -243,7 +243,7 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank == 0:
         pk = peaks()
-        fam ={k: v for k, v in prof.items() if k.startswith("vca_conv_") and k.endswith("_tc")}
+        fam ={k: v for k, v in prof.items() if k.startswith("vca_conv_") and (k.endswith("_tc") or k.endswith("_tc_ws"))}
         flops = sum(v["flops"] for v in fam.values()); tms = sum(v["ms"] for v in fam.values())
         n_l = sum(v["n"] for v in fam.values())
         total_ms = sum(v["ms"] for v in prof.values())

@@ -53,6 +53,12 @@ int vca_conv_wgrad_simt(int dtype, const ConvGeom* g, const void* dy, const void
 int vca_conv_tc_supported(const ConvGeom* g, int kind);
 int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t stream);
 int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t stream);
+/* Split-K variants for small-grid, long-K problems (the 5x5 heads of the discriminators on 5x18 maps): the caller lends
+ * an fp32 workspace of vca_conv_tc_workspace(g, kind) bytes (0 = the plain entry points do the same work; kind 0 =
+ * forward, 1 = dgrad); partial sums are red.add-ed into it and a finishing pass adds the bias and writes bf16. */
+int vca_conv_tc_workspace(const ConvGeom* g, int kind);
+int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, float* ws, long long ws_bytes, cudaStream_t stream);
+int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);
 
 

@@ -216,8 +216,10 @@ def test_prefetched_feed_matches_direct_replay():
             losses.append(seq)
             del tr
         print("direct", losses[0], "prefetched", losses[1])
-        for (ga, da), (gb, db) in zip(*losses):
-            assert abs(ga - gb) <= 2e-3 * max(1.0, abs(ga)) and abs(da - db) <= 2e-3 * max(1.0, abs(da))
+        # identical inputs in identical order; what remains is the step-to-step amplification (Adam) of the fp32
+        # atomics-order noise, which grows with every optimizer step taken
+        for (ga, da), (gb, db), tol in zip(losses[0], losses[1], (1e-4, 2e-3, 5e-3, 1e-2)):
+            assert abs(ga - gb) <= tol * max(1.0, abs(ga)) and abs(da - db) <= tol * max(1.0, abs(da)), (ga, gb, da, db)
         assert abs(losses[0][0][0] - losses[0][1][0]) > 1e-3      # the two batches really differ
     finally:
         V.set_precision("fp32")

@@ -23,6 +23,7 @@ SHAPES = [  # name, N, H, W, Cin, Cout, (kh,kw), (ph,pw)
     ("resnet.layer4.conv", 2400, 4, 4, 512, 512, (3, 3), (1, 1)),
     ("v_front.stem(5,1)", 32, 75, 3136, 64, 64, (5, 1), (2, 0)),
     ("dis3.cond.1", 32, 5, 18, 1024, 512, (5, 5), (2, 2)),
+    ("dis3.uncond.1(p0)", 32, 5, 18, 512, 512, (5, 5), (0, 0)),
     ("gru.proj(linear)", 2400, 1, 1, 1024, 1536, (1, 1), (0, 0)),
 ]
 
@@ -34,6 +35,7 @@ def main():
     ap.add_argument("--filter", default="")
     ap.add_argument("--ws", type=int, default=1, help="weights-stationary kernel: 0 off, 1 auto, 2 force")
     ap.add_argument("--hs", type=int, default=1, help="halo-resident / streamed-weights kernel: 0 off, 1 auto, 2 force")
+    ap.add_argument("--splitk", type=int, default=1, help="lend the split-K workspace the library asks for (0 = never split)")
     ap.add_argument("--wgws", type=int, default=1, help="multi-tap wgrad kernel: 0 off, 1 auto (Cin <= 128), 2 any Cin")
     args = ap.parse_args()
     assert lib().cdll.vca_set_option(b"ws_mode", args.ws) == 0
@@ -55,8 +57,11 @@ def main():
         dw = torch.zeros_like(w)
         wf, wd = _packed(w, torch.bfloat16)
         flops = 2 * N * oshape[1] * oshape[2] * Cout * Cin * k[0] * k[1]
-        calls = dict(fwd=lambda: lib().call("vca_conv_fwd_tc", g, x, wd, None, y),
-                     dgrad=lambda: lib().call("vca_conv_dgrad_tc", g, dy, wf, dx),
+        wsf = lib().query("vca_conv_tc_workspace", g, 0) if args.splitk else 0
+        wsd = lib().query("vca_conv_tc_workspace", g, 1) if args.splitk else 0
+        ws = torch.empty(max(wsf, wsd, 4) // 4, dtype=torch.float32, device=dev)
+        calls = dict(fwd=lambda: lib().call("vca_conv_fwd_tc_ws", g, x, wd, None, y, ws if wsf else None, wsf),
+                     dgrad=lambda: lib().call("vca_conv_dgrad_tc_ws", g, dy, wf, dx, ws if wsd else None, wsd),
                      wgrad=lambda: lib().call("vca_conv_wgrad_tc", g, dy, x, dw))
         for kind, fn in calls.items():
             if args.only and kind != args.only:

@@ -136,6 +136,8 @@ struct FwdParams {
   int flip;                      // 1: weight tap index is mirrored (dgrad)
   uint32_t a_bytes, b_bytes;     // bytes the two TMA loads of one stage deliver
   uint32_t tmem_cols;
+  int splits, taps_per_split;    // split-K over the filter taps: blockIdx.z takes taps [z*per, (z+1)*per)
+  float* ws;                     // split-K only: fp32 [pixels][Cout] partial sums (red.add), finished by splitk_finish_kernel
   const float* bias;             // [Cout] or null
   bf16* y;
 };
@@ -160,7 +162,8 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   const int th_i = t % p.tiles_h; const int tn_i = t / p.tiles_h;
   const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
   const int co0 = blockIdx.y * p.BN;
-  const int iters = p.KH * p.KW * p.kchunks;
+  const int tap_beg = blockIdx.z * p.taps_per_split;
+  const int tap_end = min(tap_beg + p.taps_per_split, p.KH * p.KW);
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < S; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -176,47 +179,52 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int it = 0; it < iters; ++it) {
-        const int kc = it % p.kchunks; const int tap = it / p.kchunks;
-        const int a = tap / p.KW, b = tap % p.KW;
-        const int wtap = p.flip ? (p.KH - 1 - a) * p.KW + (p.KW - 1 - b) : tap;
+      int a = tap_beg / p.KW, b = tap_beg - a * p.KW;            // no division inside the loops
+      for (int tap = tap_beg; tap < tap_end; ++tap) {
         const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
-        if (r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0) continue;   // the whole box is zero padding
-        mbar_wait(&empty[stage], phase ^ 1);
-        mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
-        tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &tmA, &full[stage], kc * KC, ow0 + b - p.pw, oh0 + a - p.ph, n0);
-        tma_load_3d(sB + (size_t)stage * b_stage, &tmB, &full[stage], kc * KC, co0, wtap);
-        if (++stage == S) { stage = 0; phase ^= 1; }
+        if (!(r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0)) {   // else: the whole box is zero padding
+          const int wtap = p.flip ? (p.KH - 1 - a) * p.KW + (p.KW - 1 - b) : tap;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            mbar_expect_tx(&full[stage], p.a_bytes + p.b_bytes);
+            tma_load_4d(sA + (size_t)stage * A_STAGE_BYTES, &tmA, &full[stage], kc * KC, c0, r0, n0);
+            tma_load_3d(sB + (size_t)stage * b_stage, &tmB, &full[stage], kc * KC, co0, wtap);
+            if (++stage == S) { stage = 0; phase ^= 1; }
+          }
+        }
+        if (++b == p.KW) { b = 0; ++a; }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc(TILE_ROWS, p.BN, 0, 0);
-      int stage = 0, kcur = 0; uint32_t phase = 0, started = 0;
-      for (int it = 0; it < iters; ++it) {
-        {   // same skip rule as the producer (dgrad onto a map much taller than dY: most filter rows see only padding)
-          const int tap = it / p.kchunks, a = tap / p.KW, b = tap % p.KW;
-          const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
-          if (r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0) continue;
-        }
-        mbar_wait(&full[stage], phase);
-        tc_fence_after();
-        const uint32_t a0 = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
-        const uint32_t b0 = smem_u32(sB + (size_t)stage * b_stage);
-        const int ksteps = (kcur == p.kchunks - 1) ? p.ksteps_last : KC / 16;   // skip the zero-padded tail of a K chunk
-        if (++kcur == p.kchunks) kcur = 0;
+      int stage = 0; uint32_t phase = 0, started = 0;
+      int a = tap_beg / p.KW, b = tap_beg - a * p.KW;
+      for (int tap = tap_beg; tap < tap_end; ++tap) {
+        // same skip rule as the producer (dgrad onto a map much taller than dY: most filter rows see only padding)
+        const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
+        const bool dead = r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0;
+        if (++b == p.KW) { b = 0; ++a; }
+        if (dead) continue;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
+          const uint32_t b0 = smem_u32(sB + (size_t)stage * b_stage);
+          const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : KC / 16;   // skip the zero-padded tail of a K chunk
 #pragma unroll
-        for (int k = 0; k < KC / 16; ++k) {
-          if (k < ksteps) {
-            const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
-            const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
-            umma_bf16(tmem_base, ad, bd, idesc, (started | (uint32_t)k) != 0);
+          for (int k = 0; k < KC / 16; ++k) {
+            if (k < ksteps) {
+              const uint64_t ad = make_desc(a0 + k * 32, 0, 1024);
+              const uint64_t bd = make_desc(b0 + k * 32, 0, 1024);
+              umma_bf16(tmem_base, ad, bd, idesc, (started | (uint32_t)k) != 0);
+            }
           }
+          started = 1;
+          umma_commit(&empty[stage]);  // implies tcgen05.fence::before_thread_sync
+          if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        started = 1;
-        umma_commit(&empty[stage]);  // implies tcgen05.fence::before_thread_sync
-        if (++stage == S) { stage = 0; phase ^= 1; }
       }
       umma_commit(accum_bar);
     }
@@ -233,6 +241,25 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
     bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
     mbar_wait(accum_bar, 0);
     tc_fence_after();
+    if (p.ws) {
+      // split-K: add this CTA's partial sums (if it executed any tap at all) into the fp32 workspace
+      bool any = false;
+      for (int tap = tap_beg; tap < tap_end; ++tap) {
+        const int a = tap / p.KW, b = tap % p.KW;
+        const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
+        any = any || !(r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0);
+      }
+      float* wrow = p.ws + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
+      for (int c = 0; c < p.BN && any; c += 16) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        if (row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (co0 + c + i < p.Cout) atomicAdd(wrow + c + i, v[i]);
+        }
+      }
+    } else
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
@@ -259,6 +286,27 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+// y[m][c] = bf16(ws[m][c] + bias[c]): finishes a split-K convolution
+__global__ void splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ y,
+                                     long long total, int Cout) {
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < total; i += (long long)gridDim.x * blockDim.x * 8) {
+    if (i + 8 <= total && Cout % 8 == 0) {
+      const float4 a = *reinterpret_cast<const float4*>(ws + i), b = *reinterpret_cast<const float4*>(ws + i + 4);
+      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      const int c = (int)(i % Cout);
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k] + (bias ? bias[c + 2 * k] : 0.f), v[2 * k + 1] + (bias ? bias[c + 2 * k + 1] : 0.f));
+        w[k] = *reinterpret_cast<uint32_t*>(&h);
+      }
+      *reinterpret_cast<uint4*>(y + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+      for (long long j = i; j < total && j < i + 8; ++j) y[j] = __float2bfloat16_rn(ws[j] + (bias ? bias[j % Cout] : 0.f));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -435,9 +483,21 @@ void choose_box(int NF, int H, int W, int& tn, int& th, int& tw, int max_th = 1 
 }
 uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
+// Split-K plan of the streaming kernel for small-grid, long-K problems (the 5x5 heads of the discriminators on 5x18
+// maps: 32 CTAs x 200 stages): number of K splits (1 = none) for a grid of `ctas` CTAs and `taps` filter taps.
+int plan_splits(long long ctas, int taps) {
+  if (ctas * 4 > vca_num_sms() || taps < 8) return 1;
+  int sp = (int)(vca_num_sms() / ctas);
+  if (sp > 8) sp = 8;
+  if (sp > taps / 2) sp = taps / 2;
+  return sp < 2 ? 1 : sp;
+}
+
 int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-             const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s) {
-  {
+             const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s, float* ws = nullptr,
+             size_t ws_bytes = 0, size_t* ws_need = nullptr) {
+  if (ws_need) *ws_need = 0;
+  if (!ws_need) {
     int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
     if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
     if (r != 0) return r < 0 ? r : VCA_OK;
@@ -466,7 +526,15 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   // Two CTAs per SM (100 KB each) hide each other's TMA latency on big grids.  A grid that cannot even fill the SMs
   // once (small feature maps of the discriminator heads) gets one deep pipeline per CTA instead: a stage is only
   // 4 MMAs (~0.15-0.3 us) while a TMA round trip is ~1.5 us.
-  const long long total_ctas = ptiles * ((Nout + bn - 1) / bn);
+  long long total_ctas = ptiles * ((Nout + bn - 1) / bn);
+  int splits = plan_splits(total_ctas, KH * KW);
+  const size_t need = (size_t)NF * OH * OW * Nout * sizeof(float);
+  if (ws_need) { *ws_need = splits > 1 ? need : 0; return VCA_OK; }   // planning query only
+  if (splits > 1 && (!ws || ws_bytes < need)) splits = 1;
+  const int taps_per_split = (KH * KW + splits - 1) / splits;
+  splits = (KH * KW + taps_per_split - 1) / taps_per_split;
+  p.splits = splits; p.taps_per_split = taps_per_split; p.ws = splits > 1 ? ws : nullptr;
+  total_ctas *= splits;
   const size_t budget = total_ctas <= vca_num_sms() ? 196 * 1024 : 100 * 1024;
   int stages = (int)(budget / stage_bytes);
   const int max_stages = total_ctas <= vca_num_sms() ? 12 : 6;
@@ -486,9 +554,18 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
     }
     attr_set = true;
   }
-  dim3 grid((unsigned)ptiles, (unsigned)((Nout + bn - 1) / bn), 1);
+  if (p.ws) {
+    p.bias = nullptr;   // added by the finishing pass
+    if (cudaMemsetAsync(ws, 0, need, s) != cudaSuccess) { vca_set_error("split-K workspace memset failed"); return VCA_ERR_CUDA; }
+  }
+  dim3 grid((unsigned)ptiles, (unsigned)((Nout + bn - 1) / bn), (unsigned)splits);
   conv_tc_fwd_kernel<<<grid, 192, smem, s>>>(tmA, tmB, p);
   VCA_LAUNCH_CHECK();
+  if (p.ws) {
+    const long long total = (long long)NF * OH * OW * Nout;
+    splitk_finish_kernel<<<vca_grid_1d(total, 256, 8), 256, 0, s>>>(ws, bias, (bf16*)y, total, Nout);
+    VCA_LAUNCH_CHECK();
+  }
   return VCA_OK;
 }
 
@@ -511,16 +588,36 @@ int vca_conv_tc_supported(const ConvGeom* g, int kind) {
   return 0;
 }
 
+// Bytes of fp32 workspace with which vca_conv_{fwd,dgrad}_tc_ws would run this geometry split-K (0 = no split: the
+// plain entry points do the same work).  kind 0 = forward, 1 = dgrad.
+int vca_conv_tc_workspace(const ConvGeom* g, int kind) {
+  if (!g || kind < 0 || kind > 1 || !vca_conv_tc_supported(g, kind)) return 0;
+  size_t need = 0;
+  if (kind == 0) fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, nullptr, nullptr, nullptr,
+                          nullptr, 0, nullptr, 0, &need);
+  else fwd_like(g->N, g->OH, g->OW, g->Cout, g->IH, g->IW, g->Cin, g->KH, g->KW, g->KH - 1 - g->ph, g->KW - 1 - g->pw, 1, nullptr,
+                nullptr, nullptr, nullptr, 0, nullptr, 0, &need);
+  return need > 0x7fffffff ? 0 : (int)need;
+}
 // x [N,IH,IW,Cin] bf16; wd = packed [taps][Cout][Cin] bf16 (vca_pack_conv_weight "wd"); y [N,OH,OW,Cout] bf16.
+// ws / ws_bytes: optional fp32 workspace (see vca_conv_tc_workspace); null = never split.
+int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, float* ws, long long ws_bytes,
+                       cudaStream_t s) {
+  VCA_CHECK_ARG(g && x && wd && y && ws_bytes >= 0 && vca_conv_tc_supported(g, 0));
+  return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, bias, y, s, ws,
+                  (size_t)ws_bytes);
+}
 int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t s) {
-  VCA_CHECK_ARG(g && x && wd && y && vca_conv_tc_supported(g, 0));
-  return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, bias, y, s);
+  return vca_conv_fwd_tc_ws(g, x, wd, bias, y, nullptr, 0, s);
 }
 // dy [N,OH,OW,Cout] bf16; wf = packed [taps][Cin][Cout] bf16 (vca_pack_conv_weight "wf"); dx [N,IH,IW,Cin] bf16.
-int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t s) {
-  VCA_CHECK_ARG(g && dy && wf && dx && vca_conv_tc_supported(g, 1));
+int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t s) {
+  VCA_CHECK_ARG(g && dy && wf && dx && ws_bytes >= 0 && vca_conv_tc_supported(g, 1));
   return fwd_like(g->N, g->OH, g->OW, g->Cout, g->IH, g->IW, g->Cin, g->KH, g->KW, g->KH - 1 - g->ph, g->KW - 1 - g->pw, 1, dy, wf,
-                  nullptr, dx, s);
+                  nullptr, dx, s, ws, (size_t)ws_bytes);
+}
+int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t s) {
+  return vca_conv_dgrad_tc_ws(g, dy, wf, dx, nullptr, 0, s);
 }
 // dw fp32 [Cout][Cin][taps], zero on entry (accumulated with red.add across pixel splits).
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t s) {

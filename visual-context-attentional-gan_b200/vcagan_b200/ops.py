@@ -29,6 +29,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
     pair_merge_channels = (32,)   # 64 -> 64 as 128 -> 128 over pairs works too but measured no faster (62.2 vs 61.8 ms/step)
@@ -180,13 +181,22 @@ def _tc_ok(g: ConvGeom, kind: int, dtype) -> bool:
     return cfg.use_tc and dtype == torch.bfloat16 and lib().query("vca_conv_tc_supported", g, kind) == 1
 
 
+def _splitk_workspace(g: ConvGeom, kind: int, device):
+    """fp32 scratch the library asks for when it wants to run this geometry split-K (small grid, long K), else (None, 0)."""
+    nb = lib().query("vca_conv_tc_workspace", g, kind) if cfg.splitk else 0
+    if nb <= 0:
+        return None, 0
+    return torch.empty(nb // 4, dtype=torch.float32, device=device), nb
+
+
 def _conv_fwd_raw(x, w, bias, stride, pad):
     g, oshape = _geom(x.shape, w.shape, stride, pad)
     wf, wd = _packed(w, x.dtype)
     y = torch.empty(oshape, dtype=x.dtype, device=x.device)
     b = None if bias is None else _c(bias.detach().float())
     if _tc_ok(g, 0, x.dtype):
-        lib().call("vca_conv_fwd_tc", g, x, wd, b, y)
+        ws, nb = _splitk_workspace(g, 0, x.device)
+        lib().call("vca_conv_fwd_tc_ws", g, x, wd, b, y, ws, nb)
     else:
         lib().call("vca_conv_fwd_simt", _dt(x), g, x, wf, b, y)
     return y
@@ -198,7 +208,8 @@ def _conv_dgrad_raw(dy, w, stride, pad, xshape):
     wf, wd = _packed(w, dy.dtype)
     dx = torch.empty(xshape, dtype=dy.dtype, device=dy.device)
     if _tc_ok(g, 1, dy.dtype):
-        lib().call("vca_conv_dgrad_tc", g, dy, wf, dx)
+        ws, nb = _splitk_workspace(g, 1, dy.device)
+        lib().call("vca_conv_dgrad_tc_ws", g, dy, wf, dx, ws, nb)
     else:
         lib().call("vca_conv_dgrad_simt", _dt(dy), g, dy, wd, dx)
     return dx
