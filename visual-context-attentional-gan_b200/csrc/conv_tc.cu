@@ -374,11 +374,11 @@ __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constan
     if (warp == 0) {
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
+        int tw_i, th_i, tn_i;                                        // tile coordinates, advanced without divisions
+        { int t = pt_beg; tw_i = t % p.tiles_w; t /= p.tiles_w; th_i = t % p.tiles_h; tn_i = t / p.tiles_h; }
         for (int it = 0; it < iters; ++it) {
-          int t = pt_beg + it;
-          const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-          const int th_i = t % p.tiles_h; const int tn_i = t / p.tiles_h;
           const int ow0 = tw_i * p.tw, oh0 = th_i * p.th, n0 = tn_i * p.tn;
+          if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++tn_i; } }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], (uint32_t)(p.a_atoms + p.b_atoms) * p.atom_bytes);
           for (int a = 0; a < p.a_atoms; ++a)

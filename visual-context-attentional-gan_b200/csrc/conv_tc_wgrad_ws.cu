@@ -82,20 +82,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
     if (warp == 0) {
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
+        int tw_i, th_i, n;                                           // tile coordinates, advanced without divisions
+        { int t = t_beg; tw_i = t % p.tiles_w; t /= p.tiles_w; th_i = t % p.tiles_h; n = t / p.tiles_h; }
         for (int it = 0; it < iters; ++it) {
-          int t = t_beg + it;
-          const int tw_i = t % p.tiles_w; t /= p.tiles_w;
-          const int th_i = t % p.tiles_h; const int n = t / p.tiles_h;
           const int ow0 = tw_i * p.tw, oh0 = th_i * p.th;
+          const int n_cur = n;
+          if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++n; } }
           mbar_wait(&empty[stage], phase ^ 1);
           mbar_expect_tx(&full[stage], p.x_tx_bytes + (uint32_t)(p.a_atoms * p.th) * p.a_row_tx_bytes);
           // X halo: rows oh0 - ph + kh0 ... (+ x_rows), columns ow0 - pw ... (+ P)
-          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], ci0, ow0 - p.pw, oh0 - p.ph + kh0, n);
+          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], ci0, ow0 - p.pw, oh0 - p.ph + kh0, n_cur);
           // dY: one box per image row, written at pitch P so that tile row r*P + w is pixel (oh0 + r, ow0 + w)
           for (int a = 0; a < p.a_atoms; ++a)
             for (int r = 0; r < p.th; ++r)
               tma_load_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)a * ATOM_BYTES + (size_t)r * p.P * 128, &tmDY, &full[stage],
-                          co0 + a * KC, ow0, oh0 + r, n);
+                          co0 + a * KC, ow0, oh0 + r, n_cur);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
