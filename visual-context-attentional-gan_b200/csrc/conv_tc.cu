@@ -486,7 +486,7 @@ uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return 
 // Split-K plan of the streaming kernel for small-grid, long-K problems (the 5x5 heads of the discriminators on 5x18
 // maps: 32 CTAs x 200 stages): number of K splits (1 = none) for a grid of `ctas` CTAs and `taps` filter taps.
 int plan_splits(long long ctas, int taps) {
-  if (ctas * 4 > vca_num_sms() || taps < 8) return 1;
+  if (ctas * 2 > vca_num_sms() || taps < 8) return 1;
   int sp = (int)(vca_num_sms() / ctas);
   if (sp > 8) sp = 8;
   if (sp > taps / 2) sp = taps / 2;
@@ -516,7 +516,11 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   int bn = Nout >= 256 ? 256 : ((Nout + 15) / 16) * 16;
   // keep >= ~1 wave of CTAs when the problem is small: halve BN
   long long ptiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
-  while (bn > 64 && ptiles * ((Nout + bn - 1) / bn) < vca_num_sms() && bn % 32 == 0) bn /= 2;
+  // (with enough filter taps and a workspace on offer, splitting K keeps the MMA N wide instead: a 64-wide tile caps
+  //  the tensor pipe at 50 %)
+  const bool can_split = (ws_need != nullptr || ws != nullptr) && plan_splits(ptiles * ((Nout + bn - 1) / bn), KH * KW) > 1 &&
+                         (ws_need != nullptr || ws_bytes >= (size_t)NF * OH * OW * Nout * sizeof(float));
+  while (!can_split && bn > 64 && ptiles * ((Nout + bn - 1) / bn) < vca_num_sms() && bn % 32 == 0) bn /= 2;
   p.BN = bn;
   p.a_bytes = (uint32_t)(p.tn * p.th * p.tw) * 128u;
   p.b_bytes = (uint32_t)bn * 128u;
