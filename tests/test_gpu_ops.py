@@ -159,6 +159,7 @@ TC_CASES = [
     (3, 32, 9, 50, 32, 5, 2),      # ... ragged tiles
     (2, 64, 12, 30, 64, 5, 2),     # ... 64 -> 64 as 128 -> 128 over pairs
     (2, 32, 7, 25, 32, 5, 2),      # odd W: plain 32-channel path (half-filled K chunk)
+    (2, 64, 1, 40, 321, 1, 0),     # Cout % 8 != 0 (Postnet projection): zero-padded output channels
     (2, 256, 20, 19, 512, 3, 1),   # wgrad with 256-wide input-channel tiles
     (2, 128, 20, 25, 128, 5, 2),   # multi-tap wgrad with two 64-channel chunks of Cin
     (3, 128, 14, 14, 192, 3, 1),   # ... 3x3, two output-channel tiles

@@ -422,6 +422,14 @@ def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
             and w.dim() == 4 and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels
             and pad == (2, 2) and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0 and x.is_contiguous()):
         return _conv5_via_pairs(x, w, bias)
+    if (x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and all(s == 1 for s in stride) and w.shape[0] % 8 != 0
+            and w.shape[0] >= 64 and x.shape[-1] % 8 == 0):
+        # Postnet's 256 -> 321 projection (generator.py:185): the tcgen05 kernels want Cout % 8 == 0 (16-byte rows for the
+        # TMA maps of dgrad / wgrad), so run it with 7 zero output channels appended and hand back the first 321
+        padc = (-w.shape[0]) % 8
+        w2 = torch.cat([w, w.new_zeros((padc,) + tuple(w.shape[1:]))], 0)
+        b2 = None if bias is None else torch.cat([bias, bias.new_zeros(padc)])
+        return ConvFn.apply(x, w2, b2, stride, pad)[..., :w.shape[0]]
     if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0:
         k = tuple(w.shape[2:])
         if k == (3, 3) and pad == (1, 1) and x.shape[-1] >= 8:
