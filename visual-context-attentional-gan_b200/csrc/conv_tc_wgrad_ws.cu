@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
 }  // namespace
 
 int g_wgws_mode = 1;   // 0 off, 1 auto, 2 any Cin
+int g_wgws_waves = 1;  // "wgws_waves": CTAs per SM over the kernel's life (more = shorter CTAs, friendlier to concurrent streams)
 
 // 1 = launched, 0 = not applicable, < 0 error.  dw fp32 [Cout][Cin][taps], zero on entry.
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s) {
@@ -215,7 +216,8 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   p.dw = dw;
   const int co_tiles = (g.Cout + 127) / 128;
   const long long base_ctas = (long long)co_tiles * p.ci_tiles * p.groups;
-  int split = (int)(vca_num_sms() / base_ctas);   // one CTA per SM (smem-bound): never spill into a second wave
+  extern int g_wgws_waves;
+  int split = (int)(g_wgws_waves * vca_num_sms() / base_ctas);   // one CTA per SM (smem-bound): whole waves only
   if (split < 1) split = 1; if (split > p.num_tiles) split = p.num_tiles;
   p.tiles_per_split = (p.num_tiles + split - 1) / split;
   split = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;

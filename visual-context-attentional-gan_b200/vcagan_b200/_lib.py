@@ -63,6 +63,11 @@ class _Lib:
         for name, (res, args) in self.protos.items():
             fn = getattr(self.cdll, name)
             fn.restype, fn.argtypes = res, args
+        # tuning switches from the environment, e.g. VCA_OPTS="wgws_waves=2,hs_mode=0" (see vca_set_option)
+        for kv in filter(None, os.environ.get("VCA_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            if self.cdll.vca_set_option(k.strip().encode(), int(v)) != 0:
+                raise VcaError(f"VCA_OPTS: {self.cdll.vca_last_error().decode()}")
 
     def call(self, name, *args):
         fn = getattr(self.cdll, name)
