@@ -223,3 +223,40 @@ def test_prefetched_feed_matches_direct_replay():
         assert abs(losses[0][0][0] - losses[0][1][0]) > 1e-3      # the two batches really differ
     finally:
         V.set_precision("fp32")
+
+
+def test_lrs_variant_step_matches_oracle():
+    """train_LRS.py:179-243 variant of the step (0.5 x sync loss, L1 on raw mels, plain Adam) at T = 24 with ragged
+    lengths, against the oracle's restatement run on the same weights / inputs / noise (fp32 mode)."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    B, T = 2, 24
+    g = torch.Generator().manual_seed(77)
+    vid = torch.randn(B, 1, T, 112, 112, generator=g)
+    mel = torch.rand(B, 1, 80, 4 * T, generator=g) * 2 - 1
+    sp = torch.rand(B, 1, 321, 4 * T, generator=g)
+    noise = torch.randn(B, 128, 20, T, generator=g)
+    lens = [T, 17]
+    sds = {m: make_state(spec, m, requires_grad=True) for m in O.MODULES}
+    par = lambda ms: [p for m in ms for p in sds[m].values() if p.is_floating_point() and p.requires_grad]   # noqa: E731
+    g_opt = torch.optim.Adam(par(("v_front", "gen", "post")), lr=1e-4, weight_decay=1e-5, amsgrad=False)
+    d_opt = torch.optim.Adam(par(("dis1", "dis2", "dis3", "s_dis")), lr=1e-4, weight_decay=1e-5, amsgrad=False)
+    ref = O.train_step_with_adam(sds, dict(mel=mel, spec=sp, vid=vid, vid_len=lens), noise, g_opt, d_opt, lrs=True)
+    try:
+        state = {m: make_state(spec, m) for m in O.MODULES}
+        tr = Trainer(precision="fp32", state=state, dropout=False, lrs=True)
+        out = tr.step(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise=noise)
+        torch.cuda.synchronize()
+        for k in ("dis_loss", "sync_loss", "real_loss", "fake_loss", "gen_loss", "g_sync", "recon"):
+            r, got = float(ref[k]), float(out[k])
+            assert abs(got - r) <= 1e-4 * max(1.0, abs(r)), (k, got, r)
+        for k in ("g1", "g2", "g3", "gs"):
+            assert rel_l2(out[k].cpu(), ref[k]) < 1e-4, k
+        # post-Adam weights of the well-conditioned heads (no BN in the discriminators): plain Adam, no amsgrad state
+        for mod, key in (("dis3", "uncond.4.weight"), ("dis1", "main.0.weight"), ("post", "postnet.6.weight")):
+            mine = dict(tr.mods[mod].named_parameters())[key].detach().cpu()
+            assert rel_l2(mine, sds[mod][key].detach()) < 1e-4, (mod, key)
+        assert tr.g_opt.vmax is None and tr.d_opt.vmax is None
+    finally:
+        V.set_precision("fp32")
