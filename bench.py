@@ -58,7 +58,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([c.strip() for c in o])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
