@@ -68,10 +68,12 @@ int vca_gemm_simt(int dtA, int dtB, int dtC, const void* A, const void* B, void*
 
 /* ---- BatchNorm (+residual) (+PReLU/LeakyReLU/ReLU), activations (visual_front.py:12-13, resnet.py:34-63,
  *      generator.py:9,52,95,105-126,179,209-225,325-329) --------------------------------------------------- */
-int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
+/* sums_prezeroed / flags bit 0: `sums` is a persistent scratch that is zero on entry and left zeroed (no memset launch);
+ * flags bit 1 of vca_bn_act_bwd: dgamma / dbeta / dprelu are added to in place (gradient accumulation). */
+int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, int sums_prezeroed, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
 int vca_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t stream);
 int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, cudaStream_t stream);
-int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, cudaStream_t stream);
+int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags, cudaStream_t stream);
 int vca_lrelu_fwd(int dtype, const void* x, void* y, long long n, float slope, cudaStream_t stream);
 int vca_lrelu_bwd(int dtype, const void* dy, const void* x, void* dx, long long n, float slope, cudaStream_t stream);
 int vca_tanh_fwd(int dtype, const void* x, void* y, long long n, cudaStream_t stream);

@@ -37,9 +37,9 @@ for R, C, act, has_res in SHAPES:
     dg, db, dp = f32(), f32(), f32()
     nb = x.numel() * 2 / 1e6   # MB per tensor pass
     t_copy = timed(lambda: y.copy_(x))
-    t_st = timed(lambda: L.call("vca_bn_stats", 1, x, R, C, 1e-5, 0.1, sums, mean, invstd, rm, rv))
+    t_st = timed(lambda: L.call("vca_bn_stats", 1, x, R, C, 1e-5, 0.1, sums, 0, mean, invstd, rm, rv))
     t_fw = timed(lambda: L.call("vca_bn_act_fwd", 1, x, res, y, R, C, mean, invstd, gamma, beta, act, 0.2, pw))
-    bw = lambda: L.call("vca_bn_act_bwd", 1, dy, x, res, dx, dres, R, C, mean, invstd, gamma, beta, act, 0.2, pw, 1, sums, dg, db, dp)
+    bw = lambda: L.call("vca_bn_act_bwd", 1, dy, x, res, dx, dres, R, C, mean, invstd, gamma, beta, act, 0.2, pw, 1, sums, dg, db, dp, 0)
     L.cdll.vca_set_option(b"bn_vec", 8)
     t_bw8 = timed(bw)
     L.cdll.vca_set_option(b"bn_vec", 4)

@@ -99,13 +99,14 @@ __global__ void __launch_bounds__(256, 3) bn_stats_kernel(const typename VT::Ele
   block_col_reduce<V>(s2, sh, sums + C, cv * V, active);
 }
 
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, long long R, int C, float eps, float momentum,
+__global__ void bn_finalize_kernel(double* __restrict__ sums, long long R, int C, float eps, float momentum,
                                    float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var) {
+                                   float* __restrict__ running_var, int rezero) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double m = sums[c] / (double)R;
   double var = sums[C + c] / (double)R - m * m;
+  if (rezero) { sums[c] = 0; sums[C + c] = 0; }   // persistent scratch: leave it zeroed for the next call (no memset launch)
   if (var < 0) var = 0;
   mean[c] = (float)m;
   invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
@@ -251,13 +252,14 @@ bn_act_bwd_apply_kernel(const typename VT::Elem* __restrict__ dy, const typename
   BN_ROW_LOOP(U, (RES ? 3 : 2), RD_LOADS, AP_BODY, )
 }
 
-__global__ void bn_param_grads_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma,
-                                      float* __restrict__ dbeta, float* __restrict__ dprelu) {
+__global__ void bn_param_grads_kernel(double* __restrict__ sums, int C, float* __restrict__ dgamma,
+                                      float* __restrict__ dbeta, float* __restrict__ dprelu, int rezero, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dgamma) dgamma[c] = (float)sums[C + c];
-  if (dbeta) dbeta[c] = (float)sums[c];
-  if (dprelu) dprelu[c] = (float)sums[2 * C + c];
+  if (dgamma) dgamma[c] = (float)sums[C + c] + (accumulate ? dgamma[c] : 0.f);
+  if (dbeta) dbeta[c] = (float)sums[c] + (accumulate ? dbeta[c] : 0.f);
+  if (dprelu) dprelu[c] = (float)sums[2 * C + c] + (accumulate ? dprelu[c] : 0.f);
+  if (rezero) { sums[c] = 0; sums[C + c] = 0; sums[2 * C + c] = 0; }
 }
 
 // ---- column sums of a [R, C] matrix (bias gradients); the scalar kernel handles any C ---------------------------
@@ -368,18 +370,19 @@ void launch_bwd(const void* dy, const void* x, const void* res, void* dx, void* 
 
 extern "C" {
 
-// sums: device scratch double[2*C], zeroed here.  Writes mean/invstd (biased var) and updates running stats
+// sums: device scratch double[2*C]; sums_prezeroed = 0: zeroed here (memset); 1: the caller keeps a persistent scratch
+// that is zero on entry and is left zeroed on exit.  Writes mean/invstd (biased var) and updates running stats
 // (momentum, unbiased var) when running_mean != null.
-int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, float* mean,
-                 float* invstd, float* running_mean, float* running_var, cudaStream_t s) {
+int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, int sums_prezeroed,
+                 float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t s) {
   VCA_CHECK_ARG(x && sums && mean && invstd && R > 0 && C > 0);
   const bool ok = dtype == VCA_F32 ? vec_ok<Vec<float>>(x, 0, 0, 0, 0, C) : vec_ok<Vec<bf16>>(x, 0, 0, 0, 0, C);
   if (!ok) { vca_set_error("vca_bn_stats: C must be a multiple of %d and x 16-byte aligned", dtype == VCA_F32 ? 4 : 8); return VCA_ERR_UNSUPPORTED; }
-  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
+  if (!sums_prezeroed) cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
   if (dtype == VCA_F32) launch_stats<Vec<float>>(x, R, C, sums, s);
   else launch_stats<Vec<bf16>>(x, R, C, sums, s);
   VCA_LAUNCH_CHECK();
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var);
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var, sums_prezeroed);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
@@ -404,23 +407,25 @@ int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
-// sums: device scratch double[3*C] (zeroed here).  dres must be given iff res is; dgamma/dbeta/dprelu may be null.
+// sums: device scratch double[3*C].  flags bit 0: sums is a persistent scratch, zero on entry and left zeroed (else it is
+// zeroed here); bit 1: dgamma / dbeta / dprelu are ADDED to (gradient accumulation in place).  dres must be given iff
+// res is; dgamma/dbeta/dprelu may be null.
 int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C,
                    const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope,
-                   const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu,
+                   const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags,
                    cudaStream_t s) {
   VCA_CHECK_ARG(dy && x && dx && mean && invstd && gamma && beta && sums && R > 0 && C > 0 && act >= ACT_NONE &&
                 act <= ACT_RELU && (act != ACT_PRELU || prelu_w) && ((res != nullptr) == (dres != nullptr)));
   const bool ok = dtype == VCA_F32 ? vec_ok<Vec<float>>(dy, x, res, dx, dres, C) : vec_ok<Vec<bf16>>(dy, x, res, dx, dres, C);
   if (!ok) { vca_set_error("vca_bn_act_bwd: C must be a multiple of %d and tensors 16-byte aligned", dtype == VCA_F32 ? 4 : 8); return VCA_ERR_UNSUPPORTED; }
-  cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, s);
+  if (!(flags & 1)) cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, s);
   BnParams p{mean, invstd, gamma, beta, prelu_w, slope};
   const bool has_res = res != nullptr;
   if (dtype == VCA_F32) { BN_DISPATCH(launch_bwd, Vec<float>, dy, x, res, dx, dres, R, C, p, train, sums, s) }
   else if (g_bn_vec == 8) { BN_DISPATCH(launch_bwd, Vec<bf16>, dy, x, res, dx, dres, R, C, p, train, sums, s) }
   else { BN_DISPATCH(launch_bwd, VecH4, dy, x, res, dx, dres, R, C, p, train, sums, s) }
   VCA_LAUNCH_CHECK();
-  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, dgamma, dbeta, act == ACT_PRELU ? dprelu : nullptr);
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, dgamma, dbeta, act == ACT_PRELU ? dprelu : nullptr, flags & 1, (flags >> 1) & 1);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

@@ -29,6 +29,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
@@ -57,13 +58,15 @@ def _c(t: torch.Tensor) -> torch.Tensor:
     return t if t.is_contiguous() else t.contiguous()
 
 
-def _needed(ctx, i: int) -> bool:
-    """True when the engine will actually consume the gradient of input i in this backward pass."""
+def _needed(ctx, i: int, edge: Optional[int] = None) -> bool:
+    """True when the engine will actually consume the gradient of input i in this backward pass.  `edge` = index of
+    that input in ctx.next_functions, which lists the TENSOR arguments only (None / non-tensor arguments have no edge);
+    it defaults to i, which is right whenever no such argument precedes input i."""
     if not ctx.needs_input_grad[i]:
         return False
     if not cfg.skip_unneeded_wgrad:
         return True
-    fn = ctx.next_functions[i][0]
+    fn = ctx.next_functions[i if edge is None else edge][0]
     if fn is None:
         return False
     try:
@@ -465,6 +468,20 @@ def linear(x, w, bias=None):
 # ------------------------------------------------------------------------------------------------------------
 # BatchNorm (+residual) + activation
 # ------------------------------------------------------------------------------------------------------------
+_bn_scratch = {}
+
+
+def _bn_sums(key_tensor, n, slot):
+    """Persistent fp64 scratch of one BatchNorm (keyed by its running_mean storage), zero when a kernel sequence starts
+    and left zeroed by its last kernel -- so the per-call memset launches disappear (56 x 2 per step)."""
+    key = (key_tensor.data_ptr(), n, slot)
+    t = _bn_scratch.get(key)
+    if t is None or t.device != key_tensor.device:
+        t = torch.zeros(n, dtype=torch.float64, device=key_tensor.device)
+        _bn_scratch[key] = t
+    return t
+
+
 class BNActFn(Function):
     """y = act(BN(x) [+ res]).  Training mode uses batch statistics over all leading dims and updates the running
     buffers in place (momentum 0.1, unbiased variance), eval mode uses the running statistics."""
@@ -480,8 +497,8 @@ class BNActFn(Function):
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
         if training:
-            sums = torch.empty(2 * C, dtype=torch.float64, device=dev)
-            lib().call("vca_bn_stats", _dt(x), x, R, C, eps, momentum, sums, mean, invstd, running_mean, running_var)
+            lib().call("vca_bn_stats", _dt(x), x, R, C, eps, momentum, _bn_sums(running_mean, 2 * C, 0), 1, mean, invstd,
+                       running_mean, running_var)
         else:
             lib().call("vca_bn_eval_stats", running_mean, running_var, C, eps, mean, invstd)
         y = torch.empty_like(x)
@@ -490,6 +507,7 @@ class BNActFn(Function):
         lib().call("vca_bn_act_fwd", _dt(x), x, res, y, R, C, mean, invstd, g32, b32, act, slope, pw)
         ctx.save_for_backward(x, res, gamma, beta, prelu_w, mean, invstd)
         ctx.cfg = (training, act, slope)
+        ctx.key = running_mean
         return y
 
     @staticmethod
@@ -503,12 +521,25 @@ class BNActFn(Function):
         dev = x.device
         dx = torch.empty_like(x)
         dres = torch.empty_like(x) if res is not None else None
-        sums = torch.empty(3 * C, dtype=torch.float64, device=dev)
-        dgamma = torch.empty(C, dtype=torch.float32, device=dev)
-        dbeta = torch.empty(C, dtype=torch.float32, device=dev)
-        dprelu = torch.empty(C, dtype=torch.float32, device=dev) if prelu_w is not None else None
+        # parameter gradients straight into the flat .grad views when all of them are trainer-owned leaves
+        e0 = 1 + (res is not None)       # edge index of gamma: x [, res], gamma, beta, running_mean, running_var [, prelu_w]
+        wanted = [_needed(ctx, 2, e0), _needed(ctx, 3, e0 + 1)] + ([_needed(ctx, 6, e0 + 4)] if prelu_w is not None else [])
+        sinks = [_grad_sink(p) for p in (gamma, beta) + ((prelu_w,) if prelu_w is not None else ())]
+        fused = all(wanted) and all(t is not None for t in sinks)
+        if not any(wanted):          # e.g. the sync discriminator's BatchNorms in the G phase: no parameter gradients at all
+            dgamma = dbeta = dprelu = None
+        elif fused:
+            dgamma, dbeta = sinks[0], sinks[1]
+            dprelu = sinks[2] if prelu_w is not None else None
+        else:
+            dgamma = torch.empty(C, dtype=torch.float32, device=dev)
+            dbeta = torch.empty(C, dtype=torch.float32, device=dev)
+            dprelu = torch.empty(C, dtype=torch.float32, device=dev) if prelu_w is not None else None
         lib().call("vca_bn_act_bwd", _dt(x), dy, x, res, dx, dres, R, C, mean, invstd, gamma.detach(), beta.detach(), act, slope,
-                   None if prelu_w is None else prelu_w.detach(), 1 if training else 0, sums, dgamma, dbeta, dprelu)
+                   None if prelu_w is None else prelu_w.detach(), 1 if training else 0, _bn_sums(ctx.key, 3 * C, 1), dgamma, dbeta,
+                   dprelu, 1 | (2 if fused else 0))
+        if fused:
+            return dx, dres, None, None, None, None, None, None, None, None, None, None
         return dx, dres, dgamma, dbeta, None, None, dprelu, None, None, None, None, None
 
 
@@ -516,9 +547,25 @@ def bn_act(x, bn: torch.nn.Module, act=ACT_NONE, slope=0.0, prelu_w=None, res=No
     """`bn` is any module holding weight/bias/running_mean/running_var/num_batches_tracked/eps/momentum/training."""
     training = bn.training
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        if cfg.deferred_counters is not None:       # the trainer bumps all of them with one foreach add per step
+            cfg.deferred_counters.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
     return BNActFn.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu_w, training, act, float(slope),
                          float(bn.eps), float(bn.momentum))
+
+
+def flush_deferred_counters():
+    """num_batches_tracked += (number of train-mode forwards since the last flush), one fused launch per distinct count."""
+    lst, cfg.deferred_counters = cfg.deferred_counters, None
+    if not lst:
+        return
+    count, by_ptr = {}, {}
+    for t in lst:
+        count[t.data_ptr()] = count.get(t.data_ptr(), 0) + 1
+        by_ptr[t.data_ptr()] = t
+    for k in sorted(set(count.values())):
+        torch._foreach_add_([by_ptr[p] for p, c in count.items() if c == k], k)
 
 
 # ------------------------------------------------------------------------------------------------------------

@@ -201,6 +201,7 @@ class Trainer:
         dis = (m["dis1"], m["dis2"], m["dis3"])
         s_dis = m["s_dis"]
         gen.fixed_noise = noise
+        ops.cfg.deferred_counters = []      # BatchNorm.num_batches_tracked of the whole step: one foreach add in _phase_g
         self.G.zero_grad()                                                # train.py:168
         mel1, mel2 = bilinear_down(mel, 4), bilinear_down(mel, 2)          # train.py:170-171
         T = vid.size(2)
@@ -278,6 +279,7 @@ class Trainer:
         else:
             gen_loss.backward(inputs=self.G.params)
         self._join_branches()
+        ops.flush_deferred_counters()
         st["out"].update(gen_loss=gen_loss.detach(), g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(),
                          g2=g[1].detach(), g3=g[2].detach(), gs=gs.detach())
 
