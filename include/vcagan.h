@@ -131,6 +131,13 @@ int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsi
 int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float* mag_t, float* frames, float* spec_out, int B, int T, int L, cudaStream_t stream);
 int vca_gl_ola(const float* frames, float* sig_out, int B, int T, int L, cudaStream_t stream);
 
+/* ---- waveform tail / mel front (src/data/vid_aud_grid.py:190-232, 291-307; src/data/vid_aud_lrs2.py:257-263) -------- */
+/* out[b][f][t] = post(sum_k pre(in[b][k][t]) * w[k][f]);  pre 1: exp(in*pre_mul+pre_add);  post 0: *post_arg, 1: log(max(.,post_arg)) */
+int vca_filterbank_apply(const float* in, const float* w, float* out, int B, int K, int F, int T, int pre, int post, float pre_mul, float pre_add, float post_arg, cudaStream_t stream);
+int vca_exp_affine(const float* x, float* y, long long n, float mul, float add, float scale, cudaStream_t stream);
+/* y[n] = x[n] + coef*y[n-1] in fp64 (scipy.signal.lfilter([1],[1,-coef])), clamped to [lo,hi] (np.clip) */
+int vca_deemphasis_clip(const float* x, float* y, int B, int L, double coef, float lo, float hi, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -339,6 +339,74 @@ def griffin_lim(mag: torch.Tensor, init_phase: torch.Tensor, n_iters: int = 60,
 
 
 # --------------------------------------------------------------------------
+# waveform tail / mel front  (src/data/vid_aud_grid.py:190-240, 270-307;
+# src/data/vid_aud_lrs2.py:257-296).  The mel basis comes from librosa
+# (librosa.filters.mel, un-vendored, no pinned version; the reference calls the
+# positional librosa<0.10 signature at vid_aud_grid.py:278) which is absent
+# here: `slaney_mel_basis` restates its published algorithm -- PARITY UNPINNED
+# for that one matrix.  The de-emphasis filter is pinned against
+# scipy.signal.lfilter in tests/test_oracle_golden.py.
+# --------------------------------------------------------------------------
+def deemphasize_clip(wav: np.ndarray, coef: float = 0.97) -> np.ndarray:
+    """signal.lfilter([1], [1, -coef], w) per waveform in float64, then np.clip(-1, 1)
+    (vid_aud_grid.py:205-209, 230-232).  wav (B,L) -> float64 (B,L)."""
+    x = np.asarray(wav, dtype=np.float64)
+    y = np.empty_like(x)
+    state = np.zeros(x.shape[0], dtype=np.float64)
+    for n in range(x.shape[1]):
+        state = x[:, n] + coef * state
+        y[:, n] = state
+    return np.clip(y, -1.0, 1.0)
+
+
+def slaney_mel_basis(sr: int = 16000, n_fft: int = 640, n_mels: int = 80,
+                     fmin: float = 55.0, fmax: float = 7500.0) -> np.ndarray:
+    """librosa.filters.mel defaults (htk=False, norm='slaney') as used at vid_aud_grid.py:278."""
+    def to_mel(hz: float) -> float:
+        if hz < 1000.0:
+            return 3.0 * hz / 200.0
+        return 15.0 + 27.0 * math.log(hz / 1000.0) / math.log(6.4)
+
+    def to_hz(mel: float) -> float:
+        if mel < 15.0:
+            return 200.0 * mel / 3.0
+        return 1000.0 * math.exp(math.log(6.4) * (mel - 15.0) / 27.0)
+
+    lo, hi = to_mel(fmin), to_mel(fmax)
+    edges = [to_hz(lo + (hi - lo) * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    n_bins = n_fft // 2 + 1
+    basis = np.zeros((n_mels, n_bins), dtype=np.float64)
+    for m in range(n_mels):
+        left, centre, right = edges[m], edges[m + 1], edges[m + 2]
+        for k in range(n_bins):
+            f = k * (sr / 2.0) / (n_bins - 1)
+            tri = min((f - left) / (centre - left), (right - f) / (right - centre))
+            basis[m, k] = max(0.0, tri) * 2.0 / (right - left)
+    return basis.astype(np.float32)
+
+
+def mel_to_spec(mel: torch.Tensor, basis: np.ndarray) -> torch.Tensor:
+    """Front of inverse_mel, vid_aud_grid.py:194-200: (B,1,80,T) normalised mel -> (B,321,T)."""
+    m = torch.exp(denormalize(mel))                      # :194-195 (spectral_de_normalize = exp, C = 1)
+    m = m.transpose(2, 3).contiguous()                   # B,1,T,80
+    s = torch.matmul(m, torch.from_numpy(basis))         # :198
+    return s.transpose(2, 3).squeeze(1) * 1000.0         # :199-200
+
+
+def lrs_denormalize_spec(spec: torch.Tensor) -> torch.Tensor:
+    """vid_aud_lrs2.py:261-263: denormalize -> exp -> * 14."""
+    return torch.exp(denormalize(spec)) * 14.0
+
+
+def mel_spectrogram(y: torch.Tensor, basis: np.ndarray, n_fft: int = 640, hop: int = 160):
+    """TacotronSTFT.mel_spectrogram, vid_aud_grid.py:291-307: (B,L) -> (log-mel (B,80,frames), magnitudes)."""
+    fwd, _ = stft_bases(n_fft, hop)
+    mag, _ = stft_transform(y, fwd, n_fft, hop)
+    mel = torch.matmul(torch.from_numpy(basis), mag)
+    return torch.log(torch.clamp(mel, min=1e-5)), mag
+
+
+# --------------------------------------------------------------------------
 # one G+D training step  (train.py:166-237; LRS variant train_LRS.py:179-243)
 # --------------------------------------------------------------------------
 MODULES = ("v_front", "gen", "post", "dis1", "dis2", "dis3", "s_dis")

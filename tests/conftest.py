@@ -30,6 +30,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_tail():
+    """Waveform tail / mel front vectors from the reference's dataset methods (tests/golden/make_golden_tail.py)."""
+    return dict(np.load(os.path.join(GOLD, "golden_tail.npz")))
+
+
+@pytest.fixture(scope="session")
 def state_spec():
     return json.load(open(os.path.join(GOLD, "state_spec.json")))
 

@@ -2,6 +2,7 @@
 (tests/golden/make_golden.py).  CPU only."""
 import json, os
 import numpy as np
+import pytest
 import torch
 from conftest import make_state, golden_inputs, rel_l2, GOLD
 from oracle import vca_oracle as O
@@ -98,3 +99,48 @@ def test_stft_griffin_lim_matches_reference(golden):
     ts = torch.stft(sig, 640, 160, 640, torch.hann_window(640, periodic=True), center=True, pad_mode="reflect",
                     return_complex=True)
     assert rel_l2(mag, ts.abs()) < 1e-5
+
+
+# ---- waveform tail / mel front -----------------------------------------------------
+def test_deemphasis_matches_reference_and_scipy(golden_tail):
+    x = golden_tail["deemph_in"]
+    y = O.deemphasize_clip(x)
+    assert np.abs(y - np.clip(golden_tail["deemph_out"], -1, 1)).max() < 1e-12
+    signal = pytest.importorskip("scipy.signal")
+    ref = np.stack([signal.lfilter([1], [1, -0.97], w) for w in x])     # vid_aud_grid.py:230-232
+    assert np.abs(y - np.clip(ref, -1, 1)).max() < 1e-12
+
+
+def test_mel_basis_properties():
+    """librosa is absent, so the Slaney basis is checked through the properties its definition gives: shape, triangular
+    non-negative filters with a single peak, area normalisation 2 / (f[m+2] - f[m]), support inside [fmin, fmax]."""
+    for fmax in (7500.0, 7600.0):                    # GRID vid_aud_grid.py:37, LRS vid_aud_lrs2.py
+        b = O.slaney_mel_basis(16000, 640, 80, 55.0, fmax).astype(np.float64)
+        assert b.shape == (80, 321) and (b >= 0).all()
+        freqs = np.arange(321) * 25.0
+        assert b[:, freqs < 55.0].sum() == 0 and b[:, freqs > fmax].sum() == 0
+        for m in range(80):
+            nz = np.nonzero(b[m])[0]
+            assert len(nz) > 0 and (np.diff(nz) == 1).all()
+            pk = nz[np.argmax(b[m, nz])]
+            assert (np.diff(b[m, nz[0]:pk + 1]) >= -1e-12).all() and (np.diff(b[m, pk:nz[-1] + 1]) <= 1e-12).all()
+        # a triangle of height h over [l, r] integrates to h (r - l) / 2 = 1 for every filter (area normalisation);
+        # sampled every 25 Hz the sum * 25 approaches 1 for the wide high filters
+        assert np.abs(b[40:].sum(1) * 25.0 - 1.0).max() < 0.05
+
+
+def test_tail_restatement_matches_reference(golden_tail):
+    gt = golden_tail
+    basis = O.slaney_mel_basis()
+    assert np.array_equal(basis, gt["mel_basis"])
+    assert rel_l2(O.mel_to_spec(torch.from_numpy(gt["mel"]), basis), gt["mel_to_spec"]) < 1e-6
+    ph = torch.from_numpy(gt["grid_phase"])
+    wav = O.deemphasize_clip(O.griffin_lim(torch.from_numpy(gt["grid_spec"]).squeeze(1), ph, 60).numpy())
+    assert rel_l2(wav, gt["grid_inverse_spec"]) < 1e-4                 # vid_aud_grid.py:212-224
+    wav = O.deemphasize_clip(O.griffin_lim(O.mel_to_spec(torch.from_numpy(gt["mel"]), basis), ph, 60).numpy())
+    assert rel_l2(wav, gt["grid_inverse_mel"]) < 1e-4                  # vid_aud_grid.py:190-210
+    mag = O.lrs_denormalize_spec(torch.from_numpy(gt["lrs_spec"])).squeeze(1)
+    wav = O.deemphasize_clip(O.griffin_lim(mag, ph, 60).numpy())
+    assert rel_l2(wav, gt["lrs_inverse_spec"]) < 1e-4                  # vid_aud_lrs2.py:257-272
+    mel, mags = O.mel_spectrogram(torch.from_numpy(gt["melspec_in"]), basis)
+    assert rel_l2(mags, gt["melspec_mag"]) < 1e-6 and rel_l2(mel, gt["melspec_out"]) < 1e-5

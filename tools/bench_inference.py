@@ -39,9 +39,16 @@ def main():
     alg_bytes = B * (a.iters + 1) * (321 * Tp * 4 + 2 * 160 * (Tp - 1) * 4)   # mag read + signal read + write
     ms_all = ev_time(lambda: infer.synthesize(vf, gen, post, vid, lens, n_iters=a.iters, tta=True))
     ms_fwd = ev_time(lambda: infer.synthesize(vf, gen, post, vid, lens, n_iters=0, tta=True))
+    wav = audio.griffin_lim(spec, None, 1)
+    ms_de = ev_time(lambda: audio.deemphasize(wav))
+    tstft = audio.TacotronSTFT().to(dev)
+    mel = torch.rand(B, 1, 80, Tp, device=dev) * 2 - 1
+    ms_m2s = ev_time(lambda: tstft.mel_to_spec(mel))
     line = {"metric": "test-time inference clips/s (generator + flip TTA + Postnet + Griffin-Lim)", "value": B / ms_all * 1e3,
             "unit": "clips/s", "batch": B, "frames": T, "gl_iters": a.iters, "ms_total": ms_all, "ms_forward_tta": ms_fwd,
-            "ms_griffin_lim": ms_gl, "dtype": "bf16 network / f32 Griffin-Lim",
+            "ms_griffin_lim": ms_gl,
+            "ms_deemphasis_clip": ms_de, "deemphasis_gbs": 2 * 4 * wav.numel() / (ms_de * 1e-3) / 1e9,
+            "ms_mel_to_spec": ms_m2s, "dtype": "bf16 network / f32 Griffin-Lim",
             "roofline": {"bound": "hbm", "kernel": "gl_frames_kernel + gl_ola_kernel", "achieved": alg_bytes / (ms_gl * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / (ms_gl * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes": alg_bytes}}

@@ -22,7 +22,7 @@ class ConvGeom(ctypes.Structure):
 
 
 _CT = {
-    "int": ctypes.c_int, "float": ctypes.c_float, "long long": ctypes.c_longlong,
+    "int": ctypes.c_int, "float": ctypes.c_float, "double": ctypes.c_double, "long long": ctypes.c_longlong,
     "unsigned long long": ctypes.c_ulonglong, "cudaStream_t": ctypes.c_void_p,
 }
 

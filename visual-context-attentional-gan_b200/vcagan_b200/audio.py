@@ -83,3 +83,117 @@ def griffin_lim(magnitudes, stft_fn=None, n_iters=30, init_angles: Optional[torc
     for _ in range(n_iters):
         sig = _ola(_frames(1, sig, None, mag_t))
     return sig
+
+
+# ------------------------------------------------------------------------------------------------------------
+# waveform tail / mel front: vid_aud_grid.py:190-240, 270-307; vid_aud_lrs2.py:235-296
+# ------------------------------------------------------------------------------------------------------------
+LOG1E5 = math.log(1e-5)                 # vid_aud_grid.py:22
+DENORM_MUL = -LOG1E5 / 2.0              # denormalize(m) = (m + 1) * (-log1e5 / 2) + log1e5 = m * MUL + ADD
+DENORM_ADD = LOG1E5 / 2.0
+
+
+def mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float, fmax: float):
+    """The (n_mels, 1 + n_fft//2) float32 matrix `librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)` returns with its
+    defaults (Slaney mel scale, triangular filters, area normalisation) -- vid_aud_grid.py:278.  Built once on the
+    host at construction time, exactly where the reference builds it."""
+    import numpy as np
+    f_sp, min_log_hz = 200.0 / 3.0, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        return min_log_mel + math.log(f / min_log_hz) / logstep if f >= min_log_hz else f / f_sp
+
+    mels = np.linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mels + 2)
+    mel_f = np.where(mels >= min_log_mel, min_log_hz * np.exp(logstep * (mels - min_log_mel)), f_sp * mels)
+    fftfreqs = np.linspace(0.0, sr / 2.0, 1 + n_fft // 2)
+    fdiff = np.diff(mel_f)
+    ramps = mel_f[:, None] - fftfreqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    weights = np.maximum(0.0, np.minimum(lower, upper))
+    weights *= (2.0 / (mel_f[2:n_mels + 2] - mel_f[:n_mels]))[:, None]
+    return weights.astype(np.float32)
+
+
+def _filterbank(x, w, pre, post, pre_mul, pre_add, post_arg):
+    """x (B,K,T) fp32, w (K,F) fp32 -> (B,F,T); see vca_filterbank_apply in include/vcagan.h."""
+    if not x.is_cuda:
+        raise RuntimeError("the filterbank kernels need CUDA tensors: there is no CPU fallback")
+    x = x.contiguous().float()
+    B, K, T = x.shape
+    F = w.shape[1]
+    out = torch.empty((B, F, T), dtype=torch.float32, device=x.device)
+    lib().call("vca_filterbank_apply", x, w, out, B, K, F, T, pre, post, pre_mul, pre_add, post_arg)
+    return out
+
+
+class TacotronSTFT(torch.nn.Module):
+    """vid_aud_grid.py:270-307 (constructed at :38 with 640/160/640, 80 mels, 16 kHz, fmin 55, fmax 7500; LRS 7600)."""
+
+    def __init__(self, filter_length=640, hop_length=160, win_length=640, n_mel_channels=80, sampling_rate=16000,
+                 mel_fmin=55.0, mel_fmax=7500.0):
+        super().__init__()
+        self.n_mel_channels, self.sampling_rate = n_mel_channels, sampling_rate
+        self.stft_fn = STFT(filter_length, hop_length, win_length)
+        basis = torch.from_numpy(mel_filterbank(sampling_rate, filter_length, n_mel_channels, mel_fmin, mel_fmax))
+        self.register_buffer("mel_basis", basis)                                            # (80, 321), the reference's key
+        self.register_buffer("_mel_basis_t", basis.t().contiguous(), persistent=False)      # (321, 80)
+
+    def spectral_normalize(self, magnitudes):            # log(clamp(x, 1e-5)), audio_processing.py:71-78
+        return torch.log(torch.clamp(magnitudes, min=1e-5))
+
+    def spectral_de_normalize(self, magnitudes):         # audio_processing.py:81-88
+        return torch.exp(magnitudes)
+
+    def mel_spectrogram(self, y):
+        """y (B,L) in [-1,1] -> (mel (B,80,frames) log-compressed, magnitudes (B,321,frames)); vid_aud_grid.py:291-307."""
+        magnitudes, _ = self.stft_fn.transform(y)
+        mel = _filterbank(magnitudes, self._mel_basis_t, 0, 1, 0.0, 0.0, 1e-5)
+        return mel, magnitudes
+
+    def mel_to_spec(self, mel):
+        """Normalised mel (B,1,80,T) or (B,80,T) -> linear magnitudes (B,321,T) * 1000: the front of inverse_mel
+        (vid_aud_grid.py:194-200) as one kernel (denormalize -> exp -> mel_basis matmul -> scale)."""
+        m = mel.reshape(-1, self.n_mel_channels, mel.shape[-1])
+        return _filterbank(m, self.mel_basis, 1, 0, DENORM_MUL, DENORM_ADD, 1000.0)
+
+
+def deemphasize(wav: torch.Tensor, coef: float = 0.97, clip: bool = True) -> torch.Tensor:
+    """scipy.signal.lfilter([1], [1, -coef], w) per waveform followed by np.clip(-1, 1) (vid_aud_grid.py:205-209,
+    230-232), batched on the device: wav (B,L) -> (B,L) fp32."""
+    if not wav.is_cuda:
+        raise RuntimeError("deemphasize needs CUDA tensors: there is no CPU fallback")
+    x = wav.reshape(-1, wav.shape[-1]).contiguous().float()
+    y = torch.empty_like(x)
+    lo, hi = (-1.0, 1.0) if clip else (-3.0e38, 3.0e38)
+    lib().call("vca_deemphasis_clip", x, y, x.shape[0], x.shape[1], float(coef), lo, hi)
+    return y.view(wav.shape)
+
+
+def lrs_denormalize_spec(mag: torch.Tensor) -> torch.Tensor:
+    """denormalize -> exp -> * 14 (vid_aud_lrs2.py:261-263, 286-296) as one element-wise kernel."""
+    if not mag.is_cuda:
+        raise RuntimeError("lrs_denormalize_spec needs CUDA tensors: there is no CPU fallback")
+    mag = mag.contiguous().float()
+    out = torch.empty_like(mag)
+    lib().call("vca_exp_affine", mag, out, mag.numel(), DENORM_MUL, DENORM_ADD, 14.0)
+    return out
+
+
+def inverse_spec(spec, stft: Optional[TacotronSTFT] = None, n_iters: int = 60, lrs: bool = False, init_angles=None):
+    """MultiDataset.inverse_spec: GRID vid_aud_grid.py:212-224 (raw magnitudes), LRS vid_aud_lrs2.py:257-272
+    (denormalize -> exp -> *14 first).  spec (B,1,321,T) or (1,321,T) -> clipped waveforms (B, 160*(T-1)) on the device."""
+    if spec.dim() < 4:
+        spec = spec.unsqueeze(0)
+    mag = spec.squeeze(1).contiguous().float()
+    if lrs:
+        mag = lrs_denormalize_spec(mag)
+    return deemphasize(griffin_lim(mag, None if stft is None else stft.stft_fn, n_iters, init_angles=init_angles))
+
+
+def inverse_mel(mel, stft: TacotronSTFT, n_iters: int = 60, init_angles=None):
+    """MultiDataset.inverse_mel (vid_aud_grid.py:190-210): normalised mel (B,1,80,T) -> clipped waveforms (B, 160*(T-1))."""
+    if mel.dim() < 4:
+        mel = mel.unsqueeze(0)
+    return deemphasize(griffin_lim(stft.mel_to_spec(mel), stft.stft_fn, n_iters, init_angles=init_angles))
