@@ -138,6 +138,11 @@ int vca_exp_affine(const float* x, float* y, long long n, float mul, float add, 
 /* y[n] = x[n] + coef*y[n-1] in fp64 (scipy.signal.lfilter([1],[1,-coef])), clamped to [lo,hi] (np.clip) */
 int vca_deemphasis_clip(const float* x, float* y, int B, int L, double coef, float lo, float hi, cudaStream_t stream);
 
+/* ---- clip preprocessing of the loader (src/data/vid_aud_grid.py:94-121, src/data/vid_aud_lrs2.py:87-120) -------------- */
+/* frames u8 [n][H][W][3] -> out f32 [n][OH][OW]: PIL crop + bilinear resize (fixed-point tables kx/bx, ky/by from the host) +
+   hflip + luma + ToTensor + Normalize + erase box; meta int [n][10] = l,u,r,b, flip, ex0,ey0,ex1,ey1, valid.  Bit-exact. */
+int vca_clip_preprocess(const unsigned char* frames, int n_frames, int H, int W, const int* meta, const int* kx, const int* bx, const int* ky, const int* by, int ksx, int ksy, int crop_w, int crop_h, int OW, int OH, float mean, float stdv, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

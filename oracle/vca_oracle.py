@@ -407,6 +407,86 @@ def mel_spectrogram(y: torch.Tensor, basis: np.ndarray, n_fft: int = 640, hop: i
 
 
 # --------------------------------------------------------------------------
+# clip preprocessing of the loader  (MultiDataset.build_tensor,
+# src/data/vid_aud_grid.py:94-121; LRS src/data/vid_aud_lrs2.py:87-120).
+# The pixel arithmetic is Pillow's (third-party, un-vendored; 12.2.0 in this image:
+# src/libImaging/Resample.c bilinear 8bpc, Convert.c rgb2l), restated in
+# integers; pinned bit-exactly to the reference's own build_tensor through
+# tests/golden/golden_preproc.npz and, where PIL/torchvision are installed, live.
+# --------------------------------------------------------------------------
+PIL_PRECISION_BITS = 22
+
+
+def pil_bilinear_tables(in_size: int, out_size: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the triangle filter.
+    -> (first input index [out], tap count [out], int64 coefficients [out, ksize])."""
+    scale = in_size / out_size
+    fscale = scale if scale > 1.0 else 1.0
+    support = fscale                       # bilinear support 1.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    first = np.zeros(out_size, np.int64); count = np.zeros(out_size, np.int64)
+    coef = np.zeros((out_size, ksize), np.int64)
+    for o in range(out_size):
+        center = (o + 0.5) * scale
+        lo = int(center - support + 0.5)
+        lo = 0 if lo < 0 else lo
+        hi = int(center + support + 0.5)
+        hi = in_size if hi > in_size else hi
+        weights = []
+        for x in range(lo, hi):
+            a = (x - center + 0.5) * (1.0 / fscale)
+            a = -a if a < 0.0 else a
+            weights.append(1.0 - a if a < 1.0 else 0.0)
+        s = 0.0
+        for w in weights:
+            s += w
+        for i, w in enumerate(weights):
+            w = w / s if s != 0.0 else w
+            coef[o, i] = int(0.5 + w * (1 << PIL_PRECISION_BITS)) if w >= 0 else int(-0.5 + w * (1 << PIL_PRECISION_BITS))
+        first[o], count[o] = lo, hi - lo
+    return first, count, coef
+
+
+def _pil_resample_axis0(img: np.ndarray, out_size: int) -> np.ndarray:
+    """One 8bpc pass along axis 0 of a (n, ..., 3) uint8 array: 2^21 + sum(p * k) >> 22, clipped to a byte."""
+    first, count, coef = pil_bilinear_tables(img.shape[0], out_size)
+    src = img.astype(np.int64)
+    out = np.empty((out_size,) + img.shape[1:], np.uint8)
+    for o in range(out_size):
+        acc = np.full(img.shape[1:], 1 << (PIL_PRECISION_BITS - 1), np.int64)
+        for j in range(int(count[o])):
+            acc += src[first[o] + j] * coef[o, j]
+        out[o] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+    return out
+
+
+def preprocess_clip(frames: np.ndarray, boxes: np.ndarray, max_t: int, flip: bool = False,
+                    erase: Optional[Tuple[int, int]] = None, out_size: int = 112) -> torch.Tensor:
+    """build_tensor (vid_aud_grid.py:94-121): frames uint8 (n,H,W,3), boxes (n,4) or (4,) = left, upper, right, lower
+    -> float32 (1, max_t, out, out).  Crop (zero outside the frame) -> Resize (horizontal pass, then vertical) ->
+    hflip -> luma -> /255 -> Normalize(0.4136, 0.17); frames n..max_t-1 stay zero; erase = (x_s, y_s) of :116-117."""
+    boxes = np.broadcast_to(np.asarray(boxes).reshape(-1, 4), (len(frames), 4))
+    vol = torch.zeros(max_t, 1, out_size, out_size)
+    for i, (frame, (l, u, r, b)) in enumerate(zip(frames, boxes)):
+        H, W, _ = frame.shape
+        crop = np.zeros((b - u, r - l, 3), np.uint8)
+        y0, y1, x0, x1 = max(u, 0), min(b, H), max(l, 0), min(r, W)
+        if y1 > y0 and x1 > x0:
+            crop[y0 - u:y1 - u, x0 - l:x1 - l] = frame[y0:y1, x0:x1]
+        horiz = _pil_resample_axis0(crop.transpose(1, 0, 2), out_size).transpose(1, 0, 2)
+        img = _pil_resample_axis0(horiz, out_size).astype(np.int64)
+        if flip:
+            img = img[:, ::-1]
+        luma = (img[..., 0] * 19595 + img[..., 1] * 38470 + img[..., 2] * 7471 + 0x8000) >> 16
+        t = torch.from_numpy(luma.astype(np.uint8)).to(torch.float32).div(255)           # ToTensor
+        vol[i, 0] = (t - torch.tensor(0.4136)) / torch.tensor(0.1700)                    # Normalize
+    if erase is not None:
+        xs, ys = erase
+        vol[:, :, max(0, ys):min(out_size, ys + 56), max(0, xs):min(out_size, xs + 56)] = 0.0
+    return vol.transpose(1, 0)
+
+
+# --------------------------------------------------------------------------
 # one G+D training step  (train.py:166-237; LRS variant train_LRS.py:179-243)
 # --------------------------------------------------------------------------
 MODULES = ("v_front", "gen", "post", "dis1", "dis2", "dis3", "s_dis")

@@ -36,6 +36,12 @@ def golden_tail():
 
 
 @pytest.fixture(scope="session")
+def golden_preproc():
+    """Clip preprocessing vectors from the reference's build_tensor (tests/golden/make_golden_preproc.py)."""
+    return dict(np.load(os.path.join(GOLD, "golden_preproc.npz")))
+
+
+@pytest.fixture(scope="session")
 def state_spec():
     return json.load(open(os.path.join(GOLD, "state_spec.json")))
 
@@ -64,3 +70,16 @@ def golden_inputs(B=2, T=20):
 def rel_l2(a, b):
     a = torch.as_tensor(a).double().flatten(); b = torch.as_tensor(b).double().flatten()
     return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def synthetic_frames(seed, n, H, W):
+    """Seeded uint8 RGB frames (n,H,W,3): a smooth moving pattern plus noise (so both interpolation and rounding
+    matter).  Shared by tests/golden/make_golden_preproc.py and the preprocessing tests; numpy's PCG64 stream is
+    stable across versions, so the frames themselves need not be committed."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float64)
+    out = np.empty((n, H, W, 3), np.uint8)
+    for i in range(n):
+        base = np.stack([127 + 120 * np.sin(xx / (9.0 + c) + 0.3 * i) * np.cos(yy / (7.0 + 2 * c) - 0.2 * i) for c in range(3)], -1)
+        out[i] = np.clip(base + rng.integers(-40, 41, (H, W, 3)), 0, 255).astype(np.uint8)
+    return out

@@ -144,3 +144,51 @@ def test_tail_restatement_matches_reference(golden_tail):
     assert rel_l2(wav, gt["lrs_inverse_spec"]) < 1e-4                  # vid_aud_lrs2.py:257-272
     mel, mags = O.mel_spectrogram(torch.from_numpy(gt["melspec_in"]), basis)
     assert rel_l2(mags, gt["melspec_mag"]) < 1e-6 and rel_l2(mel, gt["melspec_out"]) < 1e-5
+
+
+# ---- clip preprocessing of the loader ---------------------------------------------
+def _lrs_boxes(centres, s):
+    c = np.asarray(centres).reshape(-1, 2)
+    return np.stack([c[:, 0] - 40 + s, c[:, 1] - 40 + s, c[:, 0] + 40 + s, c[:, 1] + 40 + s], 1)   # vid_aud_lrs2.py:93-98
+
+
+def preproc_cases(gp):
+    """(name, frames, boxes, max_t, flip, erase) for every vector of golden_preproc.npz."""
+    from conftest import synthetic_frames
+    fg, fl = synthetic_frames(11, 3, 288, 360), synthetic_frames(12, 4, 160, 160)
+    cases = [("grid_plain", fg, np.array([59, 95, 195, 231]), 5, False, None)]
+    for seed in (3, 4, 10):
+        flip, xs, ys = gp[f"grid_aug{seed}_draws"]
+        cases.append((f"grid_aug{seed}", fg, np.array([59, 95, 195, 231]), 5, bool(flip), (int(xs), int(ys))))
+    cases.append(("lrs_plain", fl, _lrs_boxes(gp["lrs_centres"], 0), 6, False, None))
+    for seed in (1, 2):
+        s, flip = gp[f"lrs_aug{seed}_draws"]
+        cases.append((f"lrs_aug{seed}", fl, _lrs_boxes(gp["lrs_centres"], int(s)), 6, bool(flip), None))
+    return cases
+
+
+def test_preprocess_restatement_is_bit_exact(golden_preproc):
+    flips = set()
+    for name, frames, boxes, max_t, flip, erase in preproc_cases(golden_preproc):
+        got = O.preprocess_clip(frames, boxes, max_t, flip, erase)
+        assert torch.equal(got, torch.from_numpy(golden_preproc[name])), name
+        flips.add(flip)
+    assert flips == {False, True}          # the seeds cover both branches of the flip
+
+
+def test_pil_tables_against_live_pil():
+    """Where PIL is installed, pin the coefficient restatement to the library itself (an impulse through Image.resize
+    reads the fixed-point kernel back) for the two shrink / enlarge factors of the path and a few others."""
+    Image = pytest.importorskip("PIL.Image")
+    for n_in, n_out in ((136, 112), (80, 112), (112, 112), (300, 112), (57, 112)):
+        first, count, coef = O.pil_bilinear_tables(n_in, n_out)
+        assert (coef.sum(1) > 0).all() and abs(coef.sum(1) - (1 << 22)).max() <= 3
+        for pos in (0, n_in // 3, n_in - 1):
+            line = np.zeros((1, n_in), np.uint8); line[0, pos] = 255
+            ref = np.asarray(Image.fromarray(line).resize((n_out, 1), Image.BILINEAR))[0]
+            mine = np.zeros(n_out, np.int64)
+            for o in range(n_out):
+                j = pos - first[o]
+                if 0 <= j < count[o]:
+                    mine[o] = np.clip(((1 << 21) + 255 * coef[o, j]) >> 22, 0, 255)
+            assert np.array_equal(mine, ref), (n_in, n_out, pos)
