@@ -27,53 +27,83 @@ __device__ __forceinline__ cpx cconj(cpx a) { return {a.x, -a.y}; }
 // multiply by -i (forward) or +i (inverse)
 __device__ __forceinline__ cpx rot(cpx a, bool inv) { return inv ? cpx{-a.y, a.x} : cpx{a.y, -a.x}; }
 
-// One warp: 320-point complex FFT (Stockham autosort, radices 4,4,4,5) between two shared buffers; result in `a`.
-// tw[m] = exp(-2 pi i m / 320).  inv: conjugate twiddles (no 1/N scaling).
-__device__ void fft320(cpx* a, cpx* b, const cpx* __restrict__ tw, bool inv, int lane) {
-  cpx* in = a; cpx* out = b;
-  int Ns = 1;
-#pragma unroll 1
-  for (int stage = 0; stage < 4; ++stage) {
-    const int R = stage < 3 ? 4 : 5;
-    const int nb = NH / R;                   // butterflies
-    const int tstep = NH / (Ns * R);         // twiddle index stride: W_{Ns*R}^{k t} = tw[k t tstep]
-    for (int j = lane; j < nb; j += 32) {
-      const int k = j % Ns;
-      const int j0 = (j / Ns) * Ns * R + k;
-      cpx v[5];
+// One Stockham stage of the 320-point FFT done by one warp: radix R butterflies with input stride NH/R, output
+// blocks of NS*R.  NS, R and the direction are compile-time, so the index arithmetic is shifts and constants.
+// tw[m] = exp(-2 pi i m / 320); the twiddle of input t of butterfly column k is W_{NS*R}^{k t} = tw[k t NH/(NS R)]
+// (k t < NS R, so the index never wraps).
+template <int NS, int R, bool INV>
+__device__ __forceinline__ void fft_stage(const cpx* __restrict__ in, cpx* __restrict__ out, const cpx* __restrict__ tw,
+                                          int lane) {
+  constexpr int nb = NH / R, tstep = NH / (NS * R);
 #pragma unroll
-      for (int t = 0; t < 5; ++t) {
-        if (t < R) {
-          cpx x = in[j + t * nb];
-          if (t > 0 && k > 0) {
-            cpx w = tw[(k * t * tstep) % NH];
-            if (inv) w.y = -w.y;
-            x = cmul(x, w);
-          }
-          v[t] = x;
-        }
+  for (int j = lane; j < nb; j += 32) {
+    const int k = j % NS;                        // NS is a power of two
+    const int j0 = (j / NS) * (NS * R) + k;
+    cpx v[R];
+#pragma unroll
+    for (int t = 0; t < R; ++t) {
+      cpx x = in[j + t * nb];
+      if (NS > 1 && t > 0) {                     // k == 0 multiplies by tw[0] = 1: cheaper than a divergent branch
+        cpx w = tw[k * t * tstep];
+        if (INV) w.y = -w.y;
+        x = cmul(x, w);
       }
-      if (R == 4) {
-        const cpx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), t3 = rot(csub(v[1], v[3]), inv);
-        out[j0] = cadd(t0, t2); out[j0 + Ns] = cadd(t1, t3); out[j0 + 2 * Ns] = csub(t0, t2); out[j0 + 3 * Ns] = csub(t1, t3);
-      } else {
-        const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
-        const cpx b1 = cadd(v[1], v[4]), b2 = cadd(v[2], v[3]), d1 = csub(v[1], v[4]), d2 = csub(v[2], v[3]);
-        const cpx m1 = {v[0].x + c1 * b1.x + c2 * b2.x, v[0].y + c1 * b1.y + c2 * b2.y};
-        const cpx m2 = {v[0].x + c2 * b1.x + c1 * b2.x, v[0].y + c2 * b1.y + c1 * b2.y};
-        const cpx n1 = {s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y};
-        const cpx n2 = {s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y};
-        const cpx in1 = rot(n1, inv), in2 = rot(n2, inv);    // (-i) n  for forward, (+i) n for inverse
-        out[j0] = {v[0].x + b1.x + b2.x, v[0].y + b1.y + b2.y};
-        out[j0 + Ns] = cadd(m1, in1); out[j0 + 4 * Ns] = csub(m1, in1);
-        out[j0 + 2 * Ns] = cadd(m2, in2); out[j0 + 3 * Ns] = csub(m2, in2);
-      }
+      v[t] = x;
     }
-    __syncwarp();
-    Ns *= R;
-    cpx* t = in; in = out; out = t;
+    if (R == 4) {
+      const cpx t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]), t2 = cadd(v[1], v[3]), t3 = rot(csub(v[1], v[3]), INV);
+      const cpx o0 = cadd(t0, t2), o1 = cadd(t1, t3), o2 = csub(t0, t2), o3 = csub(t1, t3);
+      if (NS == 1) {                             // 4 consecutive outputs: two 16-byte stores (buffers are 16-byte aligned)
+        float4* o = reinterpret_cast<float4*>(out + j0);
+        o[0] = make_float4(o0.x, o0.y, o1.x, o1.y);
+        o[1] = make_float4(o2.x, o2.y, o3.x, o3.y);
+      } else {
+        out[j0] = o0; out[j0 + NS] = o1; out[j0 + 2 * NS] = o2; out[j0 + 3 * NS] = o3;
+      }
+    } else {
+      const float c1 = 0.30901699437494745f, c2 = -0.8090169943749475f, s1 = 0.9510565162951535f, s2 = 0.5877852522924731f;
+      const cpx b1 = cadd(v[1], v[R - 1]), b2 = cadd(v[2], v[R - 2]), d1 = csub(v[1], v[R - 1]), d2 = csub(v[2], v[R - 2]);
+      const cpx m1 = {v[0].x + c1 * b1.x + c2 * b2.x, v[0].y + c1 * b1.y + c2 * b2.y};
+      const cpx m2 = {v[0].x + c2 * b1.x + c1 * b2.x, v[0].y + c2 * b1.y + c1 * b2.y};
+      const cpx n1 = {s1 * d1.x + s2 * d2.x, s1 * d1.y + s2 * d2.y};
+      const cpx n2 = {s2 * d1.x - s1 * d2.x, s2 * d1.y - s1 * d2.y};
+      const cpx in1 = rot(n1, INV), in2 = rot(n2, INV);    // (-i) n  for forward, (+i) n for inverse
+      out[j0] = {v[0].x + b1.x + b2.x, v[0].y + b1.y + b2.y};
+      out[j0 + NS] = cadd(m1, in1); out[j0 + 4 * NS] = csub(m1, in1);
+      out[j0 + 2 * NS] = cadd(m2, in2); out[j0 + 3 * NS] = csub(m2, in2);
+    }
   }
-  // 4 stages: the result sits where it started (a)
+  __syncwarp();
+}
+
+// One warp: 320-point complex FFT (Stockham autosort, radices 4,4,4,5) between two shared buffers; the result sits
+// where it started (a).  INV: conjugate twiddles (no 1/N scaling).
+template <bool INV>
+__device__ __forceinline__ void fft320(cpx* a, cpx* b, const cpx* __restrict__ tw, int lane) {
+  fft_stage<1, 4, INV>(a, b, tw, lane);
+  fft_stage<4, 4, INV>(b, a, tw, lane);
+  fft_stage<16, 4, INV>(a, b, tw, lane);
+  fft_stage<64, 5, INV>(b, a, tw, lane);
+}
+
+// Twiddle / window tables, built once per device by gl_tables_kernel (the frames kernel used to spend a fifth of its
+// instructions on sincosf for them in every CTA): [tw 320 cpx][tw2 322 cpx (321 used)][win 640 floats].
+constexpr int TAB_FLOATS = 2 * NH + 2 * (NH + 2) + NFFT;
+__device__ __align__(16) float g_tab[TAB_FLOATS];
+
+__global__ void gl_tables_kernel() {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < NFFT; i += gridDim.x * blockDim.x) {
+    float s, c;
+    if (i < NH) {
+      sincosf(-PI2 * (float)i / (float)NH, &s, &c);
+      g_tab[2 * i] = c; g_tab[2 * i + 1] = s;
+    }
+    if (i < NH + 2) {
+      sincosf(-PI2 * (float)i / (float)NFFT, &s, &c);
+      g_tab[2 * NH + 2 * i] = c; g_tab[2 * NH + 2 * i + 1] = s;
+    }
+    g_tab[2 * NH + 2 * (NH + 2) + i] = 0.5f - 0.5f * cosf(PI2 * (float)i / (float)NFFT);
+  }
 }
 
 __device__ __forceinline__ int reflect_idx(int j, int L) {   // F.pad(mode='reflect')
@@ -88,22 +118,14 @@ __global__ void __launch_bounds__(WARPS * 32) gl_frames_kernel(int mode, const f
                                                                const float* __restrict__ angles_t,
                                                                const float* __restrict__ mag_t, float* __restrict__ frames,
                                                                float* __restrict__ spec_out, int B, int T, int L) {
-  __shared__ cpx tw[NH];            // exp(-2 pi i m / 320)
-  __shared__ cpx tw2[NH + 1];       // exp(-2 pi i k / 640)
-  __shared__ float win[NFFT];
-  __shared__ cpx buf[WARPS][2][NH + 1];
-  for (int i = threadIdx.x; i < NH; i += blockDim.x) {
-    float s, c;
-    sincosf(-PI2 * (float)i / (float)NH, &s, &c);
-    tw[i] = {c, s};
-  }
-  for (int i = threadIdx.x; i <= NH; i += blockDim.x) {
-    float s, c;
-    sincosf(-PI2 * (float)i / (float)NFFT, &s, &c);
-    tw2[i] = {c, s};
-  }
-  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) win[i] = 0.5f - 0.5f * cosf(PI2 * (float)i / (float)NFFT);
+  __shared__ __align__(16) float tab[TAB_FLOATS];
+  __shared__ __align__(16) cpx buf[WARPS][2][NH + 2];   // stride 322 * 8 B keeps every buffer 16-byte aligned
+  for (int i = threadIdx.x; i < TAB_FLOATS / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(tab)[i] = reinterpret_cast<const float4*>(g_tab)[i];
   __syncthreads();
+  const cpx* tw = reinterpret_cast<const cpx*>(tab);                  // exp(-2 pi i m / 320), m < 320
+  const cpx* tw2 = reinterpret_cast<const cpx*>(tab + 2 * NH);        // exp(-2 pi i k / 640), k <= 320
+  const float* win = tab + 2 * NH + 2 * (NH + 2);                     // periodic Hann, 640
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int t = blockIdx.x * WARPS + warp;
@@ -120,7 +142,7 @@ __global__ void __launch_bounds__(WARPS * 32) gl_frames_kernel(int mode, const f
       A[n] = {sb[reflect_idx(i0, L)] * win[2 * n], sb[reflect_idx(i0 + 1, L)] * win[2 * n + 1]};
     }
     __syncwarp();
-    fft320(A, Bf, tw, false, lane);
+    fft320<false>(A, Bf, tw, lane);
     // X[k] = E[k] + W640^k O[k];  E = (Z[k] + conj Z[N-k])/2, O = (Z[k] - conj Z[N-k])/(2i).  Then Y[k] = mag * X/|X|.
     for (int k = lane; k <= NH; k += 32) {
       const cpx zk = A[k % NH], zn = cconj(A[(NH - k) % NH]);
@@ -129,9 +151,10 @@ __global__ void __launch_bounds__(WARPS * 32) gl_frames_kernel(int mode, const f
       const cpx o = {0.5f * d.y, -0.5f * d.x};          // d / (2i)
       cpx X = (k == NH) ? csub(e, o) : cadd(e, cmul(tw2[k], o));
       if (spec_out) { spec_out[(fo * NBIN + k) * 2] = X.x; spec_out[(fo * NBIN + k) * 2 + 1] = X.y; }
-      const float r = sqrtf(X.x * X.x + X.y * X.y);
+      const float r2 = X.x * X.x + X.y * X.y;
       const float m = mg[k];
-      cpx Y = r > 0.f ? cpx{m * X.x / r, m * X.y / r} : cpx{m, 0.f};   // atan2(0,0) = 0
+      const float sc = m * rsqrtf(r2);                                  // mag / |X|
+      cpx Y = r2 > 0.f ? cpx{sc * X.x, sc * X.y} : cpx{m, 0.f};         // atan2(0,0) = 0
       Bf[k] = Y;
     }
   } else {
@@ -156,7 +179,7 @@ __global__ void __launch_bounds__(WARPS * 32) gl_frames_kernel(int mode, const f
     A[k] = {e.x - o.y, e.y + o.x};                      // e + i o
   }
   __syncwarp();
-  fft320(A, Bf, tw, true, lane);
+  fft320<true>(A, Bf, tw, lane);
   float* fr = frames + fo * NFFT;
   const float sc = 1.f / (float)NH;
   for (int n = lane; n < NH; n += 32) {
@@ -198,6 +221,14 @@ int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float
                   int T, int L, cudaStream_t s) {
   VCA_CHECK_ARG(mag_t && frames && B > 0 && T > 1 && L == HOP * (T - 1) && (mode == 0 ? angles_t != nullptr : sig != nullptr));
   VCA_CHECK_ARG(B <= 65535);
+  static bool tables_ready[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !tables_ready[dev]) {   // stream-ordered in front of the first use on this device
+    gl_tables_kernel<<<3, 256, 0, s>>>();
+    VCA_LAUNCH_CHECK();
+    if (dev >= 0 && dev < 64) tables_ready[dev] = true;
+  }
   dim3 grid((T + WARPS - 1) / WARPS, B);
   gl_frames_kernel<<<grid, WARPS * 32, 0, s>>>(mode, sig, angles_t, mag_t, frames, spec_out, B, T, L);
   VCA_LAUNCH_CHECK();

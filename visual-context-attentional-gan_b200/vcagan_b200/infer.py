@@ -14,11 +14,18 @@ def synthesize(v_front, gen, post, vid, vid_len, n_iters=60, tta=True, mel_len=N
     spectrogram de-normalisation of vid_aud_lrs2.py:261-263 first (test_LRS.py:161)."""
     for m in (v_front, gen, post):
         m.eval()
-    phon, sent = v_front(vid)
-    g3 = gen(sent, phon, vid_len)[2]
-    if tta:                                               # test.py:134-140
-        phon_f, sent_f = v_front(vid.flip(4))
-        g3 = (g3 + gen(sent_f, phon_f, vid_len)[2]) / 2.0
+    if tta:
+        # test.py:134-140 runs the clip and its mirror image one after the other.  In eval mode nothing couples the
+        # samples of a batch (BatchNorm uses its running statistics), so both go through as ONE batch of 2B: the same
+        # per-sample arithmetic, half the launches, twice the rows per GEMM tile wave.
+        B = vid.shape[0]
+        lens = torch.as_tensor(vid_len).reshape(-1)
+        phon, sent = v_front(torch.cat([vid, vid.flip(4)], 0))
+        g = gen(sent, phon, torch.cat([lens, lens], 0))[2]
+        g3 = (g[:B] + g[B:]) / 2.0
+    else:
+        phon, sent = v_front(vid)
+        g3 = gen(sent, phon, vid_len)[2]
     gs = post(g3)                                         # test.py:141
     spec = gs if mel_len is None else gs[..., :int(mel_len)]      # test.py:143 slices the whole batch to mel_len[0]
     mag = spec.squeeze(1).contiguous().float()
