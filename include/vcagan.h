@@ -130,6 +130,8 @@ int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsi
 /* ---- Griffin-Lim STFT / ISTFT (src/data/stft.py:70-129, src/data/audio_processing.py:51-68) ---------------------- */
 int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float* mag_t, float* frames, float* spec_out, int B, int T, int L, cudaStream_t stream);
 int vca_gl_ola(const float* frames, float* sig_out, int B, int T, int L, cudaStream_t stream);
+/* out[row][k1*32 + lane] = in[row][k1 + 10*bitrev5(lane)], bin 320 last: the bin order vca_gl_frames reads with unit stride when (mode & 2) */
+int vca_gl_permute_bins(const float* in, float* out, long long rows, cudaStream_t stream);
 
 /* ---- waveform tail / mel front (src/data/vid_aud_grid.py:190-232, 291-307; src/data/vid_aud_lrs2.py:257-263) -------- */
 /* out[b][f][t] = post(sum_k pre(in[b][k][t]) * w[k][f]);  pre 1: exp(in*pre_mul+pre_add);  post 0: *post_arg, 1: log(max(.,post_arg)) */

@@ -80,8 +80,12 @@ def griffin_lim(magnitudes, stft_fn=None, n_iters=30, init_angles: Optional[torc
     else:
         ang_t = init_angles.to(mag_t.device).transpose(1, 2).contiguous().float()
     sig = _ola(_frames(0, None, ang_t, mag_t))
-    for _ in range(n_iters):
-        sig = _ola(_frames(1, sig, None, mag_t))
+    if n_iters > 0:
+        # the magnitudes are read 60 times: reorder their bins once into the lane-major order of the register FFT
+        mag_p = torch.empty_like(mag_t)
+        lib().call("vca_gl_permute_bins", mag_t, mag_p, mag_t.shape[0] * mag_t.shape[1])
+        for _ in range(n_iters):
+            sig = _ola(_frames(3, sig, None, mag_p))
     return sig
 
 
