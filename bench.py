@@ -267,7 +267,11 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"GRID G+D train step (BASELINE config[1]), batch {B}/GPU, T={T}, 112x112 lips -> 80x{4 * T} mel",
                    "global_batch": world * B, "parallelism": f"dp{world}", "l2": "256 MiB flush buffer written between timed steps",
-                   "launch": "eager" if args.no_graph else "3 CUDA graphs per step (D phase | G phase | G optimizer)",
+                   "launch": "eager" if args.no_graph else (
+                       "3 CUDA graphs per step (D phase | G phase | G optimizer)" if world == 1 else
+                       "4 CUDA graphs per step (D phase | G phase to the generator's leaves | visual front-end backward | G "
+                       "optimizer); NCCL all-reduce of D grads between 1-2, of gen+post grads underneath graph 3, of v_front "
+                       "grads before graph 4"),
                    "e2e_feed": "per-step blocking copy" if args.no_graph else
                                "one timed region over all e2e steps; step i+1's H2D copy overlaps step i on a copy stream",
                    "step_tensor_roofline_frac": (sps / world * gf * 1e9 / (pk["tf_sust"] * 1e12)) if gf else None,

@@ -260,3 +260,57 @@ def test_lrs_variant_step_matches_oracle():
         assert tr.g_opt.vmax is None and tr.d_opt.vmax is None
     finally:
         V.set_precision("fp32")
+
+
+def test_split_g_backward_matches_single_backward():
+    """Data-parallel runs split the G backward at the generator's input leaves so that the all-reduce of the gen + post
+    gradients overlaps the visual front-end's backward (Trainer.split_g_backward).  The split must produce the
+    gradients, losses and -- through the 4-graph capture -- the updated weights of the single backward."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    vid, mel, sp, noise = golden_inputs()
+    lens = torch.tensor([20, 13], dtype=torch.int32).cuda()
+    try:
+        res = []
+        for split in (False, False, True):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision="fp32", state=state, dropout=False)
+            tr.split_g_backward = split
+            tr.G.zero_grad()
+            tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)
+            tr._phase_g()
+            if split:
+                torch.cuda.synchronize()
+                assert float(tr.G.grad[:tr._vf_numel].abs().max()) == 0.0     # nothing of v_front has been written yet
+                assert float(tr.G.grad[tr._vf_numel:].abs().max()) > 0.0
+                tr._phase_g2()
+            torch.cuda.synchronize()
+            gg = tr.G.grad.clone()
+            out = tr._phase_end()
+            torch.cuda.synchronize()
+            res.append((gg, {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
+            del tr
+        (g0, o0), (ge, oe), (g1, o1) = res
+        noise_g = rel_l2(ge.cpu(), g0.cpu())
+        print("single-vs-single grad noise", noise_g, "split-vs-single", rel_l2(g1.cpu(), g0.cpu()))
+        assert rel_l2(g1.cpu(), g0.cpu()) <= 3 * noise_g + 1e-5
+        for k in ("gen_loss", "dis_loss", "recon", "sync_loss"):
+            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-5 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
+        # captured: 4 graphs, two replays against two replays of the 3-graph capture
+        losses = []
+        for split in (False, True):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision="fp32", state=state, dropout=False)
+            tr.split_g_backward = split
+            tr.capture(vid.cuda(), mel.cuda(), sp.cuda(), lens, warmup=1, noise=noise)
+            assert len(tr._graphs) == (4 if split else 3)
+            o = [{k: float(v) for k, v in tr.replay().items() if torch.is_tensor(v) and v.numel() == 1} for _ in range(2)]
+            torch.cuda.synchronize()
+            losses.append(o)
+            del tr
+        for k in ("gen_loss", "dis_loss", "recon"):
+            for a, b in zip(*losses):
+                assert abs(a[k] - b[k]) <= 2e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])
+    finally:
+        V.set_precision("fp32")

@@ -99,6 +99,7 @@ class Trainer:
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
         self._branch_streams = None
+        self._br_used = []                  # branch streams with work since the last join
         self.device = torch.device(device)
         self.mods = dict(v_front=M.Visual_front(1), gen=M.Decoder(), post=M.Postnet(), dis1=M.Discriminator(phase='1'),
                          dis2=M.Discriminator(phase='2'), dis3=M.Discriminator(phase='3'), s_dis=M.sync_Discriminator(temp))
@@ -117,20 +118,33 @@ class Trainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        # Data-parallel runs split the G backward where the generator's last gradient is written: the all-reduce of the
+        # gen + post gradients (62 % of the G buffer) then runs on the comm stream underneath the visual front-end's
+        # backward.  Single-GPU runs keep the backward in one piece (no all-reduce to hide, one graph less).
+        self.split_g_backward = self.world > 1
+        n_vf = sum(1 for _ in self.mods["v_front"].parameters())
+        self._vf_params = self.G.params[:n_vf]
+        self._genpost_params = self.G.params[n_vf:]
+        self._vf_numel = self.G.offsets[n_vf]             # v_front gradients are G.grad[:_vf_numel]
         # weight / bias gradients that accumulate straight into the flat .grad buffer overlap the dgrad chain
         ops.cfg.param_grad_streams = tuple(torch.cuda.Stream(device=self.device) for _ in range(2)) if self.parallel_branches else ()
         if hasattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch"):
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the branch streams are intentional
 
     # -- data-parallel exchange ---------------------------------------------------------------------------------
-    def _allreduce(self, group: FlatGroup, bucket_elems: int = 8 << 20):
+    def _allreduce(self, group: FlatGroup, bucket_elems: int = 8 << 20, lo: int = 0, hi: Optional[int] = None,
+                   wait: bool = True):
+        """Sum-all-reduce group.grad[lo:hi] on the comm stream, ordered after the current stream.  wait=False leaves it
+        running underneath whatever the current stream does next; the next waiting call (or an explicit
+        `cur.wait_stream(comm_stream)`) joins it."""
         if self.world == 1:
             return
         cur = torch.cuda.current_stream()
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_flat(group.grad, self.pg, bucket_elems)
-        cur.wait_stream(self.comm_stream)
+            dp.allreduce_flat(group.grad[lo:group.numel if hi is None else hi], self.pg, bucket_elems)
+        if wait:
+            cur.wait_stream(self.comm_stream)
 
     def _branches(self, fns):
         """Run independent sub-graphs concurrently: fns[0] on the current stream, the others on side streams that fork
@@ -150,6 +164,7 @@ class Trainer:
             with torch.cuda.stream(st):
                 outs[i] = fns[i]()
             used.append(st)
+        self._br_used.extend(used)          # their backward kernels will run there too: joined by _join_branches
         outs[0] = fns[0]()
         for st in used:
             cur.wait_stream(st)
@@ -172,15 +187,18 @@ class Trainer:
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 outs.append(f())
+            self._br_used.append(st)
         return outs
 
     def _join_branches(self):
         """After a backward pass: the branch backward kernels (incl. the wgrad kernels that accumulate straight into
         the flat .grad buffer, which autograd's own leaf-stream bookkeeping does not see) ran on the side streams."""
         cur = torch.cuda.current_stream()
-        if self._branch_streams is not None:
-            for st in self._branch_streams:
-                cur.wait_stream(st)
+        # only streams that took part since the last join: inside a graph capture, waiting on a stream that is not part of
+        # the capture would tie the graph to work outside it and invalidate the capture
+        for st in dict.fromkeys(self._br_used):
+            cur.wait_stream(st)
+        self._br_used.clear()
         for st in ops.cfg._pg_used:         # parameter-gradient side streams with work since the last join
             cur.wait_stream(st)
         ops.cfg._pg_used.clear()
@@ -191,7 +209,12 @@ class Trainer:
         self._phase_d(vid, mel, spec, vid_len, noise)
         self._allreduce(self.D)
         self._phase_g()
-        self._allreduce(self.G)
+        if self.split_g_backward:
+            self._allreduce(self.G, lo=self._vf_numel, wait=False)        # gen + post, underneath ...
+            self._phase_g2()                                              # ... the visual front-end's backward
+            self._allreduce(self.G, hi=self._vf_numel)
+        else:
+            self._allreduce(self.G)
         return self._phase_end()
 
     def _phase_d(self, vid, mel, spec, vid_len, noise=None):
@@ -219,7 +242,15 @@ class Trainer:
         early = self._fork([real_early(2), real_early(1), real_early(0)], [2, 0, 1])
         early = {2: early[0], 1: early[1], 0: early[2]}
         phon, sent = v_front(vid)
-        g = gen(sent, phon, vid_len)                                       # g1, g2, g3
+        if self.split_g_backward:
+            # the generator sees detached leaves: its backward stops there (_phase_g) and the visual front-end's
+            # backward is a second autograd call fed with their gradients (_phase_g2)
+            assert self.merge_vfront_backward
+            phon_g, sent_g = phon.detach().requires_grad_(True), sent.detach().requires_grad_(True)
+            g = gen(sent_g, phon_g, vid_len)                               # g1, g2, g3
+        else:
+            phon_g = sent_g = None
+            g = gen(sent, phon, vid_len)
         gen.fixed_noise = None
         assert phon.size(1) == T
         sdet = sent.detach()
@@ -254,6 +285,7 @@ class Trainer:
             dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
         self._join_branches()
         self._st = dict(mel=mel, mel1=mel1, mel2=mel2, spec=spec, phon=phon, phon_leaf=phon_leaf, sdet=sdet, g=g, T=T,
+                        sent=sent, phon_g=phon_g, sent_g=sent_g,
                         out=dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
                                  fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp])))
 
@@ -274,7 +306,9 @@ class Trainer:
             + ops.l1_mean(gs, st["spec"])
         gen_loss = g_adv + g_sync + 50.0 * recon
         # D weight grads are skipped (the reference computes and discards them, train.py:235-236)
-        if self.merge_vfront_backward:
+        if self.split_g_backward:
+            torch.autograd.backward([gen_loss], inputs=self._genpost_params + [st["phon_g"], st["sent_g"]])
+        elif self.merge_vfront_backward:
             torch.autograd.backward([gen_loss, phon], [None, st["phon_leaf"].grad], inputs=self.G.params)
         else:
             gen_loss.backward(inputs=self.G.params)
@@ -282,6 +316,14 @@ class Trainer:
         ops.flush_deferred_counters()
         st["out"].update(gen_loss=gen_loss.detach(), g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(),
                          g2=g[1].detach(), g3=g[2].detach(), gs=gs.detach())
+
+    def _phase_g2(self):
+        """Second half of a split G backward: the visual front-end, fed with d(gen_loss)/d(phon, sent) from the
+        generator's leaves and d(dis_loss)/d(phon) from the D phase (autograd sums the two roots on phon)."""
+        st = self._st
+        torch.autograd.backward([st["phon"], st["phon"], st["sent"]],
+                                [st["phon_g"].grad, st["phon_leaf"].grad, st["sent_g"].grad], inputs=self._vf_params)
+        self._join_branches()
 
     def _phase_end(self):
         self.g_opt.step(1.0 / self.world)
@@ -306,7 +348,7 @@ class Trainer:
         torch.cuda.synchronize()
         ops.clear_pack_cache()            # every weight (re)pack must be recorded inside the graphs
         pool = torch.cuda.graph_pool_handle()
-        self._graphs = [torch.cuda.CUDAGraph() for _ in range(3)]
+        self._graphs = [torch.cuda.CUDAGraph() for _ in range(4 if self.split_g_backward else 3)]
         n0 = lib().launches
         # The critical path (main chain + discriminator branches) is captured on high-priority streams, the
         # parameter-gradient side streams keep the default (lowest) priority: when both have CTAs pending, the SMs
@@ -316,7 +358,10 @@ class Trainer:
             self._phase_d(*self._sin, noise=self._snoise)
         with torch.cuda.graph(self._graphs[1], pool=pool, stream=cap):
             self._phase_g()
-        with torch.cuda.graph(self._graphs[2], pool=pool, stream=cap):
+        if self.split_g_backward:
+            with torch.cuda.graph(self._graphs[2], pool=pool, stream=cap):
+                self._phase_g2()
+        with torch.cuda.graph(self._graphs[-1], pool=pool, stream=cap):
             self._sout = self._phase_end()
         self.launches_per_step = lib().launches - n0
         return self
@@ -329,8 +374,13 @@ class Trainer:
         self._graphs[0].replay()
         self._allreduce(self.D)
         self._graphs[1].replay()
-        self._allreduce(self.G)
-        self._graphs[2].replay()
+        if self.split_g_backward:
+            self._allreduce(self.G, lo=self._vf_numel, wait=False)
+            self._graphs[2].replay()
+            self._allreduce(self.G, hi=self._vf_numel)
+        else:
+            self._allreduce(self.G)
+        self._graphs[-1].replay()
         return self._sout
 
     # -- pipelined input feed: the host->device copy of step i+1 runs on a copy stream underneath step i ------------
