@@ -10,8 +10,13 @@ path is the CUDA library under ``visual-context-attentional-gan_b200/``.
 
 Parity pin: the reference ships no golden vectors, so the
 pin is ``tests/golden/*.npz`` -- outputs of the *unmodified reference modules*
-imported from /root/reference by ``tests/golden/make_golden.py`` (committed);
-``tests/test_oracle_golden.py`` holds this restatement to those vectors.
+imported from /root/reference by ``tests/golden/make_golden.py`` (models, one
+full G+D step, STFT / Griffin-Lim), ``make_golden_tail.py`` (the dataset
+classes' inverse_spec / inverse_mel / deemphasize, TacotronSTFT.mel_spectrogram)
+and ``make_golden_preproc.py`` (build_tensor: the PIL / torchvision clip
+preprocessing), all committed; ``tests/test_oracle_golden.py`` holds this
+restatement to those vectors.  UNPINNED: one matrix, the librosa mel basis
+(librosa is not installed; see ``slaney_mel_basis``).
 
 Every function cites the reference lines it follows (paths relative to
 /root/reference).
