@@ -220,3 +220,40 @@ def test_bf16_mode_forward_bound(V, state_spec, golden):
             assert all(v < BF16_TOL for v in errs.values()), errs
     finally:
         V.set_precision("fp32")
+
+
+@pytest.mark.parametrize("T,length", [(75, 75), (250, 173), (21, 5)])
+def test_odd_long_and_short_sequences(V, state_spec, T, length):
+    """Shapes the B = 2, T = 20 fixtures do not reach: odd T (75 -> 37 -> 18 through the
+    floor of avg_pool2d; the discriminator width must equal final_length(T)), the LRS length T = 250 with a ragged
+    key mask, and a clip close to the minimum (T >= 20 for the pad-0 5x5 head) with only 5 valid frames.  Eval-mode
+    forward of every module, fp32, against the oracle on the same weights, inputs and noise: <= 1e-4."""
+    V.set_precision("fp32")
+    g = torch.Generator().manual_seed(T)
+    vid = torch.randn(1, 1, T, 112, 112, generator=g)
+    noise = torch.randn(1, 128, 20, T, generator=g)
+    mel = torch.rand(1, 1, 80, 4 * T, generator=g) * 2 - 1
+    with torch.no_grad():
+        phon_r, sent_r = O.visual_front(make_state(state_spec, "v_front"), vid, False)
+        g_r = O.decoder(make_state(state_spec, "gen"), sent_r, phon_r, [length], noise, False)
+        gs_r = O.postnet(make_state(state_spec, "post"), g_r[2], False)
+        vf, gen, post = (build(V, state_spec, n, False) for n in ("v_front", "gen", "post"))
+        gen.fixed_noise = noise
+        phon, sent = vf(vid.cuda())
+        assert phon.shape == (1, T, 512) and sent.shape == (1, 512, T)
+        assert rel_l2(phon.cpu(), phon_r) < TOL and rel_l2(sent.cpu(), sent_r) < TOL
+        gd = gen(sent_r.cuda(), phon_r.cuda(), torch.tensor([length]))
+        gs = post(gd[2])
+        assert gd[0].shape == (1, 1, 20, T) and gd[2].shape == (1, 1, 80, 4 * T) and gs.shape == (1, 1, 321, 4 * T)
+        for a, b in zip((*gd, gs), (*g_r, gs_r)):
+            assert rel_l2(a.cpu(), b) < TOL
+        for name, scale in (("dis1", 0.25), ("dis2", 0.5), ("dis3", 1.0)):
+            x = mel if scale == 1.0 else O.bilinear_half(mel, scale)
+            ur, cr = O.discriminator(make_state(state_spec, name), x, sent_r, T)
+            u, c = build(V, state_spec, name, False)(x.cuda(), sent_r.cuda(), T)
+            assert rel_l2(u.cpu(), ur) < TOL and rel_l2(c.cpu(), cr) < TOL, name
+        sd = make_state(state_spec, "s_dis")
+        sm = build(V, state_spec, "s_dis", False)
+        for flag in (False, True):
+            assert rel_l2(sm(phon_r.cuda(), mel.cuda(), flag).cpu(), O.sync_discriminator(sd, phon_r, mel, flag, False)) < TOL
+    assert O.final_length(T) == V.models.final_length(T) == T // 2 // 2
