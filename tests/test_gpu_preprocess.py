@@ -47,10 +47,11 @@ def test_default_grid_crop_and_batch_arguments():
 
 
 @pytest.mark.parametrize("size,box", [(80, (-40, -40, 40, 40)), (136, (100, 150, 236, 286)), (150, (5, 5, 155, 155)),
-                                      (300, (0, 0, 300, 300)), (57, (10, 20, 67, 77))])
+                                      (300, (0, 0, 300, 300)), (57, (10, 20, 67, 77)),
+                                      (99, (20, 30, 120, 166)), (98, (-5, 10, 395, 110))])
 def test_other_crop_sizes_and_out_of_frame_boxes(size, box):
     """Enlarging (80 -> 112, 3 taps), shrinking (up to 300 -> 112, 7 taps, > 48 KB of shared memory), boxes hanging
-    over every edge of the frame."""
+    over every edge of the frame, non-square boxes (3 x 5 and 9 x 3 taps: the generic kernel)."""
     frames = synthetic_frames(size, 2, 240, 260)
     assert torch.equal(run(frames, np.array(box), 3, False, None), O.preprocess_clip(frames, np.array(box), 3))
 

@@ -25,8 +25,9 @@ __device__ __forceinline__ int clip8(int acc) {
   return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
+// Generic fall-back (any tap counts, thread per output): used for non-square crops or more than 7 taps.
 __global__ void __launch_bounds__(PP_THREADS)
-clip_preprocess_kernel(const unsigned char* __restrict__ frames, int H, int W, const int* __restrict__ meta,
+clip_preprocess_generic_kernel(const unsigned char* __restrict__ frames, int H, int W, const int* __restrict__ meta,
                        const int* __restrict__ kx, const int* __restrict__ bx, const int* __restrict__ ky,
                        const int* __restrict__ by, int ksx, int ksy, int cw, int ch, int OW, int OH,
                        float mean, float stdv, float* __restrict__ out) {
@@ -81,6 +82,90 @@ clip_preprocess_kernel(const unsigned char* __restrict__ frames, int H, int W, c
   }
 }
 
+// The kernel the path uses (tap counts 3, 5 or 7 per axis = enlarging, up to 2x and up to 3x shrinking).  Same
+// arithmetic as the generic one, organised so that the inner loops carry no index arithmetic and no branches:
+//   * a lane owns an output COLUMN xx for the whole frame: its horizontal taps (coefficients, clamped byte offsets,
+//     zeroed where the window leaves the frame) are loaded once into registers; a warp walks the rows, so the row
+//     base and the vertical taps are warp-uniform;
+//   * taps beyond a window's real count carry coefficient 0 and a clamped address, so every window is KS taps long;
+//   * ToTensor + Normalize is a 256-entry table built per CTA with the same two IEEE divisions (g is a byte).
+template <int KS>
+__global__ void __launch_bounds__(PP_THREADS)
+clip_preprocess_kernel(const unsigned char* __restrict__ frames, int H, int W, const int* __restrict__ meta,
+                       const int* __restrict__ kx, const int* __restrict__ bx, const int* __restrict__ ky,
+                       const int* __restrict__ by, int cw, int ch, int OW, int OH, float mean, float stdv,
+                       float* __restrict__ out) {
+  extern __shared__ unsigned char tmp[];   // [ch][OW][3]
+  __shared__ float lut[256];
+  const int n = blockIdx.x;
+  const int* m = meta + (size_t)n * PP_META;
+  float* dst = out + (size_t)n * OH * OW;
+  if (!m[9]) {                              // behind the clip's last frame: temporalVolume stays zero
+    for (int i = threadIdx.x; i < OH * OW; i += PP_THREADS) dst[i] = 0.f;
+    return;
+  }
+  lut[threadIdx.x] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)threadIdx.x, 255.f), mean), stdv);   // PP_THREADS == 256
+  const int l = m[0], u = m[1], flip = m[4], ex0 = m[5], ey0 = m[6], ex1 = m[7], ey1 = m[8];
+  const unsigned char* src = frames + (size_t)n * H * W * 3;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = PP_THREADS / 32, HALF = 1 << (PP_PREC - 1);
+
+  for (int c0 = 0; c0 < OW; c0 += 32) {                                // horizontal pass
+    const int xx = c0 + lane;
+    const bool act = xx < OW;
+    int k[KS], off[KS];
+#pragma unroll
+    for (int j = 0; j < KS; ++j) { k[j] = 0; off[j] = 0; }
+    if (act) {
+      const int x0 = l + bx[2 * xx], cnt = bx[2 * xx + 1];
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const int fx = x0 + j;
+        const bool in = j < cnt && fx >= 0 && fx < W;
+        k[j] = in ? kx[xx * KS + j] : 0;
+        off[j] = in ? fx * 3 : 0;
+      }
+    }
+    for (int y = warp; y < ch; y += NW) {
+      const int fy = u + y;                                            // warp-uniform
+      int a0 = HALF, a1 = HALF, a2 = HALF;
+      if (fy >= 0 && fy < H) {
+        const unsigned char* row = src + fy * W * 3;
+#pragma unroll
+        for (int j = 0; j < KS; ++j) {
+          const unsigned char* p = row + off[j];
+          a0 += p[0] * k[j]; a1 += p[1] * k[j]; a2 += p[2] * k[j];
+        }
+      }
+      if (act) {
+        unsigned char* t = tmp + (y * OW + xx) * 3;
+        t[0] = (unsigned char)clip8(a0); t[1] = (unsigned char)clip8(a1); t[2] = (unsigned char)clip8(a2);
+      }
+    }
+  }
+  __syncthreads();
+
+  for (int c0 = 0; c0 < OW; c0 += 32) {                                // vertical pass, luma, normalise, flip, erase
+    const int xx = c0 + lane;
+    if (xx >= OW) continue;
+    const int ox = flip ? OW - 1 - xx : xx;
+    const bool ecol = ox >= ex0 && ox < ex1;
+    const unsigned char* col = tmp + xx * 3;
+    for (int yy = warp; yy < OH; yy += NW) {                           // warp-uniform row: uniform taps
+      const int y0 = by[2 * yy], cnt = by[2 * yy + 1];
+      int a0 = HALF, a1 = HALF, a2 = HALF;
+#pragma unroll
+      for (int j = 0; j < KS; ++j) {
+        const int c = j < cnt ? ky[yy * KS + j] : 0;
+        const unsigned char* p = col + min(y0 + j, ch - 1) * (OW * 3);
+        a0 += p[0] * c; a1 += p[1] * c; a2 += p[2] * c;
+      }
+      const int g = (clip8(a0) * 19595 + clip8(a1) * 38470 + clip8(a2) * 7471 + 0x8000) >> 16;
+      dst[yy * OW + ox] = (ecol && yy >= ey0 && yy < ey1) ? 0.f : lut[g];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -94,14 +179,26 @@ int vca_clip_preprocess(const unsigned char* frames, int n_frames, int H, int W,
   const size_t smem = (size_t)crop_h * OW * 3;
   VCA_CHECK_ARG(smem <= 200 * 1024);
   if (smem > 48 * 1024) {   // per-device attribute: set on every such call (crops taller than 146 rows only)
-    cudaError_t e = cudaFuncSetAttribute(clip_preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(clip_preprocess_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       vca_set_error("%s:%d: cudaFuncSetAttribute failed: %s", __FILE__, __LINE__, cudaGetErrorString(e));
       return VCA_ERR_CUDA;
     }
   }
-  clip_preprocess_kernel<<<n_frames, PP_THREADS, smem, s>>>(frames, H, W, meta, kx, bx, ky, by, ksx, ksy, crop_w, crop_h,
-                                                            OW, OH, mean, stdv, out);
+  const bool fast = ksx == ksy && (ksx == 3 || ksx == 5 || ksx == 7);
+#define VCA_PP_LAUNCH(KS)                                                                                            \
+  do {                                                                                                               \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(clip_preprocess_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    clip_preprocess_kernel<KS><<<n_frames, PP_THREADS, smem, s>>>(frames, H, W, meta, kx, bx, ky, by, crop_w, crop_h, OW, OH, \
+                                                                  mean, stdv, out);                                  \
+  } while (0)
+  if (fast && ksx == 3) VCA_PP_LAUNCH(3);
+  else if (fast && ksx == 5) VCA_PP_LAUNCH(5);
+  else if (fast) VCA_PP_LAUNCH(7);
+  else
+    clip_preprocess_generic_kernel<<<n_frames, PP_THREADS, smem, s>>>(frames, H, W, meta, kx, bx, ky, by, ksx, ksy, crop_w,
+                                                                      crop_h, OW, OH, mean, stdv, out);
+#undef VCA_PP_LAUNCH
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
