@@ -229,6 +229,16 @@ def run_ours(args):
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, ms_e2e = float(t[0]), float(t[1])
+    # data-parallel invariant: every rank applied the same averaged gradients to the same weights, so the replicas must
+    # still be bit-identical after all those steps (checksum of both flat parameter buffers, min == max over ranks)
+    in_sync = None
+    if world > 1:
+        cs = torch.stack([tr.G.flat.double().sum(), tr.D.flat.double().sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        in_sync = bool(torch.equal(lo, hi))
+        assert in_sync, f"replicas diverged: parameter checksums {lo.tolist()} .. {hi.tolist()}"
 
     # dominant kernel family: the tcgen05 implicit-GEMM conv (fwd + dgrad share one kernel); timed live per launch
     roof = None
@@ -266,7 +276,7 @@ def run_ours(args):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": f"GRID G+D train step (BASELINE config[1]), batch {B}/GPU, T={T}, 112x112 lips -> 80x{4 * T} mel",
-                   "global_batch": world * B, "parallelism": f"dp{world}", "l2": "256 MiB flush buffer written between timed steps",
+                   "global_batch": world * B, "parallelism": f"dp{world}", "replicas_in_sync": in_sync, "l2": "256 MiB flush buffer written between timed steps",
                    "launch": "eager" if args.no_graph else (
                        "3 CUDA graphs per step (D phase | G phase | G optimizer)" if world == 1 else
                        "4 CUDA graphs per step (D phase | G phase to the generator's leaves | visual front-end backward | G "
