@@ -25,7 +25,7 @@
 
 namespace {
 
-constexpr int NFFT = 640, HOP = 160, NH = 320, NBIN = 321, WARPS = 8, FPW = 2;   // FPW: frames per warp
+constexpr int NFFT = 640, HOP = 160, NH = 320, NBIN = 321, WARPS = 8;
 constexpr float PI2 = 6.283185307179586f;
 
 struct cpx { float x, y; };
@@ -179,7 +179,7 @@ __device__ __forceinline__ int reflect_idx(int j, int L) {   // F.pad(mode='refl
 __global__ void __launch_bounds__(WARPS * 32, 3) gl_frames_kernel(int mode, const float* __restrict__ sig,
                                                                const float* __restrict__ angles_t,
                                                                const float* __restrict__ mag_t, float* __restrict__ frames,
-                                                               float* __restrict__ spec_out, int B, int T, int L) {
+                                                               float* __restrict__ spec_out, int B, int T, int L, int fpw) {
   __shared__ __align__(16) float tab[TAB_FLOATS];
   for (int i = threadIdx.x; i < TAB_FLOATS / 4; i += blockDim.x)
     reinterpret_cast<float4*>(tab)[i] = reinterpret_cast<const float4*>(g_tab)[i];
@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(WARPS * 32, 3) gl_frames_kernel(int mode, cons
   const float* sb = sig + (long long)b * L;
 
 #pragma unroll 1
-  for (int f = 0; f < FPW; ++f) {
-    const int t = (blockIdx.x * FPW + f) * WARPS + warp;
+  for (int f = 0; f < fpw; ++f) {                                     // fpw frames per warp amortise the table load
+    const int t = (blockIdx.x * fpw + f) * WARPS + warp;
     if (t >= T) return;                                               // warp-uniform
     const long long fo = ((long long)b * T + t);
     const float* mg = mag_t + fo * NBIN;
@@ -312,6 +312,8 @@ __global__ void __launch_bounds__(256) gl_ola_kernel(const float* __restrict__ f
 
 }  // namespace
 
+int g_gl_fpw = 2;   // "gl_fpw" in vca_set_option: frames per warp of gl_frames_kernel
+
 // Build the per-device tables, stream-ordered in front of their first use on this device.
 static int gl_ensure_tables(cudaStream_t s) {
   static bool ready[64] = {};
@@ -335,8 +337,9 @@ int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float
   VCA_CHECK_ARG(mag_t && frames && B > 0 && T > 1 && L == HOP * (T - 1) && mode >= 0 && mode <= 3 && mode != 2 && ((mode & 1) == 0 ? angles_t != nullptr : sig != nullptr));
   VCA_CHECK_ARG(B <= 65535);
   if (int e = gl_ensure_tables(s)) return e;
-  dim3 grid((T + WARPS * FPW - 1) / (WARPS * FPW), B);
-  gl_frames_kernel<<<grid, WARPS * 32, 0, s>>>(mode, sig, angles_t, mag_t, frames, spec_out, B, T, L);
+  const int fpw = g_gl_fpw;
+  dim3 grid((T + WARPS * fpw - 1) / (WARPS * fpw), B);
+  gl_frames_kernel<<<grid, WARPS * 32, 0, s>>>(mode, sig, angles_t, mag_t, frames, spec_out, B, T, L, fpw);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
