@@ -2,7 +2,7 @@
 """BASELINE config 5: batched test-time inference -- generator (+flip TTA) + Postnet + Griffin-Lim (60 iterations) for
 64 GRID clips on one B200.  Prints one JSON line with clips/s and the Griffin-Lim HBM roofline fraction.
     python tools/bench_inference.py [--batch 64] [--frames 75] [--iters 60]"""
-import argparse, json, os, sys, time
+import argparse, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "visual-context-attentional-gan_b200")); sys.path.insert(0, ROOT)
 import torch
@@ -23,7 +23,7 @@ def ev_time(fn, reps=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64); ap.add_argument("--frames", type=int, default=75)
-    ap.add_argument("--iters", type=int, default=60); ap.add_argument("--cpu-gl", action="store_true")
+    ap.add_argument("--iters", type=int, default=60)
     a = ap.parse_args()
     V.set_precision("bf16")
     torch.manual_seed(1)
@@ -52,13 +52,6 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "gl_frames_kernel + gl_ola_kernel", "achieved": alg_bytes / (ms_gl * 1e-3) / 1e9,
                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg_bytes / (ms_gl * 1e-3) / 1e9 / peaks["hbm_gbs"],
                          "algorithmic_bytes": alg_bytes}}
-    if a.cpu_gl:
-        from oracle import vca_oracle as O
-        torch.set_num_threads(os.cpu_count())
-        sm, ang = spec[:4].cpu(), (torch.rand(4, 321, Tp) * 6.2831853 - 3.1415927)
-        t0 = time.perf_counter(); O.griffin_lim(sm, ang, a.iters); dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 4 / dt, "unit": "clips/s (Griffin-Lim only)", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"oracle griffin_lim, 4 clips x {a.iters} iters, {dt:.1f} s"}
     print(json.dumps(line))
 
 
