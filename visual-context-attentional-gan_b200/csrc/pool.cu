@@ -9,6 +9,24 @@ namespace {
 #define GRID_STRIDE(i, total) \
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (total); i += (long long)gridDim.x * blockDim.x)
 
+
+// Flat index -> (i0, i1, i2, i3) with extents (n0, n1, n2, *), innermost first.  In 32 bits whenever the index fits (it
+// always does for the shapes of the path): a 64-bit div/mod costs ~100 instructions, four of them per element made
+// these one-load-one-store kernels issue-bound.
+__device__ __forceinline__ void split4(long long i, int n0, int n1, int n2, int& i0, int& i1, int& i2, int& i3) {
+  if (i < (1LL << 32)) {
+    unsigned r = (unsigned)i;
+    i0 = (int)(r % (unsigned)n0); r /= (unsigned)n0;
+    i1 = (int)(r % (unsigned)n1); r /= (unsigned)n1;
+    i2 = (int)(r % (unsigned)n2); i3 = (int)(r / (unsigned)n2);
+  } else {
+    long long r = i;
+    i0 = (int)(r % n0); r /= n0;
+    i1 = (int)(r % n1); r /= n1;
+    i2 = (int)(r % n2); i3 = (int)(r / n2);
+  }
+}
+
 // 3x3 stride-2 pad-1 max pool per frame; idx = argmax position 0..8 (first max wins, like ATen).
 template <class T, class VT>
 __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int NF,
@@ -16,8 +34,8 @@ __global__ void maxpool3x3s2_fwd_kernel(const T* __restrict__ x, T* __restrict__
   constexpr int V = VT::N;
   const int CV = C / V;
   GRID_STRIDE(i, (long long)NF * OH * OW * CV) {
-    int cv = (int)(i % CV); long long r = i / CV;
-    int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
+    int cv, ow, oh, n;
+    split4(i, CV, OW, OH, cv, ow, oh, n);
     float best[V]; int bi[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bi[k] = 0; }
@@ -61,8 +79,8 @@ __global__ void maxpool3x3s2_bwd_kernel(const T* __restrict__ dy, const unsigned
   constexpr int V = VT::N;
   const int CV = C / V;
   GRID_STRIDE(i, (long long)NF * H * W * CV) {
-    int cv = (int)(i % CV); long long r = i / CV;
-    int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+    int cv, w, h, n;
+    split4(i, CV, W, H, cv, w, h, n);
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -108,8 +126,8 @@ __global__ void pool2x2_sum_kernel(const T* __restrict__ x, T* __restrict__ y, i
   constexpr int V = VT::N;
   const int CV = C / V;
   GRID_STRIDE(i, (long long)NF * OH * OW * CV) {
-    int cv = (int)(i % CV); long long r = i / CV;
-    int ow = (int)(r % OW); r /= OW; int oh = (int)(r % OH); int n = (int)(r / OH);
+    int cv, ow, oh, n;
+    split4(i, CV, OW, OH, cv, ow, oh, n);
     const T* p = x + (((long long)n * H + oh * 2) * W + ow * 2) * C + cv * V;
     float a[V], b[V], c[V], d[V];
     VT::load(p, a); VT::load(p + C, b); VT::load(p + (long long)W * C, c); VT::load(p + (long long)W * C + C, d);
@@ -125,8 +143,8 @@ __global__ void expand2x2_kernel(const T* __restrict__ x, T* __restrict__ y, int
   constexpr int V = VT::N;
   const int CV = C / V;
   GRID_STRIDE(i, (long long)NF * H * W * CV) {
-    int cv = (int)(i % CV); long long r = i / CV;
-    int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+    int cv, w, h, n;
+    split4(i, CV, W, H, cv, w, h, n);
     const int ih = h >> 1, iw = w >> 1;
     float v[V];
 #pragma unroll
@@ -201,8 +219,8 @@ __global__ void d2s_kernel(const T* __restrict__ y, T* __restrict__ x, int NF, i
   constexpr int V = VT::N;
   const int CV = C / V;
   GRID_STRIDE(i, (long long)NF * H * W * CV) {
-    int cv = (int)(i % CV); long long r = i / CV;
-    int w = (int)(r % W); r /= W; int h = (int)(r % H); int n = (int)(r / H);
+    int cv, w, h, n;
+    split4(i, CV, W, H, cv, w, h, n);
     const int ii = (h + 1) >> 1, j = (w + 1) >> 1, par = (((h + 1) & 1) << 1) | ((w + 1) & 1);
     float v[V];
 #pragma unroll
