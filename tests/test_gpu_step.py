@@ -182,10 +182,13 @@ def test_stream_branches_match_serial_step():
         (d0, g0, o0), (de, ge, oe), (d1, g1, o1) = res
         nd, ng = rel_l2(de.cpu(), d0.cpu()), rel_l2(ge.cpu(), g0.cpu())     # serial-vs-serial noise (fp32 atomics order)
         print("serial-vs-serial grad noise", nd, ng, "branches-vs-serial", rel_l2(d1.cpu(), d0.cpu()), rel_l2(g1.cpu(), g0.cpu()))
-        assert rel_l2(d1.cpu(), d0.cpu()) <= 3 * nd + 1e-5
-        assert rel_l2(g1.cpu(), g0.cpu()) <= 3 * ng + 1e-5
+        # one eager-vs-eager sample is a noisy yard-stick (identical runs were seen 6e-7 and 3e-5 apart in G: fp32 atomics
+        # order in front of ill-conditioned train-mode BN gradients), hence the floor; a missing or doubled contribution
+        # of any layer is orders of magnitude above it
+        assert rel_l2(d1.cpu(), d0.cpu()) <= max(3 * nd, 2e-4)
+        assert rel_l2(g1.cpu(), g0.cpu()) <= max(3 * ng, 2e-4)
         for k in ("gen_loss", "dis_loss", "recon", "sync_loss"):
-            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-5 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
+            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-4 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
     finally:
         V.set_precision("fp32")
 
@@ -297,9 +300,9 @@ def test_split_g_backward_matches_single_backward():
         (g0, o0), (ge, oe), (g1, o1) = res
         noise_g = rel_l2(ge.cpu(), g0.cpu())
         print("single-vs-single grad noise", noise_g, "split-vs-single", rel_l2(g1.cpu(), g0.cpu()))
-        assert rel_l2(g1.cpu(), g0.cpu()) <= 3 * noise_g + 1e-5
+        assert rel_l2(g1.cpu(), g0.cpu()) <= max(3 * noise_g, 2e-4)      # floor: see test_stream_branches_match_serial_step
         for k in ("gen_loss", "dis_loss", "recon", "sync_loss"):
-            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-5 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
+            assert abs(o1[k] - o0[k]) <= 3 * abs(oe[k] - o0[k]) + 1e-4 * max(1.0, abs(o0[k])), (k, o0[k], o1[k])
         # captured: 4 graphs, two replays against two replays of the 3-graph capture
         losses = []
         for split in (False, True):
