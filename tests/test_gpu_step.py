@@ -150,7 +150,7 @@ def test_graph_replay_matches_eager():
         assert float((g1 - g0).abs().max()) <= 2e-3                  # a few Adam steps of lr 1e-4 apart at most
         for k in ("gen_loss", "dis_loss", "recon"):                  # step 4: the per-step yard-stick of the feed test
             assert abs(float(o0[k]) - float(o1[k])) <= 3 * abs(float(o0[k]) - float(oe[k])) + 1e-2 * max(1.0, abs(float(o0[k]))), (k, float(o0[k]), float(o1[k]))
-        assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 3 * rel_l2(oe["g3"].cpu(), o0["g3"].cpu()) + 1e-3
+        assert rel_l2(o1["g3"].cpu(), o0["g3"].cpu()) < 3 * rel_l2(oe["g3"].cpu(), o0["g3"].cpu()) + 5e-3
     finally:
         V.set_precision("fp32")
 
