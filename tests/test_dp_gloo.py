@@ -40,6 +40,16 @@ def _worker(rank, port, tmp):
         for w in dp.allreduce_flat(flat, None, bucket_elems=300, async_op=True):
             w.wait()
         assert torch.equal(flat, torch.full((n,), 3.0))
+        # ---- the split G all-reduce of the trainer (gen + post slice first, v_front slice later) == one all-reduce of the
+        #      whole buffer: in-place reduction of two disjoint views of the flat gradient buffer
+        whole = torch.arange(n, dtype=torch.float32) * (rank + 1)
+        parts = whole.clone()
+        cut = 413                                   # not a bucket multiple, like Trainer._vf_numel
+        dp.allreduce_flat(parts[cut:], None, bucket_elems=256)
+        assert torch.equal(parts[:cut], whole[:cut])          # the other slice is untouched in between
+        dp.allreduce_flat(parts[:cut], None, bucket_elems=256)
+        dp.allreduce_flat(whole, None, bucket_elems=256)
+        assert torch.equal(parts, whole)
         # ---- broadcast makes replicas identical
         w0 = torch.randn(50) if rank == 0 else torch.zeros(50)
         dp.broadcast_flat(w0, 0)
