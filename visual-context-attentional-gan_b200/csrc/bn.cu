@@ -256,9 +256,16 @@ __global__ void bn_param_grads_kernel(double* __restrict__ sums, int C, float* _
                                       float* __restrict__ dbeta, float* __restrict__ dprelu, int rezero, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  if (dgamma) dgamma[c] = (float)sums[C + c] + (accumulate ? dgamma[c] : 0.f);
-  if (dbeta) dbeta[c] = (float)sums[c] + (accumulate ? dbeta[c] : 0.f);
-  if (dprelu) dprelu[c] = (float)sums[2 * C + c] + (accumulate ? dprelu[c] : 0.f);
+  // accumulate: the destinations are live .grad views that other streams may be adding to concurrently -> atomics
+  if (accumulate) {
+    if (dgamma) atomicAdd(&dgamma[c], (float)sums[C + c]);
+    if (dbeta) atomicAdd(&dbeta[c], (float)sums[c]);
+    if (dprelu) atomicAdd(&dprelu[c], (float)sums[2 * C + c]);
+  } else {
+    if (dgamma) dgamma[c] = (float)sums[C + c];
+    if (dbeta) dbeta[c] = (float)sums[c];
+    if (dprelu) dprelu[c] = (float)sums[2 * C + c];
+  }
   if (rezero) { sums[c] = 0; sums[C + c] = 0; sums[2 * C + c] = 0; }
 }
 
@@ -305,7 +312,7 @@ __global__ void colsum_scalar_kernel(const T* __restrict__ x, long long R, int C
 }
 __global__ void d2f_kernel(const double* __restrict__ in, float* __restrict__ out, int n, int accumulate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (float)in[i] + (accumulate ? out[i] : 0.f);
+  if (i < n) { if (accumulate) atomicAdd(&out[i], (float)in[i]); else out[i] = (float)in[i]; }
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------

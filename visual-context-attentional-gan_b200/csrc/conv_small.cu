@@ -336,7 +336,8 @@ __global__ void pair_contract_kernel(const float* __restrict__ dw2, float* __res
         if (t >= 0 && (t & 1) == 0 && t / 2 < 3)
           a += dw2[((((long long)(p * Cout + co)) * (2 * Cin) + s * Cin + ci) * KH + kh) * 3 + t / 2];
       }
-    dw[i] = a + (accumulate ? dw[i] : 0.f);
+    if (accumulate) atomicAdd(&dw[i], a);   // .grad sinks may be hit from several streams at once (real / fake pass): never a plain RMW
+    else dw[i] = a;
   }
 }
 }  // namespace

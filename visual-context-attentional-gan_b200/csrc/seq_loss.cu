@@ -294,7 +294,9 @@ __global__ void l1_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, 
 //   p -= lr/bc1 * m / (sqrt(vmax)/sqrt(bc2) + eps)
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             float* __restrict__ vmax, long long n, float lr, float b1, float b2, float eps, float wd,
-                            float bc1, float bc2_sqrt, float gscale, const int* __restrict__ step_dev) {
+                            float bc1, float bc2_sqrt, float gscale, const int* __restrict__ step_dev,
+                            const float* __restrict__ lr_dev) {
+  if (lr_dev) lr = *lr_dev;   // learning rate lives on the device: a MultiStepLR decay (train.py:85-86) reaches captured graphs
   if (step_dev) {   // step count lives on the device (CUDA-graph replay): bias corrections computed here
     const float t = (float)(*step_dev);
     bc1 = 1.f - powf(b1, t);
@@ -483,18 +485,19 @@ int vca_adam_step(float* p, const float* g, float* m, float* v, float* vmax, lon
   float bc1 = 1.f - powf(beta1, (float)step);
   float bc2s = sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
-                                                     gscale, nullptr);
+                                                     gscale, nullptr, nullptr);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
-// Same, with the step counter resident on the device: *step_dev is incremented, then used for the bias corrections.
-// This form can be captured in a CUDA graph and replayed (the host never sees the step number).
-int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1,
+// Same, with the step counter AND the learning rate resident on the device: *step_dev is incremented, then used for
+// the bias corrections; *lr_dev is read by the kernel.  This form can be captured in a CUDA graph and replayed (the
+// host never sees the step number, and an lr schedule only has to write one float between replays).
+int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, const float* lr_dev, float beta1,
                       float beta2, float eps, float weight_decay, int* step_dev, float gscale, cudaStream_t s) {
-  VCA_CHECK_ARG(p && g && m && v && n > 0 && step_dev);
+  VCA_CHECK_ARG(p && g && m && v && n > 0 && step_dev && lr_dev);
   counter_add_i32_kernel<<<1, 1, 0, s>>>(step_dev, 1);
-  adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, lr, beta1, beta2, eps, weight_decay, 1.f, 1.f, gscale,
-                                                     step_dev);
+  adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, gscale,
+                                                     step_dev, lr_dev);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

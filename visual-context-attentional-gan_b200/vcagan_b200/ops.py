@@ -284,7 +284,15 @@ class ConvDgradFn(Function):
         if _needed(ctx, 0):
             g_dy = ConvFn.apply(ggx, w, None, ctx.stride, ctx.pad)
         if _needed(ctx, 1):
-            g_w = ConvWgradFn.apply(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape))
+            # R1 double-backward weight gradient.  When the parameter has a flat .grad sink it must go there through the
+            # atomic wgrad kernels as well: handing it to AccumulateGrad would make torch do a plain `grad += g_w`
+            # read-modify-write that can interleave with the atomic adds still queued on the side streams.
+            sink = _grad_sink(w)
+            if sink is not None:
+                with _param_grad_stream(ggx, dy):
+                    _conv_wgrad_raw(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape), out=sink)
+            else:
+                g_w = ConvWgradFn.apply(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape))
         return g_dy, g_w, None, None, None
 
 
@@ -735,7 +743,7 @@ class MulFn(Function):
         return MulFn.apply(g, mask), None
 
 
-_rng_state = {"seed": 0x5EED, "ctr": {}}
+_rng_state = {"seed": 0x5EED, "rank": 0, "ctr": {}}
 
 
 def manual_seed(seed: int):
@@ -746,6 +754,16 @@ def manual_seed(seed: int):
         c.zero_()
 
 
+def set_rng_rank(rank: int):
+    """Data-parallel runs: every rank draws from its own Philox key (seed + rank * odd 64-bit constant), so that the
+    shards of a global batch get different dropout masks / generator noise under the same manual_seed()."""
+    _rng_state["rank"] = int(rank)
+
+
+def _rng_key() -> int:
+    return (_rng_state["seed"] + _rng_state["rank"] * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+
+
 def _rng(shape, dtype, device, mode, param=0.0):
     device = torch.device(device)
     key = device.index if device.index is not None else torch.cuda.current_device()
@@ -753,7 +771,7 @@ def _rng(shape, dtype, device, mode, param=0.0):
     if ctr is None:
         ctr = _rng_state["ctr"][key] = torch.zeros(1, dtype=torch.int64, device=device)
     out = torch.empty(shape, dtype=dtype, device=device)
-    lib().call("vca_rng_dev", BF16 if dtype == torch.bfloat16 else F32, out, out.numel(), _rng_state["seed"], ctr, mode, float(param))
+    lib().call("vca_rng_dev", BF16 if dtype == torch.bfloat16 else F32, out, out.numel(), _rng_key(), ctr, mode, float(param))
     return out
 
 

@@ -64,16 +64,28 @@ class FusedAdam:
         self.v = torch.zeros_like(group.flat)
         self.vmax = torch.zeros_like(group.flat) if amsgrad else None
         self.t_dev = torch.zeros(1, dtype=torch.int32, device=group.flat.device)   # step count lives on the device
+        # ... and so does the learning rate: the kernel reads it, so an lr decay (train.py:85-86, MultiStepLR([500, 800],
+        # 0.1)) takes effect in captured CUDA graphs too -- set_lr() writes one float, no re-capture
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=group.flat.device)
 
     @property
     def t(self):
         return int(self.t_dev.item())
 
+    def set_lr(self, lr: float):
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
+
+    @property
+    def param_groups(self):
+        """torch.optim-style view for lr schedulers / logging (train.py:165 prints param_groups[0]['lr'])."""
+        return [{"lr": self.lr, "params": self.g.params}]
+
     def zero_grad(self):
         self.g.zero_grad()
 
     def step(self, grad_scale: float = 1.0):
-        lib().call("vca_adam_step_dev", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr, self.betas[0],
+        lib().call("vca_adam_step_dev", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr_dev, self.betas[0],
                    self.betas[1], self.eps, self.wd, self.t_dev, grad_scale)
         self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
 
@@ -118,6 +130,8 @@ class Trainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        if self.world > 1:
+            self._sync_replicas()
         # Data-parallel runs split the G backward where the generator's last gradient is written: the all-reduce of the
         # gen + post gradients (62 % of the G buffer) then runs on the comm stream underneath the visual front-end's
         # backward.  Single-GPU runs keep the backward in one piece (no all-reduce to hide, one graph less).
@@ -132,6 +146,38 @@ class Trainer:
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)   # the branch streams are intentional
 
     # -- data-parallel exchange ---------------------------------------------------------------------------------
+    def _sync_replicas(self):
+        """Data-parallel start-up: every replica takes rank 0's parameters and BatchNorm buffers -- only
+        gradients are exchanged afterwards, so replicas that start different stay different -- and every rank moves to
+        its own Philox sub-stream, so dropout masks and generator noise differ across the shards of a global batch."""
+        import torch.distributed as dist
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None and self.pg is not dist.group.WORLD else 0
+        dp.broadcast_flat(self.G.flat, src, self.pg)
+        dp.broadcast_flat(self.D.flat, src, self.pg)
+        bufs = [b for m in self.mods.values() for b in m.buffers()]
+        fl = [b for b in bufs if b.is_floating_point()]
+        if fl:
+            flat = torch.cat([b.reshape(-1).float() for b in fl])
+            dp.broadcast_flat(flat, src, self.pg)
+            o = 0
+            for b in fl:
+                b.copy_(flat[o:o + b.numel()].view(b.shape)); o += b.numel()
+        for b in bufs:
+            if not b.is_floating_point():
+                dist.broadcast(b, src, group=self.pg)
+        ops.set_rng_rank(dist.get_rank(self.pg))
+
+    def replicas_in_sync(self) -> bool:
+        """True when the parameter checksums of all ranks are bit-identical (they must be after any number of steps)."""
+        if self.world == 1:
+            return True
+        import torch.distributed as dist
+        cs = torch.stack([self.G.flat.double().sum(), self.D.flat.double().sum()])
+        lo, hi = cs.clone(), cs.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.pg)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.pg)
+        return bool(torch.equal(lo, hi))
+
     def _allreduce(self, group: FlatGroup, bucket_elems: int = 8 << 20, lo: int = 0, hi: Optional[int] = None,
                    wait: bool = True):
         """Sum-all-reduce group.grad[lo:hi] on the comm stream, ordered after the current stream.  wait=False leaves it
