@@ -40,6 +40,10 @@ int vca_set_option(const char* key, int value);
 /* ---- convolutions (nn.Conv1d/2d/3d: visual_front.py:11, resnet.py:5-14, generator.py:19-25,62-66,103-108,
  *      177-185,204-225,272-300,323-327) and their autograd (aten::convolution_backward) ------------------- */
 int vca_pack_conv_weight(int dtype, const float* w, void* wf, void* wd, int Cout, int Cin, int taps, cudaStream_t stream);
+/* every conv weight of an optimizer group in one launch: jobs = device table, 8 x int64 per job {w, wf, wd, Cout, Cin, taps,
+   first CTA (prefix sum of vca_pack_job_ctas), 0}; total_ctas = the sum */
+int vca_pack_job_ctas(int Cout, int Cin, int taps);
+int vca_pack_conv_weights_batched(int dtype, const long long* jobs, int njobs, long long total_ctas, cudaStream_t stream);
 /* Pixel-pair merge of a (Cin -> Cout, KH x 5, pad 2, stride 1) convolution (the 32-channel nn.Conv2d(.., 5, 1, 2) of
  * generator.py:58-60): the same linear map as a (2Cin -> 2Cout, KH x 3, pad 1) convolution over the free view
  * [N,H,W/2,2Cin], with w2[p*Cout+co][s*Cin+ci][kh][jj] = w[co][ci][kh][2jj+s-p].  expand: w -> w2 (fp32);

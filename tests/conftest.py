@@ -83,3 +83,11 @@ def synthetic_frames(seed, n, H, W):
         base = np.stack([127 + 120 * np.sin(xx / (9.0 + c) + 0.3 * i) * np.cos(yy / (7.0 + 2 * c) - 0.2 * i) for c in range(3)], -1)
         out[i] = np.clip(base + rng.integers(-40, 41, (H, W, 3)), 0, 255).astype(np.uint8)
     return out
+
+
+def sample_index(numel: int, ns: int = 512) -> torch.Tensor:
+    """Up to `ns` fixed positions spread over a flattened parameter (all of it when it is small): the sampling of the
+    gradient fixtures (tests/golden/make_golden_bf16.py) and of the tests that read them."""
+    if numel <= ns:
+        return torch.arange(numel)
+    return torch.linspace(0, numel - 1, ns, dtype=torch.float64).round().long()

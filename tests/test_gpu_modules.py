@@ -257,3 +257,56 @@ def test_odd_long_and_short_sequences(V, state_spec, T, length):
         for flag in (False, True):
             assert rel_l2(sm(phon_r.cuda(), mel.cuda(), flag).cpu(), O.sync_discriminator(sd, phon_r, mel, flag, False)) < TOL
     assert O.final_length(T) == V.models.final_length(T) == T // 2 // 2
+
+
+@pytest.mark.parametrize("T,lens", [(75, [75, 41]), (250, [250, 173])])
+def test_generator_train_mode_bf16_long_ragged(V, state_spec, golden, T, lens):
+    """Train-mode (batch-statistic BatchNorm) generator on the bf16 / tcgen05 path at the GRID length T = 75 and the LRS
+    length T = 250 with ragged key masks -- forward and parameter gradients -- against the oracle.
+    Bound: outputs no further from the fp32 oracle than 1.5 x what the unmodified reference loses under bf16 autocast
+    (golden autocast_bf16_train_errs, measured at T = 20: g1 4.3e-2, g2 6.7e-2, g3 8.2e-2).  At T = 75 the gradient
+    yard-stick is computed live: the oracle (= the reference's torch ops) under torch.autocast(bfloat16) vs its fp64
+    run; ours must stay within 2 x of it on every checked parameter."""
+    g = torch.Generator().manual_seed(1000 + T)
+    B = 2
+    sent = torch.randn(B, 512, T, generator=g) * 0.5
+    phon = torch.randn(B, T, 512, generator=g) * 0.5
+    noise = torch.randn(B, 128, 20, T, generator=g)
+    keys = ["decode.0.conv2.weight", "decode.2.norm1.weight", "att1.q.weight", "att1.k.weight", "att2.mel.weight", "attconv2.weight",
+            "g3.2.conv2.weight", "to_mel3.2.weight"]
+    with_grads = T <= 75
+
+    def oracle_run(dtype, autocast=False):
+        sd = make_state(state_spec, "gen", requires_grad=with_grads)
+        if dtype == torch.float64:
+            sd = to64(sd)
+        with torch.autocast("cpu", dtype=torch.bfloat16, enabled=autocast), torch.set_grad_enabled(with_grads):
+            out = O.decoder(sd, sent.to(dtype), phon.to(dtype), lens, noise.to(dtype), True)
+            if with_grads:
+                sum(o.float().square().mean() for o in out).backward()
+        return [o.detach().float() for o in out], ({k: sd[k].grad.double() for k in keys} if with_grads else None)
+    r32, _ = oracle_run(torch.float32)
+    ac = dict(zip(("phon", "sent", "g1", "g2", "g3", "gs"), golden["autocast_bf16_train_errs"]))
+    V.set_precision("bf16")
+    try:
+        gen = build(V, state_spec, "gen", True)
+        gen.fixed_noise = noise
+        with torch.set_grad_enabled(with_grads):
+            out = gen(sent.cuda(), phon.cuda(), torch.tensor(lens))
+            if with_grads:
+                sum(o.square().mean() for o in out).backward()
+        torch.cuda.synchronize()
+        errs = {k: rel_l2(o.detach().cpu(), r) for k, o, r in zip(("g1", "g2", "g3"), out, r32)}
+        print(f"train-mode bf16 generator, T={T}, lens={lens}: output errors vs fp32 oracle", errs)
+        for k, e in errs.items():
+            assert e < 1.5 * float(ac[k]), (k, e, float(ac[k]))
+        if with_grads:
+            _, g64 = oracle_run(torch.float64)
+            _, gac = oracle_run(torch.float32, autocast=True)
+            pd = dict(gen.named_parameters())
+            for k in keys:
+                e_o, e_r = rel_l2(pd[k].grad.cpu(), g64[k]), rel_l2(gac[k], g64[k])
+                print(f"  dW({k}): ours bf16 vs fp64 {e_o:.3e}; oracle under bf16 autocast vs fp64 {e_r:.3e}")
+                assert e_o <= 2.0 * e_r + 1e-2, (k, e_o, e_r)
+    finally:
+        V.set_precision("fp32")

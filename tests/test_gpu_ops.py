@@ -174,6 +174,12 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_bf16(V, case, hs):
     """hs = 2 forces the halo-resident / streamed-weights kernel (conv_tc_hs.cu) wherever its geometry fits"""
+    _tc_case(V, case, hs)
+
+
+def _tc_case(V, case, hs):
+    """forward / dgrad / wgrad / bias gradient of one conv on the tcgen05 path vs fp32 math (torch CPU) on the same
+    bf16-rounded inputs; tolerance BF16_TOL relative L2 (the output rounding to bf16 alone is ~2.3e-3)"""
     N, Cin, H, W, Cout, k, p = case
     assert V.lib().cdll.vca_set_option(b"hs_mode", hs) == 0
     g = torch.Generator().manual_seed(sum(case))
@@ -203,6 +209,45 @@ def test_conv_tc_bf16(V, case, hs):
     finally:
         V.set_precision("fp32")
         V.lib().cdll.vca_set_option(b"hs_mode", 1)
+
+
+# Production geometry (B = 32, T = 75 step of bench.py, batch cut to what the CPU reference finishes in seconds while the
+# grids stay multi-wave / split-K exactly as in the benchmark): the layers VERDICT r01 listed as never compared.
+PROD_CASES = [
+    (4, 640, 20, 75, 512, 5, 2),     # gen.decode.0.conv1 as a plain conv: K = 16 000, 10 K chunks, BN = 256 tiles
+    (4, 512, 20, 75, 512, 5, 2),     # gen.decode.0.conv2: 256-wide wgrad tiles
+    (4, 32, 80, 300, 32, 5, 2),      # gen.g3.*: pixel-pair merged, weights-stationary persistent kernel, multi-tap wgrad
+    (4, 64, 40, 150, 64, 5, 2),      # gen.g2.*
+    (300, 64, 28, 28, 64, 3, 1),     # resnet.layer1 at 4 clips x 75 frames: multi-wave persistent scheduling
+    (300, 128, 14, 14, 128, 3, 1),   # resnet.layer2
+    (32, 1024, 5, 18, 512, 5, 2),    # dis3.cond.1 at the full batch: split-K over the taps (small grid, K = 25 600)
+    (32, 512, 5, 18, 512, 5, 0),     # dis3.uncond.1: pad 0, split-K; dgrad onto a taller map skips all-padding taps
+]
+
+
+@pytest.mark.parametrize("case", PROD_CASES)
+def test_conv_tc_bf16_production_geometry(V, case):
+    _tc_case(V, case, 1)
+
+
+def test_stem_conv_tc_bf16_production_geometry(V):
+    """the visual front-end stem at the real frame size (75 x 112 x 112 -> 75 x 56 x 56 x 64): tiled im2col + (5,1) conv"""
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(2, 1, 75, 112, 112, generator=g).bfloat16().float()
+    w = (torch.randn(64, 1, 5, 7, 7, generator=g) / 15).bfloat16().float().requires_grad_(True)
+    y = F.conv3d(x, w, None, (1, 2, 2), (2, 3, 3))
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    y.backward(dy)
+    V.set_precision("bf16")
+    try:
+        wd = w.detach().cuda().requires_grad_(True)
+        yd = V.ops.stem_conv(x.cuda(), wd)
+        yd.backward(cl(dy).cuda().bfloat16())
+        e = dict(fwd=rel_l2(nchw(yd.detach().float().cpu()), y), wgrad=rel_l2(wd.grad.cpu(), w.grad))
+        print("stem production", e)
+        assert max(e.values()) < BF16_TOL, e
+    finally:
+        V.set_precision("fp32")
 
 
 @pytest.mark.parametrize("case", [(4, 64, 28, 28, 128, 3), (3, 128, 7, 7, 256, 3), (2, 128, 40, 30, 256, 3), (3, 64, 28, 28, 128, 1),

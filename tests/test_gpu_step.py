@@ -6,7 +6,7 @@ import os
 import pytest
 import torch
 
-from conftest import make_state, golden_inputs, rel_l2, GOLD
+from conftest import make_state, golden_inputs, rel_l2, sample_index, GOLD
 from oracle import vca_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -321,5 +321,71 @@ def test_split_g_backward_matches_single_backward():
         for k in ("gen_loss", "dis_loss", "recon"):
             for (a, b), tol in zip(zip(*losses), (5e-3, 1e-2)):
                 assert abs(a[k] - b[k]) <= tol * max(1.0, abs(a[k])), (k, a[k], b[k])
+    finally:
+        V.set_precision("fp32")
+
+
+def _sampled(names, tensors_by_name):
+    from conftest import sample_index
+    return [tensors_by_name[n].detach().double().reshape(-1)[sample_index(tensors_by_name[n].numel()).to(tensors_by_name[n].device)].cpu()
+            for n in names]
+
+
+def test_step_bf16_gradient_bound():
+    """north star: gradients of the bf16 (tcgen05) path inside "a stated bf16 bound".  The bound, per parameter, against
+    the fp64 run of the UNMODIFIED reference (tests/golden/make_golden_bf16.py, sampled at 512 fixed positions):
+        err(ours_bf16, fp64) <= 2 x err(reference under torch.autocast(bfloat16), fp64)   [per-module median]
+        err(ours_bf16, fp64) <= 4 x that + 0.05                                            [every parameter]
+    where err = ||a - b||_2 / ||b||_2 over the sampled entries; parameters whose true gradient is analytically zero
+    (conv biases in front of a BatchNorm) are excluded from the relative measure and must stay negligible instead.
+    At this B = 2, T = 20 train-mode-BatchNorm case the reference's own autocast gradients are 9 % (discriminators) to
+    50 % (visual front-end) away from fp64 -- that is the yard-stick, not a target.
+    Post-Adam weights: Adam's first update is -lr * sign(g), so weights are compared through the agreement of the
+    update sign with the fp64 run: ours must agree at least as often as the reference-autocast run (minus 2 %)."""
+    import numpy as np
+    V, tr, out = _run("bf16")
+    try:
+        z = np.load(os.path.join(GOLD, "golden_bf16_grads.npz"))
+        meta = json.load(open(os.path.join(GOLD, "golden_bf16_names.json")))
+        names, counts = meta["names"], meta["counts"]
+        pd = {f"{k}.{n}": p for k, m in tr.mods.items() for n, p in m.named_parameters()}
+        mine = _sampled(names, {n: pd[n].grad for n in names})
+        after = _sampled(names, pd)
+        g64, gac = torch.from_numpy(z["grad_fp64"]).double(), torch.from_numpy(z["grad_autocast"]).double()
+        w64, wac = torch.from_numpy(z["after_fp64"]).double(), torch.from_numpy(z["after_autocast"]).double()
+        spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+        o, rows = 0, []
+        scale = float(torch.median(torch.tensor([float(g64[sum(counts[:i]):sum(counts[:i + 1])].norm()) for i in range(len(names))])))
+        agree_o = agree_r = tot = 0
+        for n, c, g, wa in zip(names, counts, mine, after):
+            t, r = g64[o:o + c], gac[o:o + c]
+            tw, rw = w64[o:o + c], wac[o:o + c]
+            o += c
+            mod, key = n.split(".", 1)
+            w0 = O.det_tensor(n, spec[mod][key][0], torch.float32).double().reshape(-1)
+            w0 = w0[sample_index(w0.numel())]
+            if float(t.norm()) < 1e-9 * scale:                    # analytically zero gradient: what is left is rounding noise,
+                # held to the noise the reference itself leaves there under bf16 autocast (e.g. gen.attconv2.bias: 3.9e-3)
+                assert float(g.norm()) <= 2.0 * float(r.norm()) + 1e-6 * scale, (n, float(g.norm()), float(r.norm()))
+                continue
+            rows.append((n, float((g - t).norm() / t.norm()), float((r - t).norm() / t.norm())))
+            live = (t.abs() > 1e-3 * t.abs().max())               # update sign is only meaningful where the gradient is not noise
+            s64, so, sr = torch.sign(tw - w0)[live], torch.sign(wa - w0)[live], torch.sign(rw - w0)[live]
+            agree_o += int((so == s64).sum()); agree_r += int((sr == s64).sum()); tot += int(live.sum())
+        by_mod = {}
+        for n, eo, er in rows:
+            by_mod.setdefault(n.split(".")[0], []).append((eo, er))
+        worst = []
+        for m, v in sorted(by_mod.items()):
+            eo = sorted(x[0] for x in v)[len(v) // 2]
+            er = sorted(x[1] for x in v)[len(v) // 2]
+            print(f"bf16 gradient error vs fp64, {m:8s} ({len(v):3d} params): ours median {eo:.3e}   reference-autocast median {er:.3e}")
+            worst.append((m, eo, er))
+        for m, eo, er in worst:
+            assert eo <= 2.0 * er, (m, eo, er)
+        bad = [(n, eo, er) for n, eo, er in rows if eo > 4.0 * er + 0.05]
+        assert not bad, bad[:10]
+        print(f"post-Adam update-sign agreement with fp64: ours {agree_o / tot:.4f}, reference-autocast {agree_r / tot:.4f} ({tot} sampled weights)")
+        assert agree_o / tot >= agree_r / tot - 0.02
     finally:
         V.set_precision("fp32")

@@ -205,7 +205,61 @@ __global__ void __launch_bounds__(256) pack_tiled_kernel(const float* __restrict
   }
 }
 
+// ---- batched re-pack: every conv weight of an optimizer group in ONE launch -------------------------------------
+// Job table (device, 8 x int64 per job): w (fp32 [Cout][Cin][taps]), wf, wd (either may be 0), Cout, Cin, taps,
+// first CTA of the job, unused.  A CTA finds its job by binary search on the CTA offsets and then does what a CTA of
+// pack_tiled_kernel does.  Replaces ~75 launches per optimizer step (the step re-packs every weight Adam just changed).
+template <class T>
+__global__ void __launch_bounds__(256) pack_batched_kernel(const long long* __restrict__ jobs, int njobs) {
+  __shared__ float s[PK_T][PK][PK + 1];
+  int lo = 0, hi = njobs - 1;
+  const long long me = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[(long long)mid * 8 + 6] <= me) lo = mid; else hi = mid - 1;
+  }
+  const long long* j = jobs + (long long)lo * 8;
+  const float* __restrict__ w = reinterpret_cast<const float*>(j[0]);
+  T* __restrict__ wf = reinterpret_cast<T*>(j[1]);
+  T* __restrict__ wd = reinterpret_cast<T*>(j[2]);
+  const int Cout = (int)j[3], Cin = (int)j[4], taps = (int)j[5];
+  int local = (int)(me - j[6]);
+  const int tiles_ci = (Cin + PK - 1) / PK, tiles_co = (Cout + PK - 1) / PK;
+  const int bx = local % tiles_ci; local /= tiles_ci;
+  const int by = local % tiles_co; const int bz = local / tiles_co;
+  const int co0 = by * PK, ci0 = bx * PK, t0 = bz * PK_T;
+  const int tc = min(PK_T, taps - t0);
+  for (int i = threadIdx.x; i < PK * PK * tc; i += blockDim.x) {
+    const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
+    float v = 0.f;
+    if (co0 + co < Cout && ci0 + ci < Cin) v = w[((long long)(co0 + co) * Cin + ci0 + ci) * taps + t0 + t];
+    s[t][co][ci] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < PK * PK * tc; i += blockDim.x) {
+    const int a = i % PK; int r = i / PK; const int b = r % PK; const int t = r / PK;
+    if (wd && co0 + b < Cout && ci0 + a < Cin) wd[((long long)(t0 + t) * Cout + co0 + b) * Cin + ci0 + a] = from_f<T>(s[t][b][a]);
+    if (wf && ci0 + b < Cin && co0 + a < Cout) wf[((long long)(t0 + t) * Cin + ci0 + b) * Cout + co0 + a] = from_f<T>(s[t][a][b]);
+  }
+}
+
 }  // namespace
+
+extern "C" {
+// CTAs a job of this shape occupies in vca_pack_conv_weights_batched (the host builds the CTA offsets of the table with it)
+int vca_pack_job_ctas(int Cout, int Cin, int taps) {
+  if (Cout <= 0 || Cin <= 0 || taps <= 0) return 0;
+  return ((Cin + PK - 1) / PK) * ((Cout + PK - 1) / PK) * ((taps + PK_T - 1) / PK_T);
+}
+// jobs: device table described above; total_ctas = sum of vca_pack_job_ctas over the jobs.
+int vca_pack_conv_weights_batched(int dtype, const long long* jobs, int njobs, long long total_ctas, cudaStream_t s) {
+  VCA_CHECK_ARG(jobs && njobs > 0 && total_ctas > 0 && total_ctas < 0x7fffffffLL);
+  if (dtype == VCA_F32) pack_batched_kernel<float><<<(unsigned)total_ctas, 256, 0, s>>>(jobs, njobs);
+  else pack_batched_kernel<bf16><<<(unsigned)total_ctas, 256, 0, s>>>(jobs, njobs);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+}
 
 #define SMALL_T(dtype, CALL_F32, CALL_BF16) do { if ((dtype) == VCA_F32) { CALL_F32; } else { CALL_BF16; } } while (0)
 

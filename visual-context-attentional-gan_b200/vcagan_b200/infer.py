@@ -33,3 +33,34 @@ def synthesize(v_front, gen, post, vid, vid_len, n_iters=60, tta=True, mel_len=N
         mag = audio.lrs_denormalize_spec(mag)
     wav_gl = audio.griffin_lim(mag, None, n_iters, init_angles=init_angles)            # vid_aud_grid.py:212-217
     return dict(mel=g3, spec=gs, wav=audio.deemphasize(wav_gl), wav_gl=wav_gl)          # :218-223
+
+
+def save_eval_outputs(out_dir, f_names, mel, spec, mel_len, wav=None, sample_rate=16000):
+    """What test.py:145-159 leaves on disk for the downstream ASR scorers (ASR_model/*/test.py read these files):
+    `<out_dir>/spec_mel/<subject>/<file>.npz` with arrays `mel` = g3[b, :, :, :mel_len[b]] (1,80,L) and `spec` =
+    gs[b, :, :, :mel_len[b]] (1,321,L), and -- when `wav` (B, samples) is given -- `<out_dir>/wav/<subject>/<file>.wav`
+    as 16-bit PCM (the reference writes it with soundfile, subtype PCM_16; the stdlib `wave` module produces the same
+    container).  f_names follow the dataset's 'subject/video/file' form (vid_aud_grid.py f_name).  Returns the paths."""
+    import os
+    import wave
+
+    import numpy as np
+    paths = []
+    mel_c, spec_c = mel.detach().float().cpu().numpy(), spec.detach().float().cpu().numpy()
+    wav_c = None if wav is None else (wav.detach().float().cpu().numpy() if torch.is_tensor(wav) else np.asarray(wav))
+    for b, name in enumerate(f_names):
+        sub_name, _, file_name = name.split('/')
+        L = int(mel_len[b])
+        d = os.path.join(out_dir, "spec_mel", sub_name)
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, file_name + ".npz")
+        np.savez(p, mel=mel_c[b, :, :, :L], spec=spec_c[b, :, :, :L])
+        paths.append(p)
+        if wav_c is not None:
+            d = os.path.join(out_dir, "wav", sub_name)
+            os.makedirs(d, exist_ok=True)
+            pcm = (np.clip(wav_c[b], -1.0, 1.0) * 32767.0).round().astype("<i2")
+            with wave.open(os.path.join(d, file_name + ".wav"), "wb") as f:
+                f.setnchannels(1); f.setsampwidth(2); f.setframerate(sample_rate)
+                f.writeframes(pcm.tobytes())
+    return paths

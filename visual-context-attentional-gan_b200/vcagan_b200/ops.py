@@ -149,12 +149,57 @@ def _packed(w: torch.Tensor, dtype: torch.dtype):
     wd = torch.empty((taps, cout, cin), dtype=dtype, device=w.device)
     lib().call("vca_pack_conv_weight", BF16 if dtype == torch.bfloat16 else F32, wc, wf, wd, cout, cin, taps)
     if cacheable:
-        _pack_cache[key] = (tag, wf, wd, weakref.ref(base))
+        # the 5th field says whether a PackPlan may refresh this entry in place: the kernel must be able to read the
+        # parameter's own storage in [Cout][Cin][taps] order
+        direct = wc.data_ptr() == w.data_ptr() and w.dtype == torch.float32
+        _pack_cache[key] = (tag, wf, wd, weakref.ref(base), direct, (cout, cin, taps))
     return wf, wd
 
 
-def clear_pack_cache():
-    _pack_cache.clear()
+def clear_pack_cache(keep=()):
+    """Forget every packed weight except the entries owned by the given PackPlans."""
+    owned = {key for plan in keep if plan is not None for key, _, _ in plan.items}
+    for k in [k for k in _pack_cache if k not in owned]:
+        del _pack_cache[k]
+
+
+class PackPlan:
+    """One launch that re-packs EVERY cached conv / linear weight of a set of parameters (an optimizer group) into its
+    persistent bf16 slabs -- run right after the fused Adam step that changed them, instead of ~75 separate
+    vca_pack_conv_weight launches scattered over the next forward pass.  Built from the pack cache after a warm-up step
+    (only then is it known which views of which parameters the step actually packs)."""
+
+    def __init__(self, params):
+        ids = {id(p) for p in params}
+        self.items = []          # (cache key, base parameter)
+        rows, off = [], 0
+        self.dtype = None
+        for key, hit in _pack_cache.items():
+            base = hit[3]()
+            if base is None or id(base) not in ids or not hit[4]:
+                continue
+            if self.dtype is None:
+                self.dtype = key[2]
+            if key[2] != self.dtype:
+                continue
+            cout, cin, taps = hit[5]
+            rows.append([key[0], hit[1].data_ptr(), hit[2].data_ptr(), cout, cin, taps, off, 0])
+            off += lib().query("vca_pack_job_ctas", cout, cin, taps)
+            self.items.append((key, base, hit[1].data_ptr()))
+        self.total = off
+        self.table = torch.tensor(rows, dtype=torch.int64, device=params[0].device) if rows else None
+
+    def run(self):
+        """Re-pack now (on the current stream) and mark the cache entries as up to date with the parameters."""
+        if self.table is None:
+            return
+        lib().call("vca_pack_conv_weights_batched", BF16 if self.dtype == torch.bfloat16 else F32, self.table, len(self.items), self.total)
+        for key, base, slab in self.items:
+            hit = _pack_cache.get(key)
+            if hit is None or hit[1].data_ptr() != slab:      # re-packed into fresh slabs since (e.g. load_state_dict): not ours
+                continue
+            ep = getattr(base, "_vca_epoch", None)
+            _pack_cache[key] = ((base._version, ep[0] if ep is not None else 0),) + tuple(hit[1:])
 
 
 def _geom(xshape, wshape, stride, pad) -> Tuple[ConvGeom, tuple]:
@@ -655,7 +700,11 @@ class AxpbyFn(Function):
     @staticmethod
     def backward(ctx, g):
         ga = AxpbyFn.apply(g, None, ctx.alpha, 0.0) if ctx.needs_input_grad[0] else None
-        gb = AxpbyFn.apply(g, None, ctx.beta, 0.0) if (ctx.has_b and ctx.needs_input_grad[1]) else None
+        if ctx.has_b and ctx.needs_input_grad[1]:
+            # (r + s) / sqrt(2): both branches receive the SAME scaled gradient -- one kernel, one tensor
+            gb = ga if (ga is not None and ctx.alpha == ctx.beta) else AxpbyFn.apply(g, None, ctx.beta, 0.0)
+        else:
+            gb = None
         return ga, gb, None, None
 
 

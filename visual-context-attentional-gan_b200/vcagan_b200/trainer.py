@@ -110,6 +110,8 @@ class Trainer:
         self.lrs = lrs
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
+        self.batched_pack = True            # one weight re-pack launch per optimizer step (ops.PackPlan) instead of ~75
+        self._pack_g = self._pack_d = None  # built after the first step (the pack cache then lists what the step uses)
         self._branch_streams = None
         self._br_used = []                  # branch streams with work since the last join
         self.device = torch.device(device)
@@ -261,7 +263,9 @@ class Trainer:
             self._allreduce(self.G, hi=self._vf_numel)
         else:
             self._allreduce(self.G)
-        return self._phase_end()
+        out = self._phase_end()
+        self._build_pack_plans()
+        return out
 
     def _phase_d(self, vid, mel, spec, vid_len, noise=None):
         """forward of v_front + generator, the whole D phase and its backward (train.py:168-210)."""
@@ -341,6 +345,8 @@ class Trainer:
         dis = (m["dis1"], m["dis2"], m["dis3"])
         g, sdet, T, phon = st["g"], st["sdet"], st["T"], st["phon"]
         self.d_opt.step(1.0 / self.world)
+        if self._pack_d is not None:
+            self._pack_d.run()
         gs = m["post"](g[2])
         res = self._branches([lambda: dis[2](g[2], sdet, T), lambda: dis[1](g[1], sdet, T), lambda: dis[0](g[0], sdet, T),
                               lambda: m["s_dis"](phon.detach(), g[2], True).mean()])
@@ -373,8 +379,18 @@ class Trainer:
 
     def _phase_end(self):
         self.g_opt.step(1.0 / self.world)
+        if self._pack_g is not None:
+            self._pack_g.run()
         out, self._st = self._st["out"], None
         return out
+
+    def _build_pack_plans(self):
+        """After a full step the pack cache holds every (view of a) parameter the step packs: from now on they are
+        refreshed by ONE launch per optimizer step into the same persistent slabs."""
+        if not self.batched_pack or self._pack_g is not None or ops.cfg.dtype != torch.bfloat16:
+            return
+        self._pack_g, self._pack_d = ops.PackPlan(self.G.params), ops.PackPlan(self.D.params)
+        self._pack_g.run(); self._pack_d.run()
 
     # -- CUDA-graph replay of the step ----------------------------------------------------------------------------
     def capture(self, vid, mel, spec, vid_len, warmup=3, noise=None):
@@ -392,7 +408,7 @@ class Trainer:
                 self.step(*self._sin, noise=self._snoise)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        ops.clear_pack_cache()            # every weight (re)pack must be recorded inside the graphs
+        ops.clear_pack_cache(keep=(self._pack_g, self._pack_d))   # every other weight (re)pack must be recorded inside the graphs
         pool = torch.cuda.graph_pool_handle()
         self._graphs = [torch.cuda.CUDAGraph() for _ in range(4 if self.split_g_backward else 3)]
         n0 = lib().launches
