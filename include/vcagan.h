@@ -104,6 +104,12 @@ int vca_s2d(int dtype, const void* x, void* y, int NF, int H, int W, int C, int 
 int vca_d2s(int dtype, const void* y, void* x, int NF, int H, int W, int C, int H2, int W2, cudaStream_t stream);
 int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF, int H, int W, cudaStream_t stream);
 
+/* ---- batched bf16 GEMM on tcgen05 (attention backward contractions of generator.py:154-171, sync similarity :353) ----
+ * C[z] (M x N row-major, ld ldc, batch stride strideC; bf16 or fp32) = alpha * op(A[z]) op(B[z]), fp32 accumulate.
+ * a_mn = 0: A is [Z][M][K] (K contiguous, row pitch lda); a_mn = 1: A is [Z][K][M] (M contiguous).  Same for B with N.
+ * lda / ldb / strideA / strideB in elements, multiples of 8. */
+int vca_bmm_tc(const void* A, const void* B, void* C, int Z, int M, int N, int K, int a_mn, int b_mn, long long lda, long long strideA, long long ldb, long long strideB, long long ldc, long long strideC, int out_f32, float alpha, cudaStream_t stream);
+
 /* ---- GRU gates (visual_front.py:20,33-34), attention softmax (generator.py:161-164), sync losses
  *      (generator.py:347-359), gan_loss (generator.py:363-366), L1 (train.py:226-229), Adam (train.py:82-83) - */
 int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const float* hprev, float* hnext, float* out, float* gates, int ndir, int T, int B, int H, int step, cudaStream_t stream);

@@ -154,6 +154,7 @@ def test_checkpoint_roundtrip_and_eval_npz(tmp_path, state_spec):
             b = p2(g2(*reversed(v2(vid.cuda())), [20, 13])[2])
         assert rel_l2(a.cpu(), b.cpu()) < 1e-6, rel_l2(a.cpu(), b.cpu())
         # the .npz / .wav files test.py:145-159 writes
+        g2.fixed_noise = None            # flip TTA runs the clip and its mirror image as one batch of 2B: device noise
         o = infer.synthesize(v2, g2, p2, vid.cuda(), torch.tensor([20, 13]), n_iters=4, tta=True)
         names = ["s1/video/bbaf2n", "s2/video/lgwm5a"]
         paths = infer.save_eval_outputs(str(tmp_path / "test"), names, o["mel"], o["spec"], [80, 52], wav=o["wav"])

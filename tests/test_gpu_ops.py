@@ -536,3 +536,29 @@ def test_conv_rowconst(V, prec):
         assert max(e.values()) < tol, e
     finally:
         V.set_precision("fp32")
+
+
+@pytest.mark.parametrize("case", [
+    # Z, M, N, K, a_mn, b_mn, out fp32
+    (3, 75, 80, 256, 0, 0, 1),      # dP = dO V^T at GRID length (S = 75 padded to 80 columns)
+    (2, 150, 256, 80, 0, 1, 0),     # dQ = dS K      (K = padded S, rows of K beyond S are zero)
+    (2, 75, 256, 150, 1, 1, 0),     # dK = dS^T Q    (reduction over 150 queries, ragged K chunk)
+    (2, 250, 256, 500, 1, 1, 0),    # ... LRS: S = 250 keys (two M tiles), 500 queries
+    (2, 500, 256, 256, 0, 0, 1),    # LRS dP: four M tiles, full-width N
+    (4, 40, 40, 512, 0, 0, 1),      # sync similarity S x S over 512 features
+])
+def test_bmm_tc(V, case):
+    """Batched tcgen05 GEMM with K-major / MN-major operands vs fp32 matmul on the same bf16 inputs"""
+    Z, M, N, K, a_mn, b_mn, f32 = case
+    g = torch.Generator().manual_seed(sum(case))
+    pad8 = lambda n: (n + 7) // 8 * 8   # noqa: E731
+    A = torch.randn((Z, K, pad8(M)) if a_mn else (Z, M, pad8(K)), generator=g).bfloat16().cuda()
+    Bm = torch.randn((Z, K, pad8(N)) if b_mn else (Z, N, pad8(K)), generator=g).bfloat16().cuda()
+    a = A[:, :, :M].float().transpose(1, 2) if a_mn else A[:, :, :K].float()          # (Z, M, K)
+    b = Bm[:, :, :N].float() if b_mn else Bm[:, :, :K].float().transpose(1, 2)         # (Z, K, N)
+    ref = 0.25 * torch.bmm(a, b)
+    out = V.ops.bmm_tc_raw(A, Bm, M, N, K, bool(a_mn), bool(b_mn), torch.float32 if f32 else torch.bfloat16, 0.25)
+    torch.cuda.synchronize()
+    e = rel_l2(out.float().cpu(), ref.cpu())
+    print("bmm_tc", case, e)
+    assert e < (1e-5 if f32 else 5e-3), (case, e)

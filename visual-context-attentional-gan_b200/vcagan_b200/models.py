@@ -28,9 +28,10 @@ def _out_nchw(x_cl: torch.Tensor) -> torch.Tensor:
     return ops.cast(x_cl, torch.float32).permute(0, 3, 1, 2).contiguous()
 
 
-def _conv(x, m: nn.Module):
-    """Apply the conv whose parameters live in holder `m` (nn.Conv1d/2d/3d) to channels-last x."""
-    return ops.conv(x, m.weight, m.bias, m.stride, m.padding)
+def _conv(x, m: nn.Module, bn: nn.Module = None):
+    """Apply the conv whose parameters live in holder `m` (nn.Conv1d/2d/3d) to channels-last x.  `bn`: the BatchNorm the
+    output goes straight into -- in training mode the conv bias then has an identically zero gradient (ops.ConvFn)."""
+    return ops.conv(x, m.weight, m.bias, m.stride, m.padding, zero_bias_grad=bn is not None and bn.training)
 
 
 # =============================================================================================================
@@ -153,6 +154,13 @@ class Visual_front(nn.Module):
         return [getattr(g, n) for n in names]
 
     def forward(self, x):
+        phons = self.features(x)
+        return phons, self.sentence(phons)
+
+    # The two halves of forward(), callable separately: the generator's first six blocks need only `phons`, so the trainer
+    # runs the (latency-bound, sequential) GRU of sentence() on a side stream underneath them.
+    def features(self, x):
+        """frontend + ResNet + dropout: x (B,1,T,112,112) -> phons (B,T,512) fp32 (visual_front.py:24-29)"""
         B, _, T = x.shape[:3]
         c0 = self.frontend[0]
         if (cfg.dtype == torch.bfloat16 and cfg.use_tc and self.in_channels == 1 and c0.kernel_size == (5, 7, 7)
@@ -165,13 +173,17 @@ class Visual_front(nn.Module):
         x = self.resnet(x)                              # (B*T,512)
         fm, gm = self.drop_masks if self.drop_masks is not None else (None, None)
         x = ops.dropout(x, self.dropout.p, self.training, fm)
-        x = ops.cast(x, torch.float32).view(B, T, -1)
+        return ops.cast(x, torch.float32).view(B, T, -1)
+
+    def sentence(self, x):
+        """2-layer bi-GRU + fc: phons (B,T,512) -> sentence (B,512,T) fp32 (visual_front.py:30-36)"""
+        gm = self.drop_masks[1] if self.drop_masks is not None else None
         phons_tb = x.permute(1, 0, 2).contiguous()      # (T,B,512)
         h = ops.gru_layer(phons_tb, self._gru_params(0))
         h = ops.dropout(h, float(self.sentence_encoder.dropout), self.training, gm)
         h = ops.gru_layer(h, self._gru_params(1))       # (T,B,1024)
         s = ops.cast(ops.linear(ops.cast(h, cfg.dtype), self.fc.weight, self.fc.bias), torch.float32)  # (T,B,512)
-        return x, s.permute(1, 2, 0).contiguous()
+        return s.permute(1, 2, 0).contiguous()
 
 
 # =============================================================================================================
@@ -246,9 +258,10 @@ class GenResBlk(nn.Module):
         if self.upsample:
             r = ops.upsample2(r)
         if const_channels and not self.upsample and cfg.rowconst:
-            r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding))
+            r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding),
+                                  zero_bias_grad=self.norm2.training)
         else:
-            r = _conv(r, self.conv1)
+            r = _conv(r, self.conv1, self.norm2)
         r = ops.bn_act(r, self.norm2, ACT_LRELU, 0.2)
         r = _conv(r, self.conv2)
         s = ops.upsample2(x) if self.upsample else x
@@ -317,7 +330,7 @@ class Postnet(nn.Module):
         p = self.postnet
         B, _, Fm, L = x.shape
         h = ops.cast(x.reshape(B, Fm, L).permute(0, 2, 1).contiguous().view(B, 1, L, Fm), cfg.dtype)
-        h = _conv(h, p[0])
+        h = _conv(h, p[0], p[1])
         h = ops.bn_act(h, p[1], ACT_LRELU, 0.2)
         for i in (3, 4, 5):
             h = p[i](h)
@@ -378,8 +391,12 @@ class Decoder(nn.Module):
         return ops.cast(n.permute(0, 2, 3, 1).contiguous(), cfg.dtype)
 
     def forward(self, s, x, len):
+        return self.tail(s, self.stem(x), len)
+
+    # forward() in two stages: stem() needs only the phoneme features, tail() is everything from the first attention on.
+    def stem(self, x):
+        """noise + tiling + decode x3 + g1 x3 (generator.py:246-255): x (B,T,512) -> channels-last (B,20,T,128)"""
         B, T = x.size(0), x.size(1)
-        s = s.transpose(1, 2).contiguous()                                   # (B,T,512)
         n = self._noise(B, T, x.device)                                      # (B,20,T,128)
         xt = ops.spatial_tile(ops.cast(x.contiguous(), cfg.dtype).view(B, T * x.size(2)), 20).view(B, 20, T, x.size(2))
         h = torch.cat([xt, n], 3)                                            # (B,20,T,640)
@@ -387,6 +404,11 @@ class Decoder(nn.Module):
             h = blk(h, const_channels=x.size(2)) if i == 0 else blk(h)       # xt is constant along the 20 mel rows
         for blk in self.g1:
             h = blk(h)
+        return h
+
+    def tail(self, s, h, len):
+        """att1 ... to_mel3 (generator.py:256-265); s (B,512,T) sentence embedding, h = stem() output"""
+        s = s.transpose(1, 2).contiguous()                                   # (B,T,512)
         f1 = h
         c1 = self.att1(s, f1, len)
         h = _conv(torch.cat([h, c1], 3), self.attconv1)
@@ -470,8 +492,8 @@ class sync_Discriminator(nn.Module):
     def forward(self, v_feat, aud, gen=False):
         f = self.frontend
         a = _in_cl(aud)
-        a = ops.bn_act(_conv(a, f[0]), f[1], ACT_PRELU, 0.0, f[2].weight)
-        a = ops.bn_act(_conv(a, f[3]), f[4], ACT_PRELU, 0.0, f[5].weight)
+        a = ops.bn_act(_conv(a, f[0], f[1]), f[1], ACT_PRELU, 0.0, f[2].weight)
+        a = ops.bn_act(_conv(a, f[3], f[4]), f[4], ACT_PRELU, 0.0, f[5].weight)
         a = self.Res_block[0](a)                                             # (B,20,S,256)
         B, Fq, S, C = a.shape
         a = a.permute(0, 2, 3, 1).reshape(B, S, C * Fq)                      # index c*F+f (generator.py:344)

@@ -279,11 +279,16 @@ class ConvFn(Function):
     """y = conv(x, w) + bias on channels-last x; w/bias are fp32 parameters in the reference layout."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, pad):
+    def forward(ctx, x, w, bias, stride, pad, zero_bias_grad=False):
         _require_cuda(x, w)
         x = _c(x)
         ctx.save_for_backward(x, w)
         ctx.stride, ctx.pad, ctx.has_bias = stride, pad, bias is not None
+        # zero_bias_grad: the caller feeds y straight into a train-mode BatchNorm.  BN subtracts the batch mean, so the
+        # loss does not depend on this bias and BN's dx sums to zero over the rows: the bias gradient is identically 0
+        # (the reference computes ~1e-15 of rounding noise there).  The column-sum pass over dy is not run.
+        ctx.zero_bias_grad = bool(zero_bias_grad) and bias is not None
+        ctx.bias_shape = None if bias is None else (tuple(bias.shape), bias.device)
         ctx.bias_leaf = bias if (bias is not None and bias.is_leaf) else None   # only consulted by _grad_sink
         return _conv_fwd_raw(x, w, bias, stride, pad)
 
@@ -293,7 +298,12 @@ class ConvFn(Function):
         dy = _c(dy)
         dx = dw = db = None
         w_sink = _grad_sink(w) if _needed(ctx, 1) else None
-        b_sink = _grad_sink(ctx.bias_leaf) if (ctx.has_bias and _needed(ctx, 2)) else None
+        want_b = ctx.has_bias and _needed(ctx, 2)
+        if want_b and ctx.zero_bias_grad and not torch.is_grad_enabled():
+            want_b = False
+            if _grad_sink(ctx.bias_leaf) is None:        # plain autograd leaf: hand over an explicit zero (Adam still decays it)
+                db = torch.zeros(ctx.bias_shape[0], dtype=torch.float32, device=ctx.bias_shape[1])
+        b_sink = _grad_sink(ctx.bias_leaf) if want_b else None
         if w_sink is not None or b_sink is not None:
             # Parameter gradients that land straight in the flat .grad buffer have no consumer in the autograd graph:
             # they run on a side stream and overlap the dgrad chain (joined by Trainer._join_branches before Adam).
@@ -306,9 +316,9 @@ class ConvFn(Function):
             dx = ConvDgradFn.apply(dy, w, ctx.stride, ctx.pad, tuple(x.shape))
         if _needed(ctx, 1) and w_sink is None:
             dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
-        if ctx.has_bias and _needed(ctx, 2) and b_sink is None:
+        if want_b and b_sink is None:
             db = ColSumFn.apply(dy)
-        return dx, dw, db, None, None
+        return dx, dw, db, None, None, None
 
 
 class ConvDgradFn(Function):
@@ -422,7 +432,7 @@ class D2SFn(Function):
         return S2DFn.apply(g, ctx.hw2[0], ctx.hw2[1]), None, None
 
 
-def _conv3x3_s2_via_s2d(x, w, bias):
+def _conv3x3_s2_via_s2d(x, w, bias, zero_bias_grad=False):
     """3x3 / stride 2 / pad 1 conv as a 2x2 stride-1 conv over the space-to-depth input (4C channels), so that the
     forward, dgrad and wgrad all run on the stride-1 tcgen05 kernels (resnet.py:33 with stride 2, generator.py:326).
     W'[co, (pa*2+pb)*C + c, a, b] = w[co, c, 2a+pa, 2b+pb] (zero where the index is 3)."""
@@ -432,7 +442,7 @@ def _conv3x3_s2_via_s2d(x, w, bias):
     Cout = w.shape[0]
     wp = torch.nn.functional.pad(w, (0, 1, 0, 1))                      # (Cout, C, 4, 4)   [data movement]
     w2 = wp.view(Cout, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 4 * C, 2, 2)
-    return ConvFn.apply(xs, w2, bias, (1, 1), (0, 0))
+    return ConvFn.apply(xs, w2, bias, (1, 1), (0, 0), zero_bias_grad)
 
 
 class PairExpandFn(Function):
@@ -461,19 +471,22 @@ class PairExpandFn(Function):
         return dw
 
 
-def _conv5_via_pairs(x, w, bias):
+def _conv5_via_pairs(x, w, bias, zero_bias_grad=False):
     """(32 -> 32, KH x 5, pad 2) convolution as a (64 -> 64, KH x 3, pad 1) convolution over pixel pairs: the view
     [N,H,W/2,64] of x costs nothing, the weight is Toeplitz-expanded (1.2x the MACs), and the tcgen05 kernels run with
     N = 64 instead of 32 -- their tensor pipe is bound by the A-operand shared-memory read, i.e. proportional to N."""
     N, H, W, C = x.shape
     w2 = PairExpandFn.apply(w)
     b2 = None if bias is None else torch.cat([bias, bias])
-    y2 = ConvFn.apply(x.view(N, H, W // 2, 2 * C), w2, b2, (1, 1), (w.shape[2] // 2, 1))
+    y2 = ConvFn.apply(x.view(N, H, W // 2, 2 * C), w2, b2, (1, 1), (w.shape[2] // 2, 1), zero_bias_grad)
     return y2.view(N, H, W, w.shape[0])
 
 
-def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
+def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0), zero_bias_grad=False):
+    """zero_bias_grad: see ConvFn.forward (the output goes straight into a train-mode BatchNorm)."""
     stride, pad = tuple(stride), tuple(pad)
+    if zero_bias_grad and bias is not None:
+        return _conv_zb(x, w, bias, stride, pad)
     if (cfg.pair_merge and x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and stride == (1, 1)
             and w.dim() == 4 and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels
             and pad == (2, 2) and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0 and x.is_contiguous()):
@@ -493,6 +506,19 @@ def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0)):
         if k == (1, 1) and pad == (0, 0):
             return ConvFn.apply(x[:, ::2, ::2, :].contiguous(), w, bias, (1, 1), (0, 0))   # slicing = data movement
     return ConvFn.apply(x, w, bias, stride, pad)
+
+
+def _conv_zb(x, w, bias, stride, pad):
+    """conv() for a biased convolution in front of a train-mode BatchNorm: same dispatch, ConvFn told to skip the bias
+    gradient.  (Only the plain and the stride-2 forms occur in the model: GenResBlk.conv1, Postnet[0], sync-D front.)"""
+    if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0 \
+            and tuple(w.shape[2:]) == (3, 3) and pad == (1, 1):
+        return _conv3x3_s2_via_s2d(x, w, bias, True)
+    if (cfg.pair_merge and x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and stride == (1, 1) and w.dim() == 4
+            and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels and pad == (2, 2)
+            and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0 and x.is_contiguous()):
+        return _conv5_via_pairs(x, w, bias, True)
+    return ConvFn.apply(x, w, bias, stride, pad, True)
 
 
 def stem_conv(vid, w):
@@ -738,7 +764,7 @@ class RowTapsFn(Function):
         return (dy if ctx.needs_input_grad[0] else None), dR, None, None
 
 
-def conv_rowconst(x, nc, w, bias, pad):
+def conv_rowconst(x, nc, w, bias, pad, zero_bias_grad=False):
     """conv(x, w, bias, stride 1, pad) for x (B,F,T,C) whose first `nc` channels are constant along F: those channels
     go through ONE row (kh folded into the output channels of a 1 x KW conv) + the row-tap combine, the remaining
     channels through the ordinary conv.  Exact up to summation order; F/KH-fold fewer MACs on the constant part."""
@@ -747,7 +773,7 @@ def conv_rowconst(x, nc, w, bias, pad):
     rn = x[..., nc:].contiguous()
     w_rows = w[:, :nc].permute(2, 0, 1, 3).reshape(KH * Cout, nc, 1, KW)            # R[kh] = conv1d(row, w[:, :nc, kh, :])
     R = conv(rc, w_rows, None, (1, 1), (0, pad[1]))
-    yn = conv(rn, w[:, nc:].contiguous(), bias, (1, 1), pad)
+    yn = conv(rn, w[:, nc:].contiguous(), bias, (1, 1), pad, zero_bias_grad)
     return RowTapsFn.apply(yn, R, KH, pad[0])
 
 
@@ -976,6 +1002,21 @@ def _gemm_raw(A, B, C, bias=None, alpha=1.0, beta=0.0):
     lib().call("vca_gemm_simt", _dt(A), _dt(B), _dt(C), A, B, C, bias, Z, M, N, K, sa[0] if A.shape[0] > 1 else 0, sa[1], sa[2],
                sb[0] if B.shape[0] > 1 else 0, sb[1], sb[2], sc[0], sc[1], sc[2], float(alpha), float(beta))
     return C
+
+
+def bmm_tc_raw(a, b, M, N, K, a_mn=False, b_mn=False, out_dtype=torch.bfloat16, alpha=1.0, out=None):
+    """out[z] (M x N) = alpha * op(a[z]) op(b[z]) on the tcgen05 path (csrc/bmm_tc.cu).  a, b: bf16, 3-D, last dim
+    contiguous; a is (Z, M, K) or -- a_mn -- (Z, K, M); b is (Z, N, K) or -- b_mn -- (Z, K, N).  Row pitches and batch
+    strides are taken from the tensors (views with padded rows are fine), so ragged K / M / N just pass smaller extents."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 3 and b.dim() == 3
+    assert a.stride(2) == 1 and b.stride(2) == 1
+    Z = a.shape[0]
+    if out is None:
+        out = torch.empty((Z, M, N), dtype=out_dtype, device=a.device)
+    assert out.stride(2) == 1
+    lib().call("vca_bmm_tc", a, b, out, Z, M, N, K, 1 if a_mn else 0, 1 if b_mn else 0, a.stride(1), a.stride(0) if Z > 1 else 0,
+               b.stride(1), b.stride(0) if Z > 1 else 0, out.stride(1), out.stride(0), 1 if out.dtype == torch.float32 else 0, float(alpha))
+    return out
 
 
 class BmmFn(Function):

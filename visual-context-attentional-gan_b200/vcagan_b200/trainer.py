@@ -110,6 +110,8 @@ class Trainer:
         self.lrs = lrs
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
+        self.overlap_gru = True             # the sentence GRU runs on a side stream underneath the generator's first six blocks
+        self._gru_stream = None
         self.batched_pack = True            # one weight re-pack launch per optimizer step (ops.PackPlan) instead of ~75
         self._pack_g = self._pack_d = None  # built after the first step (the pack cache then lists what the step uses)
         self._branch_streams = None
@@ -291,16 +293,37 @@ class Trainer:
             return run
         early = self._fork([real_early(2), real_early(1), real_early(0)], [2, 0, 1])
         early = {2: early[0], 1: early[1], 0: early[2]}
-        phon, sent = v_front(vid)
+        phon = v_front.features(vid)
+        # The 2-layer bi-GRU is 4 x T strictly sequential steps on a few clusters (1.25 ms with most SMs idle); the
+        # generator's stem (decode x3 + g1 x3, the heaviest convolutions) needs only `phon`.  Run the GRU on its own
+        # stream underneath the stem; autograd replays its backward there too, underneath the stem's backward.
+        cur = torch.cuda.current_stream()
+        side = self.overlap_gru and self.parallel_branches
+        if side:
+            if self._gru_stream is None:
+                self._gru_stream = torch.cuda.Stream(device=self.device, priority=-1)
+            self._gru_stream.wait_stream(cur)
+            with torch.cuda.stream(self._gru_stream):
+                sent = v_front.sentence(phon)
+            self._br_used.append(self._gru_stream)
+        else:
+            sent = v_front.sentence(phon)
         if self.split_g_backward:
             # the generator sees detached leaves: its backward stops there (_phase_g) and the visual front-end's
             # backward is a second autograd call fed with their gradients (_phase_g2)
             assert self.merge_vfront_backward
-            phon_g, sent_g = phon.detach().requires_grad_(True), sent.detach().requires_grad_(True)
-            g = gen(sent_g, phon_g, vid_len)                               # g1, g2, g3
+            phon_g = phon.detach().requires_grad_(True)
+            h = gen.stem(phon_g)
+            if side:
+                cur.wait_stream(self._gru_stream)
+            sent_g = sent.detach().requires_grad_(True)
+            g = gen.tail(sent_g, h, vid_len)                               # g1, g2, g3
         else:
             phon_g = sent_g = None
-            g = gen(sent, phon, vid_len)
+            h = gen.stem(phon)
+            if side:
+                cur.wait_stream(self._gru_stream)
+            g = gen.tail(sent, h, vid_len)
         gen.fixed_noise = None
         assert phon.size(1) == T
         sdet = sent.detach()
@@ -357,6 +380,8 @@ class Trainer:
         recon = (ops.l1_mean(g[0], st["mel1"], k) + ops.l1_mean(g[1], st["mel2"], k) + ops.l1_mean(g[2], st["mel"], k)) / 3 \
             + ops.l1_mean(gs, st["spec"])
         gen_loss = g_adv + g_sync + 50.0 * recon
+        if self._gru_stream is not None and not self.split_g_backward:
+            self._br_used.append(self._gru_stream)       # the GRU's backward kernels will run there: join it afterwards
         # D weight grads are skipped (the reference computes and discards them, train.py:235-236)
         if self.split_g_backward:
             torch.autograd.backward([gen_loss], inputs=self._genpost_params + [st["phon_g"], st["sent_g"]])
@@ -373,6 +398,8 @@ class Trainer:
         """Second half of a split G backward: the visual front-end, fed with d(gen_loss)/d(phon, sent) from the
         generator's leaves and d(dis_loss)/d(phon) from the D phase (autograd sums the two roots on phon)."""
         st = self._st
+        if self._gru_stream is not None:
+            self._br_used.append(self._gru_stream)
         torch.autograd.backward([st["phon"], st["phon"], st["sent"]],
                                 [st["phon_g"].grad, st["phon_leaf"].grad, st["sent_g"].grad], inputs=self._vf_params)
         self._join_branches()
