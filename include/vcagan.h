@@ -110,6 +110,14 @@ int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF,
  * lda / ldb / strideA / strideB in elements, multiples of 8. */
 int vca_bmm_tc(const void* A, const void* B, void* C, int Z, int M, int N, int K, int a_mn, int b_mn, long long lda, long long strideA, long long ldb, long long strideB, long long ldc, long long strideC, int out_f32, float alpha, cudaStream_t stream);
 
+/* ---- visual-context attention (generator.py:154-171): QK^T -> key mask -> softmax -> PV in one tcgen05 kernel ------------
+ * Q [B][Tq][256], K, V [B][S][256] bf16 contiguous, S <= 256; lens int32 [B] (keys >= lens[b] are masked);
+ * O [B][Tq][256] bf16; P [B][Tq][SP] bf16, SP = S rounded up to 16 (the softmax, saved for backward). */
+int vca_att_tc_supported(int S, int d);
+int vca_att_fwd_tc(const void* Q, const void* K, const void* V, const int* lens, void* O, void* P, int B, int Tq, int S, float scale, cudaStream_t stream);
+/* dS = scale * P o (dP - rowsum(dP o P)); P bf16, dP fp32, dS bf16, all [rows][SP]; columns >= S written as 0 */
+int vca_att_softmax_bwd(const void* P, const float* dP, void* dS, long long rows, int S, int SP, float scale, cudaStream_t stream);
+
 /* ---- GRU gates (visual_front.py:20,33-34), attention softmax (generator.py:161-164), sync losses
  *      (generator.py:347-359), gan_loss (generator.py:363-366), L1 (train.py:226-229), Adam (train.py:82-83) - */
 int vca_gru_gate_fwd(const float* gi, const float* gh, const float* bhh, const float* hprev, float* hnext, float* out, float* gates, int ndir, int T, int B, int H, int step, cudaStream_t stream);

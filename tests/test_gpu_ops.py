@@ -562,3 +562,41 @@ def test_bmm_tc(V, case):
     e = rel_l2(out.float().cpu(), ref.cpu())
     print("bmm_tc", case, e)
     assert e < (1e-5 if f32 else 5e-3), (case, e)
+
+
+@pytest.mark.parametrize("Tq,S,lens", [(75, 75, [75, 41, 1]), (150, 75, [75, 60, 13]), (250, 250, [250, 173, 128]), (500, 250, [250, 129, 64]),
+                                       (20, 20, [20, 13, 7])])
+def test_attention_tc(V, Tq, S, lens):
+    """Fused visual-context attention (generator.py:154-171) on tcgen05: forward and all three input gradients vs fp32 torch
+    on the same bf16 inputs, at the GRID (75 keys; 75 / 150 queries) and LRS (250 keys; 250 / 500 queries) shapes with
+    ragged key masks.  Tolerance: 1e-2 relative L2 (P and dS are rounded to bf16 for the second contraction; bf16 eps =
+    3.9e-3) -- the fp32-reference tolerance of the bf16 path, as for the convolutions.  Masked keys must not matter."""
+    B, Dm = len(lens), 256
+    g = torch.Generator().manual_seed(Tq + S)
+    q = (torch.randn(B, Tq, Dm, generator=g) * 0.7).bfloat16()
+    k = (torch.randn(B, S, Dm, generator=g) * 0.7).bfloat16()
+    v = torch.randn(B, S, Dm, generator=g).bfloat16()
+    do = torch.randn(B, Tq, Dm, generator=g).bfloat16()
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+    att = torch.bmm(qr, kr.transpose(1, 2)) / 16.0
+    for i, n in enumerate(lens):
+        att[i, :, n:] = float("-inf")
+    ref = torch.bmm(torch.softmax(att, 2), vr)
+    ref.backward(do.float())
+    qd, kd, vd = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    ld = torch.tensor(lens, dtype=torch.int32).cuda()
+    assert V.ops.attention_supported(qd, kd)
+    out = V.ops.attention(qd, kd, vd, ld, 1.0 / 16.0)
+    out.backward(do.cuda())
+    torch.cuda.synchronize()
+    e = dict(o=rel_l2(out.float().cpu(), ref), dq=rel_l2(qd.grad.float().cpu(), qr.grad), dk=rel_l2(kd.grad.float().cpu(), kr.grad),
+             dv=rel_l2(vd.grad.float().cpu(), vr.grad))
+    print("attention", Tq, S, lens, e)
+    assert max(e.values()) < 1e-2, e
+    for i, n in enumerate(lens):            # gradients of masked keys are exactly zero
+        assert float(kd.grad[i, n:].abs().max() if n < S else 0.0) == 0.0 and float(vd.grad[i, n:].abs().max() if n < S else 0.0) == 0.0
+    k2 = kd.detach().clone(); v2 = vd.detach().clone()
+    for i, n in enumerate(lens):
+        k2[i, n:] = 7.0; v2[i, n:] = -3.0
+    out2 = V.ops.attention(qd.detach(), k2, v2, ld, 1.0 / 16.0)
+    assert torch.equal(out2, out.detach())

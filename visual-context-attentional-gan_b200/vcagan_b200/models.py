@@ -307,10 +307,16 @@ class AVAttention(nn.Module):
         lens = _lens_tensor(len, g.device)
         f32 = torch.float32
         ph = ops.cast(ph, cfg.dtype)                                         # projections run in the compute dtype
-        k = ops.cast(ops.linear(ph, self.k.weight, self.k.bias), f32)        # (B,S,256)
-        v = ops.cast(ops.linear(ph, self.v.weight, self.v.bias), f32)
+        k = ops.linear(ph, self.k.weight, self.k.bias)                       # (B,S,256)
+        v = ops.linear(ph, self.v.weight, self.v.bias)
         gq = g.permute(0, 2, 3, 1).reshape(B, T, C * Fq)                     # index c*F+f as in g.view(B,C*F,T)
-        q = ops.cast(ops.linear(gq, self.q.weight, self.q.bias), f32)        # (B,T,256)
+        q = ops.linear(gq, self.q.weight, self.q.bias)                       # (B,T,256)
+        if ops.attention_supported(q, k):
+            # bf16 mode: QK^T -> key mask -> softmax -> PV in one tcgen05 kernel (scores / softmax in fp32 on chip)
+            val = ops.attention(q, k, v, lens, 1.0 / math.sqrt(self.out_dim))
+            out = ops.linear(val, self.mel.weight, self.mel.bias)            # (B,T,1280)
+            return out.view(B, T, Fq, -1).permute(0, 2, 1, 3).contiguous()   # channels-last (B,F,T,C')
+        q, k, v = ops.cast(q, f32), ops.cast(k, f32), ops.cast(v, f32)
         att = ops.bmm(q, k.transpose(1, 2), 1.0 / math.sqrt(self.out_dim))   # (B,T,S)  scores/softmax in fp32
         att = ops.masked_softmax(att, lens)
         val = ops.bmm(att, v)                                                # (B,T,256)

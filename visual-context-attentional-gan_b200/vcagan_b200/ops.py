@@ -1041,6 +1041,51 @@ def bmm(a, b, alpha=1.0):
     return BmmFn.apply(a, b, float(alpha))
 
 
+class AttentionFn(Function):
+    """O = softmax_keys(Q K^T * scale, keys >= lens masked) V on the tcgen05 path (csrc/att_tc.cu): q (B,Tq,256),
+    k, v (B,S,256) bf16, lens int32 (B,) -> (B,Tq,256) bf16.  Forward is ONE kernel (scores and O never leave TMEM / the
+    probabilities go to shared memory as the second MMA's operand); the backward's four contractions run on the batched
+    tcgen05 GEMM (csrc/bmm_tc.cu) around one row-wise softmax-gradient kernel."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, lens, scale):
+        q, k, v = _c(q), _c(k), _c(v)
+        B, Tq, Dm = q.shape
+        S = k.shape[1]
+        SP = (S + 15) // 16 * 16
+        o = torch.empty((B, Tq, Dm), dtype=torch.bfloat16, device=q.device)
+        p = torch.empty((B, Tq, SP), dtype=torch.bfloat16, device=q.device)
+        lib().call("vca_att_fwd_tc", q, k, v, lens, o, p, B, Tq, S, float(scale))
+        ctx.save_for_backward(q, k, v, p)
+        ctx.scale = float(scale)
+        return o
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        q, k, v, p = ctx.saved_tensors
+        do = _c(do)
+        B, Tq, Dm = q.shape
+        S, SP = k.shape[1], p.shape[2]
+        dp = torch.empty((B, Tq, SP), dtype=torch.float32, device=q.device)
+        bmm_tc_raw(do, v, Tq, S, Dm, False, False, out=dp)                         # dP = dO V^T
+        ds = torch.empty((B, Tq, SP), dtype=torch.bfloat16, device=q.device)
+        lib().call("vca_att_softmax_bwd", p, dp, ds, B * Tq, S, SP, ctx.scale)      # dS = scale * P o (dP - <dP, P>)
+        dq = bmm_tc_raw(ds, k, Tq, Dm, S, False, True) if ctx.needs_input_grad[0] else None      # dS K
+        dk = bmm_tc_raw(ds, q, S, Dm, Tq, True, True) if ctx.needs_input_grad[1] else None       # dS^T Q
+        dv = bmm_tc_raw(p, do, S, Dm, Tq, True, True) if ctx.needs_input_grad[2] else None       # P^T dO
+        return dq, dk, dv, None, None
+
+
+def attention_supported(q, k) -> bool:
+    return (cfg.use_tc and q.dtype == torch.bfloat16 and k.dtype == torch.bfloat16
+            and lib().query("vca_att_tc_supported", int(k.shape[1]), int(q.shape[2])) == 1)
+
+
+def attention(q, k, v, lens, scale):
+    return AttentionFn.apply(q, k, v, lens, float(scale))
+
+
 class MaskedSoftmaxFn(Function):
     """softmax over the last dim of (Z,R,S) with keys >= lens[z] masked out (generator.py:161-164)."""
 
