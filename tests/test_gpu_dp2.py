@@ -1,0 +1,57 @@
+"""Multi-GPU correctness on real GPUs: the gradients a 2-rank data-parallel step ends up with
+(NCCL sum all-reduce of the flat buffers, 1/world folded into Adam) must equal the mean of the gradients of two
+SINGLE-GPU steps, one per shard -- BatchNorm statistics are per replica in the reference's nn.DataParallel and here, so
+per-shard execution is the exact oracle.  Also: a replica constructed with different weights is overwritten by rank 0's
+at Trainer start-up, and the replicas are bit-identical after the step.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from conftest import make_state, rel_l2, GOLD, ROOT
+from oracle import vca_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import dp2_worker as W
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(ROOT, "tests", "dp2_worker.py"), str(tmp_path), precision]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ranks = [torch.load(os.path.join(tmp_path, f"rank{i}.pt")) for i in range(2)]
+    assert ranks[0]["in_sync"] and ranks[1]["in_sync"]
+    assert ranks[0]["Gw"] == ranks[1]["Gw"] and ranks[0]["Dw"] == ranks[1]["Dw"]          # bit-identical replicas after the step
+    assert torch.equal(ranks[0]["G"], ranks[1]["G"]) and torch.equal(ranks[0]["D"], ranks[1]["D"])
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    try:
+        singles = []
+        for shard in range(2):
+            state = {m: make_state(spec, m) for m in O.MODULES}
+            tr = Trainer(precision=precision, state=state, dropout=False)
+            vid, mel, sp, noise, lens = W.shard_inputs(shard)
+            out = tr.step(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise=noise)
+            torch.cuda.synchronize()
+            singles.append((W.sample(tr.G.grad), W.sample(tr.D.grad), {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
+            del tr
+        for i in range(2):      # each rank's losses are its own shard's losses
+            for k, v in singles[i][2].items():
+                assert abs(ranks[i]["losses"][k] - v) <= (1e-5 if precision == "fp32" else 2e-2) * max(1.0, abs(v)), (i, k)
+        tol = 2e-5 if precision == "fp32" else 2e-2      # bf16: split-K / wgrad atomics are not bit-reproducible run to run
+        for key, j in (("G", 0), ("D", 1)):
+            want = (singles[0][j] + singles[1][j]) / 2.0
+            got = ranks[0][key] / 2.0
+            e = rel_l2(got, want)
+            print(f"{precision}: 2-rank all-reduced {key} gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
+            assert e < tol, (key, e)
+    finally:
+        V.set_precision("fp32")
