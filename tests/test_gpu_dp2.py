@@ -34,24 +34,39 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
     assert torch.equal(ranks[0]["G"], ranks[1]["G"]) and torch.equal(ranks[0]["D"], ranks[1]["D"])
     spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
     try:
-        singles = []
+        # The per-shard oracle: two single-GPU trainers, one per shard.  The D phase (forward, D losses, D backward) of a
+        # shard depends on nothing outside the shard.  The G phase runs against the discriminators UPDATED with the
+        # rank-averaged D gradient (train.py:211 precedes :217), so the oracle hands both trainers the mean of their D
+        # gradients before their G phase -- which is all the all-reduce does.
+        trs, outs = [], []
         for shard in range(2):
             state = {m: make_state(spec, m) for m in O.MODULES}
             tr = Trainer(precision=precision, state=state, dropout=False)
             vid, mel, sp, noise, lens = W.shard_inputs(shard)
-            out = tr.step(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise=noise)
-            torch.cuda.synchronize()
-            singles.append((W.sample(tr.G.grad), W.sample(tr.D.grad), {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
-            del tr
+            tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)
+            trs.append(tr)
+        torch.cuda.synchronize()
+        d_mean = (trs[0].D.grad + trs[1].D.grad) / 2.0
+        e = rel_l2(W.sample(d_mean), ranks[0]["D"] / 2.0)
+        print(f"{precision}: 2-rank all-reduced D gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
+        tol = 2e-5 if precision == "fp32" else 5e-2      # bf16: split-K / wgrad atomics are not bit-reproducible run to run
+        assert e < tol, e
+        for tr in trs:
+            tr.D.grad.copy_(d_mean)
+            tr._phase_g()
+            outs.append(tr._phase_end())
+        torch.cuda.synchronize()
         for i in range(2):      # each rank's losses are its own shard's losses
-            for k, v in singles[i][2].items():
-                assert abs(ranks[i]["losses"][k] - v) <= (1e-5 if precision == "fp32" else 2e-2) * max(1.0, abs(v)), (i, k)
-        tol = 2e-5 if precision == "fp32" else 2e-2      # bf16: split-K / wgrad atomics are not bit-reproducible run to run
-        for key, j in (("G", 0), ("D", 1)):
-            want = (singles[0][j] + singles[1][j]) / 2.0
-            got = ranks[0][key] / 2.0
-            e = rel_l2(got, want)
-            print(f"{precision}: 2-rank all-reduced {key} gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
-            assert e < tol, (key, e)
+            for k, v in outs[i].items():
+                if torch.is_tensor(v) and v.numel() == 1:
+                    assert abs(ranks[i]["losses"][k] - float(v)) <= (2e-5 if precision == "fp32" else 3e-2) * max(1.0, abs(float(v))), (i, k)
+        g_mean = (trs[0].G.grad + trs[1].G.grad) / 2.0
+        e = rel_l2(W.sample(g_mean), ranks[0]["G"] / 2.0)
+        print(f"{precision}: 2-rank all-reduced G gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
+        assert e < tol, e
+        # ... and therefore the same weights after the step (both single-GPU oracles applied g_mean? no: each applied its own
+        # shard's G gradient -- only the D weights are comparable)
+        if precision == "fp32":
+            assert abs(float(trs[0].D.flat.double().sum()) - ranks[0]["Dw"]) <= 1e-6 * abs(ranks[0]["Dw"]) + 1e-3
     finally:
         V.set_precision("fp32")
