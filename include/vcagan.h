@@ -62,6 +62,9 @@ int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* d
  * forward, 1 = dgrad); partial sums are red.add-ed into it and a finishing pass adds the bias and writes bf16. */
 int vca_conv_tc_workspace(const ConvGeom* g, int kind);
 int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, float* ws, long long ws_bytes, cudaStream_t stream);
+/* forward conv that also ADDS the per-output-channel sum / sum of squares of y (as stored) into stats[0..Cout) / stats[Cout..2Cout)
+   (fp64): the batch statistics of a BatchNorm that follows (generator.py:115-116, resnet.py:47-48); never split-K */
+int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t stream);
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);
 
@@ -75,6 +78,9 @@ int vca_gemm_simt(int dtA, int dtB, int dtC, const void* A, const void* B, void*
 /* sums_prezeroed / flags bit 0: `sums` is a persistent scratch that is zero on entry and left zeroed (no memset launch);
  * flags bit 1 of vca_bn_act_bwd: dgamma / dbeta / dprelu are added to in place (gradient accumulation). */
 int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float momentum, double* sums, int sums_prezeroed, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
+/* mean / invstd / running-buffer update from statistics a producer kernel accumulated; sums = double[2*C*fold] ([fold][C] sums,
+   [fold][C] sums of squares), left zeroed */
+int vca_bn_finalize_stats(double* sums, long long R, int C, int fold, float eps, float momentum, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
 int vca_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t stream);
 int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, cudaStream_t stream);
 int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags, cudaStream_t stream);

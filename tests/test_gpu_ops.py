@@ -600,3 +600,48 @@ def test_attention_tc(V, Tq, S, lens):
         k2[i, n:] = 7.0; v2[i, n:] = -3.0
     out2 = V.ops.attention(qd.detach(), k2, v2, ld, 1.0 / 16.0)
     assert torch.equal(out2, out.detach())
+
+
+@pytest.mark.parametrize("case", [
+    # N, Cin, H, W, Cout, k, pad, stride, hs_mode
+    (3, 128, 20, 25, 256, 3, 1, 1, 1),    # streaming kernel, two... BN = 256 tile
+    (2, 64, 40, 46, 64, 5, 2, 1, 1),      # weights-stationary persistent kernel, several tiles per CTA
+    (4, 128, 14, 14, 128, 3, 1, 1, 2),    # halo-resident / streamed-weights kernel (forced)
+    (2, 32, 24, 50, 32, 5, 2, 1, 1),      # pixel-pair merged: statistics arrive as two column groups per channel
+    (3, 64, 28, 28, 128, 3, 1, 2, 1),     # stride 2 via space-to-depth
+    (2, 320, 9, 11, 200, 3, 1, 1, 1),     # ragged: Cout not a multiple of 16 x tile, partial last K chunk
+])
+def test_bn_stats_from_conv_epilogue(V, case):
+    """Train-mode BatchNorm whose batch statistics come out of the producing convolution's epilogue
+    (vca_conv_fwd_tc_stats + vca_bn_finalize_stats) must match the separate statistics pass over the stored tensor:
+    same normalised output (<= 2e-3 relative: one is bf16-rounded after fp32 statistics of identical values), same
+    running buffers (<= 1e-5), and the scratch accumulators are left zeroed."""
+    N, Cin, H, W, Cout, k, p, st, hs = case
+    assert V.lib().cdll.vca_set_option(b"hs_mode", hs) == 0
+    g = torch.Generator().manual_seed(sum(case))
+    x = cl((torch.randn(N, Cin, H, W, generator=g) + 0.3).bfloat16()).cuda()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / math.sqrt(Cin * k * k)).cuda()
+    b = torch.randn(Cout, generator=g).cuda()
+    V.set_precision("bf16")
+    try:
+        outs = []
+        for fused in (False, True):
+            V.ops.cfg.fuse_bn_stats = fused
+            bn = torch.nn.BatchNorm2d(Cout).cuda().train()
+            ga = torch.Generator().manual_seed(7)     # same affine for both runs
+            with torch.no_grad():
+                bn.weight.copy_(torch.rand(Cout, generator=ga) + 0.5); bn.bias.copy_(torch.randn(Cout, generator=ga))
+            y = V.ops.conv(x, w, b, (st, st), (p, p), zero_bias_grad=True, bn=bn)
+            assert hasattr(y, "_vca_bn_sums") == fused, (fused, case)
+            z = V.ops.bn_act(y, bn, V.ops.ACT_LRELU, 0.2)
+            torch.cuda.synchronize()
+            outs.append((z.float().cpu(), bn.running_mean.clone().cpu(), bn.running_var.clone().cpu(), bn))
+        (z0, m0, v0, _), (z1, m1, v1, bn1) = outs
+        assert rel_l2(z1, z0) < 2e-3, rel_l2(z1, z0)
+        assert rel_l2(m1, m0) < 1e-5 and rel_l2(v1, v0) < 1e-5, (rel_l2(m1, m0), rel_l2(v1, v0))
+        for key, t in V.ops._bn_scratch.items():
+            assert float(t.abs().max()) == 0.0, key
+    finally:
+        V.ops.cfg.fuse_bn_stats = True
+        V.set_precision("fp32")
+        V.lib().cdll.vca_set_option(b"hs_mode", 1)

@@ -117,6 +117,30 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, long long R, int C
   }
 }
 
+// Statistics that arrive as `fold` groups of C accumulators each (a pixel-pair merged convolution writes its output as
+// [.., pair position, C]: every channel has `fold` columns): sums = [fold][C] sums, then [fold][C] sums of squares.
+__global__ void bn_finalize_fold_kernel(double* __restrict__ sums, long long R, int C, int fold, float eps, float momentum,
+                                        float* __restrict__ mean, float* __restrict__ invstd, float* __restrict__ running_mean,
+                                        float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = 0, s2 = 0;
+  for (int f = 0; f < fold; ++f) {
+    s1 += sums[f * C + c]; s2 += sums[(fold + f) * C + c];
+    sums[f * C + c] = 0; sums[(fold + f) * C + c] = 0;       // persistent scratch: left zeroed for the next call
+  }
+  double m = s1 / (double)R;
+  double var = s2 / (double)R - m * m;
+  if (var < 0) var = 0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)eps));
+  if (running_mean) {
+    double unb = R > 1 ? var * (double)R / (double)(R - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)m;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+  }
+}
+
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -390,6 +414,16 @@ int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float 
   else launch_stats<Vec<bf16>>(x, R, C, sums, s);
   VCA_LAUNCH_CHECK();
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, eps, momentum, mean, invstd, running_mean, running_var, sums_prezeroed);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// Batch statistics that a producer kernel already accumulated (vca_conv_fwd_tc_stats): sums = double[2 * C * fold], laid
+// out [fold][C] sums then [fold][C] sums of squares, R = rows per channel (all folds together).  Computes mean / invstd,
+// updates the running buffers like vca_bn_stats and leaves `sums` zeroed.
+int vca_bn_finalize_stats(double* sums, long long R, int C, int fold, float eps, float momentum, float* mean, float* invstd,
+                          float* running_mean, float* running_var, cudaStream_t s) {
+  VCA_CHECK_ARG(sums && mean && invstd && R > 0 && C > 0 && fold >= 1);
+  bn_finalize_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, fold, eps, momentum, mean, invstd, running_mean, running_var);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

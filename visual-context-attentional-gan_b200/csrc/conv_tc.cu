@@ -16,15 +16,16 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
 // (TMEM lane quarter = warp_id % 4).  Descriptor encodings follow the PTX ISA "tcgen05 shared memory descriptor"
 // / "instruction descriptor" tables.
-#include "common.cuh"
-#include <cuda.h>
+#include "tc_common.cuh"
+
+using namespace tc;
 
 // conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s);
 // conv_tc_hs.cu: halo-resident activations + streamed weights for 64..128 output channels (same return convention)
 int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s);
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s);
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
 
@@ -33,95 +34,6 @@ namespace {
 constexpr int KC = 64;              // bf16 channels per K chunk = 128 B = one SWIZZLE_128B row
 constexpr int TILE_ROWS = 128;      // UMMA M
 constexpr int A_STAGE_BYTES = TILE_ROWS * 128;
-constexpr uint32_t SPIN_LIMIT = 1u << 24;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0, ok = 0;
-  const uint32_t addr = smem_u32(bar);
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) break;
-    if (++spins > SPIN_LIMIT) __trap();  // a lost arrival must fail loudly, never hang the GPU
-  }
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// Shared-memory matrix descriptor (SM100 "version 1"), SWIZZLE_128B.
-//   bits [0,14)  start address >> 4        bits [16,30) leading-dim byte offset >> 4
-//   bits [32,46) stride-dim byte offset >> 4   bits [46,48) version = 1   bits [61,64) layout type (2 = SW128)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-// Instruction descriptor, kind::f16: D = f32 (bits 4-5 = 1), A = B = bf16 (bits 7-9, 10-12 = 1),
-// a_major bit 15, b_major bit 16 (0 = K-major, 1 = MN-major), N>>3 at bits [17,23), M>>4 at bits [24,29).
-__host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16) | ((uint32_t)(N >> 3) << 17) |
-         ((uint32_t)(M >> 4) << 24);
-}
 
 struct FwdParams {
   int NF, OH, OW, Cout;          // output tensor [NF, OH, OW, Cout]
@@ -139,6 +51,7 @@ struct FwdParams {
   int splits, taps_per_split;    // split-K over the filter taps: blockIdx.z takes taps [z*per, (z+1)*per)
   float* ws;                     // split-K only: fp32 [pixels][Cout] partial sums (red.add), finished by splitk_finish_kernel
   const float* bias;             // [Cout] or null
+  double* stats;                 // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
   bf16* y;
 };
 
@@ -154,6 +67,9 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   uint64_t* empty = full + S;
   uint64_t* accum_bar = empty + S;
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
+  float* s_sum = (float*)(tmem_slot + 2);   // [BN] + [BN]: per-channel sum / sum of squares of this tile (BatchNorm statistics)
+  float* s_sq = s_sum + p.BN;
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates
@@ -259,15 +175,16 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
             if (co0 + c + i < p.Cout) atomicAdd(wrow + c + i, v[i]);
         }
       }
-    } else
+    } else {
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (row_ok && co0 + c < p.Cout) {
-        if (p.bias) {
+      if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
-        }
+        for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
+      }
+      if (p.stats) epi_stats16(v, row_ok, co0 + c, p.Cout, s_sum + c, s_sq + c, lane);
+      if (row_ok && co0 + c < p.Cout) {
         if (co0 + c + 16 <= p.Cout) {
           uint4 o0, o1;
           __nv_bfloat162 h;
@@ -281,6 +198,8 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
           for (int i = 0; i < 16 && co0 + c + i < p.Cout; ++i) yrow[c + i] = __float2bfloat16_rn(v[i]);
         }
       }
+    }
+    if (p.stats) epi_stats_flush(s_sum, s_sq, p.BN, co0, p.Cout, p.stats, (int)threadIdx.x - 64);
     }
   }
   tc_fence_before();
@@ -437,39 +356,6 @@ __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constan
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// bf16 tensor map with a 64-channel (128 B) inner box, SWIZZLE_128B, zero OOB fill.
-// dims/box are innermost-first; rank 3 or 4.
-int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { vca_set_error("cuTensorMapEncodeTiled entry point unavailable"); return VCA_ERR_CUDA; }
-  cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
-  long long stride = 2;
-  for (int i = 0; i < rank; ++i) {
-    gd[i] = (cuuint64_t)dims[i]; bx[i] = (cuuint32_t)box[i]; es[i] = 1;
-    if (i > 0) gs[i - 1] = (cuuint64_t)stride;
-    stride *= dims[i];
-  }
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { vca_set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return VCA_ERR_CUDA; }
-  return VCA_OK;
-}
-
 // choose the pixel box (tn, th, tw), tn*th*tw <= 128, that minimises the number of tiles
 void choose_box(int NF, int H, int W, int& tn, int& th, int& tw, int max_th = 1 << 30) {
   long long best = -1; tn = th = tw = 1;
@@ -481,7 +367,6 @@ void choose_box(int NF, int H, int W, int& tn, int& th, int& tw, int max_th = 1 
     }
   }
 }
-uint32_t pow2_cols(int n) { uint32_t c = 32; while ((int)c < n) c <<= 1; return c; }
 
 // Split-K plan of the streaming kernel for small-grid, long-K problems (the 5x5 heads of the discriminators on 5x18
 // maps: 32 CTAs x 200 stages): number of K splits (1 = none) for a grid of `ctas` CTAs and `taps` filter taps.
@@ -495,11 +380,11 @@ int plan_splits(long long ctas, int taps) {
 
 int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
              const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s, float* ws = nullptr,
-             size_t ws_bytes = 0, size_t* ws_need = nullptr) {
+             size_t ws_bytes = 0, size_t* ws_need = nullptr, double* stats = nullptr) {
   if (ws_need) *ws_need = 0;
   if (!ws_need) {
-    int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
-    if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, s);
+    int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, s);
+    if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, s);
     if (r != 0) return r < 0 ? r : VCA_OK;
   }
   FwdParams p;
@@ -525,7 +410,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   p.a_bytes = (uint32_t)(p.tn * p.th * p.tw) * 128u;
   p.b_bytes = (uint32_t)bn * 128u;
   p.tmem_cols = pow2_cols(bn);
-  p.bias = bias; p.y = (bf16*)y;
+  p.bias = bias; p.y = (bf16*)y; p.stats = stats;
   const size_t stage_bytes = A_STAGE_BYTES + (size_t)bn * 128;
   // Two CTAs per SM (100 KB each) hide each other's TMA latency on big grids.  A grid that cannot even fill the SMs
   // once (small feature maps of the discriminator heads) gets one deep pipeline per CTA instead: a stage is only
@@ -544,7 +429,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   const int max_stages = total_ctas <= vca_num_sms() ? 12 : 6;
   if (stages > max_stages) stages = max_stages; if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 256;
+  const size_t smem = stages * stage_bytes + 1024 + 256 + 2048;   // alignment + barriers + BatchNorm statistic accumulators
 
   CUtensorMap tmA, tmB;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.tw, p.th, p.tn};
@@ -559,6 +444,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
     attr_set = true;
   }
   if (p.ws) {
+    if (stats) { vca_set_error("conv forward: BatchNorm statistics are not available on the split-K path"); return VCA_ERR_UNSUPPORTED; }
     p.bias = nullptr;   // added by the finishing pass
     if (cudaMemsetAsync(ws, 0, need, s) != cudaSuccess) { vca_set_error("split-K workspace memset failed"); return VCA_ERR_CUDA; }
   }
@@ -613,6 +499,14 @@ int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const f
 }
 int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t s) {
   return vca_conv_fwd_tc_ws(g, x, wd, bias, y, nullptr, 0, s);
+}
+// Forward convolution that also accumulates the per-output-channel sum and sum of squares of y (as stored, i.e. bf16
+// rounded) into stats[0 .. Cout) and stats[Cout .. 2 Cout) (fp64, ADDED to): the batch statistics of a BatchNorm that
+// follows (vca_bn_finalize_stats turns them into mean / invstd).  Never runs split-K.
+int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t s) {
+  VCA_CHECK_ARG(g && x && wd && y && stats && vca_conv_tc_supported(g, 0));
+  return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, bias, y, s, nullptr, 0, nullptr,
+                  stats);
 }
 // dy [N,OH,OW,Cout] bf16; wf = packed [taps][Cin][Cout] bf16 (vca_pack_conv_weight "wf"); dx [N,IH,IW,Cin] bf16.
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t s) {

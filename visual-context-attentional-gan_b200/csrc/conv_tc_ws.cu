@@ -39,6 +39,7 @@ struct WsParams {
   uint32_t a_stage_bytes, a_tx_bytes, w_bytes, tmem_cols;
   int base_off_mode;
   const float* bias;
+  double* stats;           // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
   bf16* y;
 };
 
@@ -57,6 +58,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
   uint64_t* t_empty = t_full + 2;   // [2]
   uint32_t* tmem_slot = (uint32_t*)(t_empty + 2);
   uint32_t* s_arel = tmem_slot + 4;   // [taps <= 256] per-tap row shift of the A window, in 16-byte units
+  float* s_sum = (float*)(s_arel + 256);   // [BN] + [BN]: BatchNorm statistics of the current tile
+  float* s_sq = s_sum + p.BN;
+  if (p.stats) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.BN;
@@ -169,11 +173,12 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       for (int c = 0; c < p.BN; c += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
-        if (row_ok && co0 + c < p.Cout) {
-          if (p.bias) {
+        if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
-          }
+          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
+        }
+        if (p.stats) epi_stats16(v, row_ok, co0 + c, p.Cout, s_sum + c, s_sq + c, lane);
+        if (row_ok && co0 + c < p.Cout) {
           if (co0 + c + 16 <= p.Cout) {
             uint32_t w[8];
 #pragma unroll
@@ -188,6 +193,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&t_empty[acc]);
+      if (p.stats) epi_stats_flush(s_sum, s_sq, p.BN, co0, p.Cout, p.stats, (int)threadIdx.x - 64);
     }
   }
   tc_fence_before();
@@ -213,7 +219,7 @@ void choose_ws_tile(int H, int W, int KH, int KW, int& th, int& tw) {
 // Tries the weights-stationary kernel.  Returns 1 if it was launched, 0 if the geometry does not fit (caller uses the
 // streaming kernel), negative on error.  Arguments as conv_tc.cu::fwd_like.
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                    const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s) {
+                    const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s) {
   if (g_ws_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
   if (taps < 2 || taps > 256 || kchunks > 2 || KW > 64) return 0;
@@ -249,8 +255,8 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   p.sa = sa;
   p.tmem_cols = pow2_cols(2 * bn);
   p.base_off_mode = g_ws_base_off;
-  p.bias = bias; p.y = (bf16*)y;
-  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 2048;   // + alignment + barriers/tables
+  p.bias = bias; p.y = (bf16*)y; p.stats = stats;
+  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics
 
   CUtensorMap tmA, tmB;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.P, p.th + KH - 1, 1};

@@ -102,6 +102,47 @@ __host__ __device__ inline uint32_t make_idesc(int M, int N, int a_mn, int b_mn)
          ((uint32_t)(M >> 4) << 24);
 }
 
+// ---- BatchNorm batch statistics fused into the convolution epilogues ---------------------------------------------------
+// The conv kernels' epilogue threads hold one output pixel (tile row) per thread and 16 output channels at a time.  The
+// per-channel sum and sum of squares over the tile's rows are taken with a butterfly of warp shuffles (16 shuffles per
+// 16-column chunk and quantity instead of 16 x 5), added into shared accumulators (4 epilogue warps), and flushed with
+// one fp64 atomic per channel and tile into the BatchNorm's [2 * Cout] scratch -- the buffer bn_finalize_kernel reads.
+// Statistics are taken of the bf16-ROUNDED values, i.e. of exactly the tensor the normalisation pass will read.
+__device__ __forceinline__ float bf16_round(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
+// after the call, a[0] of lane L is the sum over all 32 lanes of column epi_col(L) (lanes 2k and 2k+1 hold the same column)
+__device__ __forceinline__ int epi_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ float colsum16(float (&a)[16], int lane) {
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float send = b4 ? a[i] : a[i + 8], keep = b4 ? a[i + 8] : a[i]; a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16); }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { const float send = b3 ? a[i] : a[i + 4], keep = b3 ? a[i + 4] : a[i]; a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8); }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { const float send = b2 ? a[i] : a[i + 2], keep = b2 ? a[i + 2] : a[i]; a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4); }
+  { const float send = b1 ? a[0] : a[1], keep = b1 ? a[1] : a[0]; a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2); }
+  a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+  return a[0];
+}
+// v: the 16 (bias-added) outputs of this thread's row for channels [co, co+16); s_sum / s_sq point at the chunk's 16 slots.
+// Must be called by all 32 lanes of the warp (rows that do not exist pass row_ok = false).
+__device__ __forceinline__ void epi_stats16(const float (&v)[16], bool row_ok, int co, int Cout, float* s_sum, float* s_sq, int lane) {
+  float a[16], b[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const float r = row_ok ? bf16_round(v[i]) : 0.f; a[i] = r; b[i] = r * r; }
+  const float sa = colsum16(a, lane), sb = colsum16(b, lane);
+  const int col = epi_col(lane);
+  if (!(lane & 1) && co + col < Cout) { atomicAdd(s_sum + col, sa); atomicAdd(s_sq + col, sb); }
+}
+// All 128 epilogue threads (tid128 = 0..127): publish the tile's sums and leave the shared accumulators zeroed.
+__device__ __forceinline__ void epi_stats_flush(float* s_sum, float* s_sq, int BN, int co0, int Cout, double* sums, int tid128) {
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  for (int c = tid128; c < BN; c += 128) {
+    if (co0 + c < Cout) { atomicAdd(sums + co0 + c, (double)s_sum[c]); atomicAdd(sums + Cout + co0 + c, (double)s_sq[c]); }
+    s_sum[c] = 0.f; s_sq[c] = 0.f;
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 // ---- host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -31,7 +31,8 @@ def _out_nchw(x_cl: torch.Tensor) -> torch.Tensor:
 def _conv(x, m: nn.Module, bn: nn.Module = None):
     """Apply the conv whose parameters live in holder `m` (nn.Conv1d/2d/3d) to channels-last x.  `bn`: the BatchNorm the
     output goes straight into -- in training mode the conv bias then has an identically zero gradient (ops.ConvFn)."""
-    return ops.conv(x, m.weight, m.bias, m.stride, m.padding, zero_bias_grad=bn is not None and bn.training)
+    train_bn = bn is not None and bn.training
+    return ops.conv(x, m.weight, m.bias, m.stride, m.padding, zero_bias_grad=train_bn, bn=bn if train_bn else None)
 
 
 # =============================================================================================================
@@ -74,14 +75,14 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         act = ACT_PRELU if self._prelu else ACT_RELU
-        out = _conv(x, self.conv1)
+        out = _conv(x, self.conv1, self.bn1)
         out = ops.bn_act(out, self.bn1, act, 0.0, self.relu1.weight if self._prelu else None)
-        out = _conv(out, self.conv2)
+        out = _conv(out, self.conv2, self.bn2)
         res = x
         if self.downsample is not None:
             if len(self.downsample) != 2:
                 raise NotImplementedError("avg_pool_downsample variant is not on the VCA-GAN path")
-            res = ops.bn_act(_conv(x, self.downsample[0]), self.downsample[1], ACT_NONE)
+            res = ops.bn_act(_conv(x, self.downsample[0], self.downsample[1]), self.downsample[1], ACT_NONE)
         return ops.bn_act(out, self.bn2, act, 0.0, self.relu2.weight if self._prelu else None, res=res)
 
 
@@ -165,7 +166,7 @@ class Visual_front(nn.Module):
         c0 = self.frontend[0]
         if (cfg.dtype == torch.bfloat16 and cfg.use_tc and self.in_channels == 1 and c0.kernel_size == (5, 7, 7)
                 and c0.stride == (1, 2, 2) and c0.padding == (2, 3, 3)):
-            x = ops.stem_conv(x, c0.weight)             # im2col(7x7) + (5,1) conv on the tcgen05 path
+            x = ops.stem_conv(x, c0.weight, self.frontend[1] if self.frontend[1].training else None)   # im2col(7x7) + (5,1) conv on tcgen05
         else:
             x = _conv(_in_cl(x), c0)                    # generic exact path: (B,T,112,112,1) -> (B,T,56,56,64)
         x = ops.bn_act(x, self.frontend[1], ACT_PRELU, 0.0, self.frontend[2].weight)

@@ -32,6 +32,7 @@ class Config:
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
+    fuse_bn_stats = True    # train-mode BatchNorm statistics come out of the producing conv's epilogue (vca_conv_fwd_tc_stats)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
     pair_merge_channels = (32,)   # 64 -> 64 as 128 -> 128 over pairs works too but measured no faster (62.2 vs 61.8 ms/step)
     param_grad_streams = ()  # side streams for those accumulations (installed by the Trainer; () = current stream)
@@ -237,17 +238,29 @@ def _splitk_workspace(g: ConvGeom, kind: int, device):
     return torch.empty(nb // 4, dtype=torch.float32, device=device), nb
 
 
-def _conv_fwd_raw(x, w, bias, stride, pad):
+def _conv_fwd_raw(x, w, bias, stride, pad, stats=None):
+    """stats: fp64 [2 * Cout] accumulators of the BatchNorm that follows (only passed when _bn_stats_possible)."""
     g, oshape = _geom(x.shape, w.shape, stride, pad)
     wf, wd = _packed(w, x.dtype)
     y = torch.empty(oshape, dtype=x.dtype, device=x.device)
     b = None if bias is None else _c(bias.detach().float())
-    if _tc_ok(g, 0, x.dtype):
+    if stats is not None:
+        lib().call("vca_conv_fwd_tc_stats", g, x, wd, b, y, stats)
+    elif _tc_ok(g, 0, x.dtype):
         ws, nb = _splitk_workspace(g, 0, x.device)
         lib().call("vca_conv_fwd_tc_ws", g, x, wd, b, y, ws, nb)
     else:
         lib().call("vca_conv_fwd_simt", _dt(x), g, x, wf, b, y)
     return y
+
+
+def _bn_stats_possible(xshape, wshape, stride, pad, dtype) -> bool:
+    """True when the forward conv of this geometry runs on a tcgen05 kernel whose epilogue can emit BatchNorm statistics
+    (every non-split-K route of vca_conv_fwd_tc_ws)."""
+    if not cfg.fuse_bn_stats or dtype != torch.bfloat16:
+        return False
+    g, _ = _geom(xshape, wshape, stride, pad)
+    return _tc_ok(g, 0, dtype) and not (cfg.splitk and lib().query("vca_conv_tc_workspace", g, 0) > 0)
 
 
 def _conv_dgrad_raw(dy, w, stride, pad, xshape):
@@ -279,7 +292,7 @@ class ConvFn(Function):
     """y = conv(x, w) + bias on channels-last x; w/bias are fp32 parameters in the reference layout."""
 
     @staticmethod
-    def forward(ctx, x, w, bias, stride, pad, zero_bias_grad=False):
+    def forward(ctx, x, w, bias, stride, pad, zero_bias_grad=False, bn_sums=None):
         _require_cuda(x, w)
         x = _c(x)
         ctx.save_for_backward(x, w)
@@ -290,7 +303,7 @@ class ConvFn(Function):
         ctx.zero_bias_grad = bool(zero_bias_grad) and bias is not None
         ctx.bias_shape = None if bias is None else (tuple(bias.shape), bias.device)
         ctx.bias_leaf = bias if (bias is not None and bias.is_leaf) else None   # only consulted by _grad_sink
-        return _conv_fwd_raw(x, w, bias, stride, pad)
+        return _conv_fwd_raw(x, w, bias, stride, pad, bn_sums)
 
     @staticmethod
     def backward(ctx, dy):
@@ -318,7 +331,7 @@ class ConvFn(Function):
             dw = ConvWgradFn.apply(x, dy, ctx.stride, ctx.pad, tuple(w.shape))
         if want_b and b_sink is None:
             db = ColSumFn.apply(dy)
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class ConvDgradFn(Function):
@@ -432,7 +445,19 @@ class D2SFn(Function):
         return S2DFn.apply(g, ctx.hw2[0], ctx.hw2[1]), None, None
 
 
-def _conv3x3_s2_via_s2d(x, w, bias, zero_bias_grad=False):
+def _conv_bn(x, w, bias, stride, pad, zero_bias_grad, bn, fold=1):
+    """ConvFn, handing the BatchNorm `bn` that consumes the output its batch statistics from the conv epilogue when this
+    geometry allows it.  The result then carries `_vca_bn_sums` = (fp64 accumulators, fold); bn_act picks it up."""
+    sums = None
+    if bn is not None and bn.training and _bn_stats_possible(x.shape, w.shape, stride, pad, x.dtype):
+        sums = _bn_sums(bn.running_mean, 2 * w.shape[0], 0)
+    y = ConvFn.apply(x, w, bias, stride, pad, zero_bias_grad, sums)
+    if sums is not None:
+        y._vca_bn_sums = (sums, fold)
+    return y
+
+
+def _conv3x3_s2_via_s2d(x, w, bias, zero_bias_grad=False, bn=None):
     """3x3 / stride 2 / pad 1 conv as a 2x2 stride-1 conv over the space-to-depth input (4C channels), so that the
     forward, dgrad and wgrad all run on the stride-1 tcgen05 kernels (resnet.py:33 with stride 2, generator.py:326).
     W'[co, (pa*2+pb)*C + c, a, b] = w[co, c, 2a+pa, 2b+pb] (zero where the index is 3)."""
@@ -442,7 +467,7 @@ def _conv3x3_s2_via_s2d(x, w, bias, zero_bias_grad=False):
     Cout = w.shape[0]
     wp = torch.nn.functional.pad(w, (0, 1, 0, 1))                      # (Cout, C, 4, 4)   [data movement]
     w2 = wp.view(Cout, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 4 * C, 2, 2)
-    return ConvFn.apply(xs, w2, bias, (1, 1), (0, 0), zero_bias_grad)
+    return _conv_bn(xs, w2, bias, (1, 1), (0, 0), zero_bias_grad, bn)
 
 
 class PairExpandFn(Function):
@@ -471,26 +496,29 @@ class PairExpandFn(Function):
         return dw
 
 
-def _conv5_via_pairs(x, w, bias, zero_bias_grad=False):
+def _conv5_via_pairs(x, w, bias, zero_bias_grad=False, bn=None):
     """(32 -> 32, KH x 5, pad 2) convolution as a (64 -> 64, KH x 3, pad 1) convolution over pixel pairs: the view
     [N,H,W/2,64] of x costs nothing, the weight is Toeplitz-expanded (1.2x the MACs), and the tcgen05 kernels run with
     N = 64 instead of 32 -- their tensor pipe is bound by the A-operand shared-memory read, i.e. proportional to N."""
     N, H, W, C = x.shape
     w2 = PairExpandFn.apply(w)
     b2 = None if bias is None else torch.cat([bias, bias])
-    y2 = ConvFn.apply(x.view(N, H, W // 2, 2 * C), w2, b2, (1, 1), (w.shape[2] // 2, 1), zero_bias_grad)
-    return y2.view(N, H, W, w.shape[0])
+    y2 = _conv_bn(x.view(N, H, W // 2, 2 * C), w2, b2, (1, 1), (w.shape[2] // 2, 1), zero_bias_grad, bn, fold=2)
+    y = y2.view(N, H, W, w.shape[0])
+    if hasattr(y2, "_vca_bn_sums"):
+        y._vca_bn_sums = y2._vca_bn_sums        # statistics columns are [pair position][channel]: folded by the finalize kernel
+    return y
 
 
-def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0), zero_bias_grad=False):
-    """zero_bias_grad: see ConvFn.forward (the output goes straight into a train-mode BatchNorm)."""
+def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0), zero_bias_grad=False, bn=None):
+    """zero_bias_grad: see ConvFn.forward (the output goes straight into a train-mode BatchNorm).  bn: that BatchNorm
+    (module holding running_mean / training), so that its batch statistics can come out of the conv epilogue."""
     stride, pad = tuple(stride), tuple(pad)
-    if zero_bias_grad and bias is not None:
-        return _conv_zb(x, w, bias, stride, pad)
+    zb = bool(zero_bias_grad) and bias is not None
     if (cfg.pair_merge and x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and stride == (1, 1)
             and w.dim() == 4 and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels
             and pad == (2, 2) and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0 and x.is_contiguous()):
-        return _conv5_via_pairs(x, w, bias)
+        return _conv5_via_pairs(x, w, bias, zb, bn)
     if (x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and all(s == 1 for s in stride) and w.shape[0] % 8 != 0
             and w.shape[0] >= 64 and x.shape[-1] % 8 == 0):
         # Postnet's 256 -> 321 projection (generator.py:185): the tcgen05 kernels want Cout % 8 == 0 (16-byte rows for the
@@ -502,26 +530,13 @@ def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0), zero_bias_grad=False):
     if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0:
         k = tuple(w.shape[2:])
         if k == (3, 3) and pad == (1, 1) and x.shape[-1] >= 8:
-            return _conv3x3_s2_via_s2d(x, w, bias)
+            return _conv3x3_s2_via_s2d(x, w, bias, zb, bn)
         if k == (1, 1) and pad == (0, 0):
-            return ConvFn.apply(x[:, ::2, ::2, :].contiguous(), w, bias, (1, 1), (0, 0))   # slicing = data movement
-    return ConvFn.apply(x, w, bias, stride, pad)
+            return _conv_bn(x[:, ::2, ::2, :].contiguous(), w, bias, (1, 1), (0, 0), zb, bn)   # slicing = data movement
+    return _conv_bn(x, w, bias, stride, pad, zb, bn)
 
 
-def _conv_zb(x, w, bias, stride, pad):
-    """conv() for a biased convolution in front of a train-mode BatchNorm: same dispatch, ConvFn told to skip the bias
-    gradient.  (Only the plain and the stride-2 forms occur in the model: GenResBlk.conv1, Postnet[0], sync-D front.)"""
-    if x.dim() == 4 and stride == (2, 2) and x.dtype == torch.bfloat16 and cfg.use_tc and x.shape[-1] % 8 == 0 \
-            and tuple(w.shape[2:]) == (3, 3) and pad == (1, 1):
-        return _conv3x3_s2_via_s2d(x, w, bias, True)
-    if (cfg.pair_merge and x.dim() == 4 and x.dtype == torch.bfloat16 and cfg.use_tc and stride == (1, 1) and w.dim() == 4
-            and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels and pad == (2, 2)
-            and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0 and x.is_contiguous()):
-        return _conv5_via_pairs(x, w, bias, True)
-    return ConvFn.apply(x, w, bias, stride, pad, True)
-
-
-def stem_conv(vid, w):
+def stem_conv(vid, w, bn=None):
     """Visual front-end stem Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (visual_front.py:11) on the tcgen05 path:
     a gather kernel unrolls the 7x7 spatial taps of the single input channel into 64 channels (49 used), the
     remaining 5-tap temporal convolution is a (5,1) stride-1 conv over (T, 56*56).  vid: (B,1,T,H,W) fp32 -> (B,T,OH,OW,64)."""
@@ -532,8 +547,11 @@ def stem_conv(vid, w):
     lib().call("vca_stem_im2col", _dt(vid), BF16 if cfg.dtype == torch.bfloat16 else F32, vid, cols, B * T, H, W)
     Cout = w.shape[0]
     w2 = torch.nn.functional.pad(w.view(Cout, 5, 49).permute(0, 2, 1), (0, 0, 0, 15)).unsqueeze(-1)   # (Cout,64,5,1)
-    y = ConvFn.apply(cols.view(B, T, OH * OW, 64), w2, None, (1, 1), (2, 0))
-    return y.view(B, T, OH, OW, Cout)
+    y4 = _conv_bn(cols.view(B, T, OH * OW, 64), w2, None, (1, 1), (2, 0), False, bn)
+    y = y4.view(B, T, OH, OW, Cout)
+    if hasattr(y4, "_vca_bn_sums"):
+        y._vca_bn_sums = y4._vca_bn_sums
+    return y
 
 
 def linear(x, w, bias=None):
@@ -566,7 +584,8 @@ class BNActFn(Function):
     buffers in place (momentum 0.1, unbiased variance), eval mode uses the running statistics."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, running_mean, running_var, prelu_w, training, act, slope, eps, momentum):
+    def forward(ctx, x, res, gamma, beta, running_mean, running_var, prelu_w, training, act, slope, eps, momentum,
+                pre_sums=None, fold=1):
         _require_cuda(x)
         x = _c(x)
         res = None if res is None else _c(res)
@@ -575,7 +594,10 @@ class BNActFn(Function):
         dev = x.device
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         invstd = torch.empty(C, dtype=torch.float32, device=dev)
-        if training:
+        if training and pre_sums is not None:
+            # the producing convolution's epilogue already accumulated sum / sum of squares: no pass over x
+            lib().call("vca_bn_finalize_stats", pre_sums, R, C, fold, eps, momentum, mean, invstd, running_mean, running_var)
+        elif training:
             lib().call("vca_bn_stats", _dt(x), x, R, C, eps, momentum, _bn_sums(running_mean, 2 * C, 0), 1, mean, invstd,
                        running_mean, running_var)
         else:
@@ -618,8 +640,8 @@ class BNActFn(Function):
                    None if prelu_w is None else prelu_w.detach(), 1 if training else 0, _bn_sums(ctx.key, 3 * C, 1), dgamma, dbeta,
                    dprelu, 1 | (2 if fused else 0))
         if fused:
-            return dx, dres, None, None, None, None, None, None, None, None, None, None
-        return dx, dres, dgamma, dbeta, None, None, dprelu, None, None, None, None, None
+            return (dx, dres) + (None,) * 12
+        return (dx, dres, dgamma, dbeta, None, None, dprelu) + (None,) * 7
 
 
 def bn_act(x, bn: torch.nn.Module, act=ACT_NONE, slope=0.0, prelu_w=None, res=None):
@@ -630,8 +652,11 @@ def bn_act(x, bn: torch.nn.Module, act=ACT_NONE, slope=0.0, prelu_w=None, res=No
             cfg.deferred_counters.append(bn.num_batches_tracked)
         else:
             bn.num_batches_tracked += 1
+    pre = getattr(x, "_vca_bn_sums", None) if training else None
+    if pre is not None and pre[0].data_ptr() != _bn_sums(bn.running_mean, pre[0].numel(), 0).data_ptr():
+        raise RuntimeError("BatchNorm statistics were accumulated for a different BatchNorm than the one consuming the tensor")
     return BNActFn.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu_w, training, act, float(slope),
-                         float(bn.eps), float(bn.momentum))
+                         float(bn.eps), float(bn.momentum), None if pre is None else pre[0], 1 if pre is None else pre[1])
 
 
 def flush_deferred_counters():
