@@ -604,12 +604,13 @@ def test_attention_tc(V, Tq, S, lens):
 
 @pytest.mark.parametrize("case", [
     # N, Cin, H, W, Cout, k, pad, stride, hs_mode
-    (3, 128, 20, 25, 256, 3, 1, 1, 1),    # streaming kernel, two... BN = 256 tile
-    (2, 64, 40, 46, 64, 5, 2, 1, 1),      # weights-stationary persistent kernel, several tiles per CTA
-    (4, 128, 14, 14, 128, 3, 1, 1, 2),    # halo-resident / streamed-weights kernel (forced)
-    (2, 32, 24, 50, 32, 5, 2, 1, 1),      # pixel-pair merged: statistics arrive as two column groups per channel
+    # (batches large enough that the forward does not run split-K, as in the training step: split-K has no statistics)
+    (24, 128, 20, 25, 256, 3, 1, 1, 1),   # streaming kernel, BN = 256 tile
+    (16, 64, 40, 46, 64, 5, 2, 1, 1),     # weights-stationary persistent kernel, several tiles per CTA
+    (64, 128, 14, 14, 128, 3, 1, 1, 2),   # halo-resident / streamed-weights kernel (forced)
+    (16, 32, 24, 50, 32, 5, 2, 1, 1),     # pixel-pair merged: statistics arrive as two column groups per channel
     (3, 64, 28, 28, 128, 3, 1, 2, 1),     # stride 2 via space-to-depth
-    (2, 320, 9, 11, 200, 3, 1, 1, 1),     # ragged: Cout not a multiple of 16 x tile, partial last K chunk
+    (100, 320, 9, 11, 200, 3, 1, 1, 1),   # ragged: Cout not a multiple of the 16-column chunks x tile, partial last K chunk
 ])
 def test_bn_stats_from_conv_epilogue(V, case):
     """Train-mode BatchNorm whose batch statistics come out of the producing convolution's epilogue

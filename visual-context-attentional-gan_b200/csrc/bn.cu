@@ -33,8 +33,8 @@ template <int ACT> __device__ __forceinline__ float act_bwd(float g, float pre, 
 
 // Sum per-thread partials over threadIdx.y (fp64 tree in shared memory, sh = double[V][256]) and add the CTA's
 // column totals to out[c] with one atomic per channel.
-template <int V, class A>
-__device__ __forceinline__ void block_col_reduce(const A (&acc)[V], double* sh, double* out, int c0, bool active) {
+template <int V, class A, class O = double>
+__device__ __forceinline__ void block_col_reduce(const A (&acc)[V], double* sh, O* out, int c0, bool active) {
   const int TX = blockDim.x, tid = threadIdx.y * TX + threadIdx.x;
   __syncthreads();
 #pragma unroll
@@ -49,7 +49,7 @@ __device__ __forceinline__ void block_col_reduce(const A (&acc)[V], double* sh, 
   }
   if (threadIdx.y == 0 && active) {
 #pragma unroll
-    for (int i = 0; i < V; ++i) atomicAdd(&out[c0 + i], sh[i * 256 + threadIdx.x]);
+    for (int i = 0; i < V; ++i) atomicAdd(&out[c0 + i], (O)sh[i * 256 + threadIdx.x]);
   }
 }
 
@@ -294,9 +294,9 @@ __global__ void bn_param_grads_kernel(double* __restrict__ sums, int C, float* _
 }
 
 // ---- column sums of a [R, C] matrix (bias gradients); the scalar kernel handles any C ---------------------------
-template <class VT>
+template <class VT, class O = double>
 __global__ void __launch_bounds__(256, 3) colsum_vec_kernel(const typename VT::Elem* __restrict__ x, long long R, int C,
-                                                            double* __restrict__ out) {
+                                                            O* __restrict__ out) {
   typedef typename AccOf<typename VT::Elem>::type Acc;
   constexpr int V = VT::N, U = 8;
   __shared__ double sh[256 * V];
@@ -473,8 +473,16 @@ int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, vo
 // out[c] (+)= sum_r x[r,c] (fp32; accumulate != 0 adds to the existing contents).  scratch: device double[C].
 int vca_colsum(int dtype, const void* x, long long R, int C, double* scratch, float* out, int accumulate, cudaStream_t s) {
   VCA_CHECK_ARG(x && out && scratch && R > 0 && C > 0);
-  cudaMemsetAsync(scratch, 0, sizeof(double) * C, s);
   const bool ok = dtype == VCA_F32 ? vec_ok<Vec<float>>(x, 0, 0, 0, 0, C) : vec_ok<Vec<bf16>>(x, 0, 0, 0, 0, C);
+  if (ok && dtype == VCA_BF16 && accumulate) {
+    // bias gradient of a bf16 tensor added into a live fp32 .grad view: one launch -- per-thread fp32 partials, fp64 tree
+    // per CTA, one fp32 atomic per channel and CTA straight into the destination (no scratch, no memset, no conversion pass)
+    RowColGrid g = one_wave_grid<colsum_vec_kernel<Vec<bf16>, float>>(R, C / 8);
+    colsum_vec_kernel<Vec<bf16>, float><<<g.grid, g.block, 0, s>>>((const bf16*)x, R, C, out);
+    VCA_LAUNCH_CHECK();
+    return VCA_OK;
+  }
+  cudaMemsetAsync(scratch, 0, sizeof(double) * C, s);
   if (ok && dtype == VCA_F32) {
     RowColGrid g = one_wave_grid<colsum_vec_kernel<Vec<float>>>(R, C / 4);
     colsum_vec_kernel<Vec<float>><<<g.grid, g.block, 0, s>>>((const float*)x, R, C, scratch);
