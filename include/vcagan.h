@@ -64,6 +64,7 @@ int vca_conv_tc_workspace(const ConvGeom* g, int kind);
 int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, float* ws, long long ws_bytes, cudaStream_t stream);
 /* forward conv that also ADDS the per-output-channel sum / sum of squares of y (as stored) into stats[0..Cout) / stats[Cout..2Cout)
    (fp64): the batch statistics of a BatchNorm that follows (generator.py:115-116, resnet.py:47-48); never split-K */
+int vca_conv_fwd_tc_stats_supported(const ConvGeom* g);
 int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t stream);
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);

@@ -500,6 +500,16 @@ int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const f
 int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t s) {
   return vca_conv_fwd_tc_ws(g, x, wd, bias, y, nullptr, 0, s);
 }
+// 1 when vca_conv_fwd_tc_stats takes this geometry AND the statistics come (almost) for free: the weights-stationary
+// persistent kernel (<= 64 channels in and out: the stem, ResNet layer 1, the 40x150 / 80x300 generator stages -- the
+// large tensors, where the separate statistics pass costs most).  The streaming / halo-resident kernels can emit them too
+// (measured: their one-tile-at-a-time epilogues pay more for the column reduction than the saved pass is worth).
+int vca_conv_fwd_tc_stats_supported(const ConvGeom* g) {
+  if (!g || !vca_conv_tc_supported(g, 0)) return 0;
+  static double dummy;
+  return conv_ws_try(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, nullptr, nullptr, nullptr, nullptr,
+                     &dummy, nullptr) == 1 ? 1 : 0;
+}
 // Forward convolution that also accumulates the per-output-channel sum and sum of squares of y (as stored, i.e. bf16
 // rounded) into stats[0 .. Cout) and stats[Cout .. 2 Cout) (fp64, ADDED to): the batch statistics of a BatchNorm that
 // follows (vca_bn_finalize_stats turns them into mean / invstd).  Never runs split-K.

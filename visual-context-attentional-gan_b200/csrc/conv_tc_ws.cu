@@ -160,6 +160,11 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
     const int m = q * 32 + lane;
     const int r = m / p.P, wq = m - r * p.P;
     int it = 0;
+    // BatchNorm statistics (BN <= 64 whenever they are requested): every thread keeps running sums of ITS tile row's
+    // 64 columns over all tiles of this persistent CTA -- two FMAs per value; the cross-row reduction happens once, below
+    float rs[64], rq[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
       const int tw_i = t % p.tiles_w; t /= p.tiles_w;
@@ -170,14 +175,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       const int acc = it & 1;
       mbar_wait(&t_full[acc], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
-      for (int c = 0; c < p.BN; c += 16) {
+#pragma unroll
+      for (int cc = 0; cc < 16; ++cc) {
+        const int c = cc * 16;
+        if (c >= p.BN) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
         if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
         }
-        if (p.stats) epi_stats16(v, row_ok, co0 + c, p.Cout, s_sum + c, s_sq + c, lane);
+        if (p.stats && cc < 4 && row_ok) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float t = bf16_round(v[i]); rs[(cc & 3) * 16 + i] += t; rq[(cc & 3) * 16 + i] = fmaf(t, t, rq[(cc & 3) * 16 + i]); }
+        }
         if (row_ok && co0 + c < p.Cout) {
           if (co0 + c + 16 <= p.Cout) {
             uint32_t w[8];
@@ -196,7 +207,20 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
     }
     // BatchNorm statistics: the shared accumulators collect ALL tiles of this persistent CTA (fp32 over a few thousand
     // rows), published once -- a flush per tile would put tens of thousands of fp64 atomics on each channel's address
-    if (p.stats) epi_stats_flush(s_sum, s_sq, p.BN, co0, p.Cout, p.stats, (int)threadIdx.x - 64);
+    if (p.stats) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc * 16 < p.BN) {
+          float a[16], b[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { a[i] = rs[cc * 16 + i]; b[i] = rq[cc * 16 + i]; }
+          const float sa = colsum16(a, lane), sb = colsum16(b, lane);
+          const int col = epi_col(lane);
+          if (!(lane & 1) && co0 + cc * 16 + col < p.Cout) { atomicAdd(s_sum + cc * 16 + col, sa); atomicAdd(s_sq + cc * 16 + col, sb); }
+        }
+      }
+      epi_stats_flush(s_sum, s_sq, p.BN, co0, p.Cout, p.stats, (int)threadIdx.x - 64);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -222,6 +246,7 @@ void choose_ws_tile(int H, int W, int KH, int KW, int& th, int& tw) {
 // streaming kernel), negative on error.  Arguments as conv_tc.cu::fwd_like.
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
                     const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s) {
+  // x == nullptr: dry run -- 1 when this kernel would take the geometry (and, with stats != nullptr, emit the statistics)
   if (g_ws_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
   if (taps < 2 || taps > 256 || kchunks > 2 || KW > 64) return 0;
@@ -256,6 +281,8 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   if (sa < 2) return 0;
   p.sa = sa;
   p.tmem_cols = pow2_cols(2 * bn);
+  if (stats && bn > 64) return 0;          // the epilogue keeps the statistics of at most 64 columns in registers
+  if (!x) return 1;
   p.base_off_mode = g_ws_base_off;
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
   const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics

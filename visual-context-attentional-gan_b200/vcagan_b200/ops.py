@@ -41,6 +41,13 @@ class Config:
 
 
 cfg = Config()
+# A/B switches from the environment, e.g. VCA_CFG="fuse_bn_stats=0,pair_merge=0" (booleans of Config only)
+import os as _os
+for _kv in filter(None, _os.environ.get("VCA_CFG", "").split(",")):
+    _k, _v = _kv.split("=")
+    if not isinstance(getattr(Config, _k.strip(), None), bool):
+        raise ValueError(f"VCA_CFG: {_k} is not a boolean switch of ops.Config")
+    setattr(cfg, _k.strip(), bool(int(_v)))
 
 
 def set_precision(p: str):
@@ -255,12 +262,12 @@ def _conv_fwd_raw(x, w, bias, stride, pad, stats=None):
 
 
 def _bn_stats_possible(xshape, wshape, stride, pad, dtype) -> bool:
-    """True when the forward conv of this geometry runs on a tcgen05 kernel whose epilogue can emit BatchNorm statistics
-    (every non-split-K route of vca_conv_fwd_tc_ws)."""
+    """True when the forward conv of this geometry runs on the tcgen05 kernel whose epilogue emits BatchNorm statistics
+    for free (the weights-stationary persistent kernel; see vca_conv_fwd_tc_stats_supported)."""
     if not cfg.fuse_bn_stats or dtype != torch.bfloat16:
         return False
     g, _ = _geom(xshape, wshape, stride, pad)
-    return _tc_ok(g, 0, dtype) and not (cfg.splitk and lib().query("vca_conv_tc_workspace", g, 0) > 0)
+    return cfg.use_tc and lib().query("vca_conv_fwd_tc_stats_supported", g) == 1
 
 
 def _conv_dgrad_raw(dy, w, stride, pad, xshape):
