@@ -83,6 +83,10 @@ int vca_bn_stats(int dtype, const void* x, long long R, int C, float eps, float 
    [fold][C] sums of squares), left zeroed */
 int vca_bn_finalize_stats(double* sums, long long R, int C, int fold, float eps, float momentum, float* mean, float* invstd, float* running_mean, float* running_var, cudaStream_t stream);
 int vca_bn_eval_stats(const float* running_mean, const float* running_var, int C, float eps, float* mean, float* invstd, cudaStream_t stream);
+/* visual front-end stem tail in one pass: BatchNorm3d -> PReLU -> MaxPool3d (1,3,3)/(1,2,2)/(0,1,1) (visual_front.py:12-14), bf16.
+   x [NF,H,W,C] raw conv output; y / idx / xmax [NF,OH,OW,C] (pooled activation, argmax code 0..8, raw x at the argmax). */
+int vca_bn_prelu_maxpool_fwd(const void* x, void* y, unsigned char* idx, void* xmax, int NF, int H, int W, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, const float* prelu_w, cudaStream_t stream);
+int vca_bn_prelu_maxpool_bwd(const void* dy, const unsigned char* idx, const void* xmax, const void* x, void* dx, int NF, int H, int W, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags, cudaStream_t stream);
 int vca_bn_act_fwd(int dtype, const void* x, const void* res, void* y, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, cudaStream_t stream);
 int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, void* dx, void* dres, long long R, int C, const float* mean, const float* invstd, const float* gamma, const float* beta, int act, float slope, const float* prelu_w, int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags, cudaStream_t stream);
 int vca_lrelu_fwd(int dtype, const void* x, void* y, long long n, float slope, cudaStream_t stream);

@@ -605,10 +605,11 @@ def test_attention_tc(V, Tq, S, lens):
 @pytest.mark.parametrize("case", [
     # N, Cin, H, W, Cout, k, pad, stride, hs_mode
     # N, Cin, H, W, Cout, k, pad, stride, expect the fused path (weights-stationary kernel: <= 64 channels in and out)
-    (16, 64, 40, 46, 64, 5, 2, 1, True),      # several tiles per persistent CTA, ragged tiles
+    (16, 64, 40, 46, 64, 3, 1, 1, True),      # several tiles per persistent CTA, ragged tiles
+    (16, 64, 40, 46, 64, 5, 2, 1, False),     # 64 -> 64 5x5: the weights do not fit next to the halo ring -> streaming kernel
     (300, 64, 28, 28, 64, 3, 1, 1, True),     # ResNet layer 1 at 4 clips: ~600 tiles, 4 per CTA
     (16, 32, 24, 50, 32, 5, 2, 1, True),      # pixel-pair merged: statistics arrive as two column groups per channel
-    (9, 48, 11, 30, 40, 5, 2, 1, True),       # ragged channels: Cout = 40 (three 16-column chunks, the last half empty), K chunk 48
+    (9, 48, 11, 30, 40, 3, 1, 1, True),       # ragged channels: Cout = 40 (three 16-column chunks, the last half empty), K chunk 48
     (24, 128, 20, 25, 256, 3, 1, 1, False),   # wide layers keep the separate statistics pass
     (3, 64, 28, 28, 128, 3, 1, 2, False),     # stride 2 via space-to-depth (256 input channels)
 ])
@@ -643,4 +644,41 @@ def test_bn_stats_from_conv_epilogue(V, case):
             assert float(t.abs().max()) == 0.0, key
     finally:
         V.ops.cfg.fuse_bn_stats = True
+        V.set_precision("fp32")
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_bn_prelu_maxpool_fused(V, train):
+    """The fused stem tail (BatchNorm3d -> PReLU -> MaxPool3d, visual_front.py:12-14) against the separate bn_act +
+    maxpool kernels on the same bf16 input: identical forward (values are rounded to bf16 before the max in both), and
+    the same input / parameter gradients and running statistics up to summation order."""
+    g = torch.Generator().manual_seed(11)
+    NF, H, W, C = 6, 18, 22, 64
+    x0 = (torch.randn(NF, H, W, C, generator=g) * 1.3 + 0.2).bfloat16().cuda()
+    dy = torch.randn(NF, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C, generator=g).bfloat16().cuda()
+    V.set_precision("bf16")
+    try:
+        res = []
+        for fused in (False, True):
+            bn = torch.nn.BatchNorm2d(C).cuda().train(train)
+            pw = torch.nn.Parameter((0.25 + 0.1 * torch.randn(C, generator=torch.Generator().manual_seed(3))).cuda())
+            with torch.no_grad():
+                ga = torch.Generator().manual_seed(5)
+                bn.weight.copy_(torch.randn(C, generator=ga)); bn.bias.copy_(torch.randn(C, generator=ga))   # negative gammas too
+                bn.running_mean.copy_(0.1 * torch.randn(C, generator=ga)); bn.running_var.copy_(1 + 0.2 * torch.rand(C, generator=ga))
+            x = x0.clone().requires_grad_(True)
+            if fused:
+                y = V.ops.bn_prelu_maxpool(x, bn, pw)
+            else:
+                y = V.ops.maxpool3x3s2(V.ops.bn_act(x, bn, V.ops.ACT_PRELU, 0.0, pw))
+            y.backward(dy)
+            torch.cuda.synchronize()
+            res.append([t.detach().float().cpu() for t in (y, x.grad, bn.weight.grad, bn.bias.grad, pw.grad, bn.running_mean, bn.running_var)])
+        a, b = res
+        assert torch.equal(a[0], b[0])
+        names = ("dx", "dgamma", "dbeta", "dprelu", "running_mean", "running_var")
+        errs = {n: rel_l2(v, u) for n, u, v in zip(names, a[1:], b[1:])}
+        print("fused stem tail vs bn_act + maxpool", train, errs)
+        assert errs["dx"] < 5e-3 and max(errs[k] for k in names[1:4]) < 1e-4 and max(errs[k] for k in names[4:]) < 1e-6, errs
+    finally:
         V.set_precision("fp32")

@@ -20,6 +20,7 @@ enum { ACT_NONE = 0, ACT_LRELU = 1, ACT_PRELU = 2, ACT_RELU = 3 };
 template <class E> struct AccOf { typedef double type; };
 template <> struct AccOf<bf16> { typedef float type; };
 
+__device__ __forceinline__ float bf16_rn(float v) { return __bfloat162float(__float2bfloat16_rn(v)); }
 template <int ACT> __device__ __forceinline__ float act_fwd(float v, float s) {
   if (ACT == ACT_NONE) return v;
   if (ACT == ACT_RELU) return v > 0.f ? v : 0.f;
@@ -276,6 +277,130 @@ bn_act_bwd_apply_kernel(const typename VT::Elem* __restrict__ dy, const typename
   BN_ROW_LOOP(U, (RES ? 3 : 2), RD_LOADS, AP_BODY, )
 }
 
+// ---- visual front-end stem: BatchNorm3d -> PReLU -> MaxPool3d((1,3,3),(1,2,2),(0,1,1)) in one pass (visual_front.py:12-14)
+// The stem's activation is the largest tensor of the step (B*T x 56 x 56 x 64 bf16 = 963 MB at B = 32, T = 75).  Unfused it
+// is written by the conv, read + written by BN/PReLU, read by the pool (+ the mirror image backward).  Here the pool reads
+// the RAW conv output, applies scale/shift/PReLU to each of the 9 taps in registers (rounded to bf16 first, so values and
+// argmax are exactly those of the unfused path) and writes only the pooled tensors: y, the argmax code, and the raw x at
+// the argmax (what the backward's reduction pass needs, at a quarter of the size).
+template <class VT>
+__global__ void __launch_bounds__(256) bn_prelu_maxpool_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                                   unsigned char* __restrict__ idx, bf16* __restrict__ xmax, int NF,
+                                                                   int H, int W, int C, int OH, int OW, BnParams p) {
+  constexpr int V = 8;
+  const int CV = C / V;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cv = (int)(tid % CV);                     // gridDim.x * blockDim.x is a multiple of CV: fixed channel group
+  float mu[V], sc[V], be[V], sl[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = cv * V + i;
+    mu[i] = p.mean[c]; sc[i] = p.invstd[c] * p.gamma[c]; be[i] = p.beta[c]; sl[i] = p.prelu_w[c];
+  }
+  const long long total = (long long)NF * OH * OW * CV;
+  for (long long i = tid; i < total; i += (long long)gridDim.x * blockDim.x) {
+    unsigned r = (unsigned)(i / CV);
+    const int ow = (int)(r % (unsigned)OW); r /= (unsigned)OW;
+    const int oh = (int)(r % (unsigned)OH); const int n = (int)(r / (unsigned)OH);
+    float best[V], xb[V]; int bi[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { best[k] = -INFINITY; bi[k] = 0; xb[k] = 0.f; }
+    uint4 raw[9]; bool ok[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {                     // all taps in flight before any is used
+      const int h = oh * 2 - 1 + t / 3, w = ow * 2 - 1 + t % 3;
+      ok[t] = (unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W;
+      if (ok[t]) raw[t] = *reinterpret_cast<const uint4*>(x + (((long long)n * H + h) * W + w) * C + cv * V);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      if (!ok[t]) continue;
+      float v[V];
+      Vec<bf16>::unpack(raw[t], v);
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        float z = (v[k] - mu[k]) * sc[k] + be[k];        // the arithmetic of bn_act_fwd_kernel, so the values are bit-identical
+        z = bf16_rn(z > 0.f ? z : z * sl[k]);
+        if (z > best[k] || (z != z && best[k] == best[k])) { best[k] = z; bi[k] = t; xb[k] = v[k]; }
+      }
+    }
+    const long long o = i * V;
+    Vec<bf16>::store(y + o, best);
+    Vec<bf16>::store(xmax + o, xb);
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { lo |= (unsigned)bi[k] << (8 * k); hi |= (unsigned)bi[4 + k] << (8 * k); }
+    *reinterpret_cast<uint2*>(idx + o) = make_uint2(lo, hi);
+  }
+}
+// backward, dense pass: dx[pos] = gamma*invstd*(g' - mean(g') - xhat*mean(g'*xhat)),  g'[pos] = prelu'(z[pos]) * sum of the
+// pooled gradients whose window has its argmax at pos (at most 2 x 2 windows contain a position); sums from the reduction
+// over the POOLED tensors (bn_act_bwd_reduce_kernel on dy_pool / xmax), means over the R_full positions.
+__global__ void __launch_bounds__(256) bn_prelu_maxpool_bwd_apply_kernel(const bf16* __restrict__ dy, const unsigned char* __restrict__ idx,
+                                                                         const bf16* __restrict__ x, bf16* __restrict__ dx, int NF, int H,
+                                                                         int W, int C, int OH, int OW, BnParams p,
+                                                                         const double* __restrict__ sums, int train) {
+  constexpr int V = 8;
+  const int CV = C / V;
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int cv = (int)(tid % CV);
+  float mu[V], is[V], ga[V], be[V], sl[V], m1[V], m2[V];
+  const double invR = 1.0 / ((double)NF * H * W);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = cv * V + i;
+    mu[i] = p.mean[c]; is[i] = p.invstd[c]; ga[i] = p.gamma[c]; be[i] = p.beta[c]; sl[i] = p.prelu_w[c];
+    m1[i] = train ? (float)(sums[c] * invR) : 0.f;
+    m2[i] = train ? (float)(sums[C + c] * invR) : 0.f;
+  }
+  const long long total = (long long)NF * H * W * CV;
+  for (long long i = tid; i < total; i += (long long)gridDim.x * blockDim.x) {
+    unsigned r = (unsigned)(i / CV);
+    const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
+    const int h = (int)(r % (unsigned)H); const int n = (int)(r / (unsigned)H);
+    const int ohs[2] = {h >> 1, (h + 1) >> 1}, ows[2] = {w >> 1, (w + 1) >> 1};
+    const bool vh[2] = {ohs[0] < OH, ohs[1] < OH && ohs[1] != ohs[0]}, vw[2] = {ows[0] < OW, ows[1] < OW && ows[1] != ows[0]};
+    const uint4 xr = *reinterpret_cast<const uint4*>(x + i * V);
+    float g[4][V]; unsigned long long codes[4];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int q = a * 2 + b;
+        codes[q] = 0xffffffffffffffffull;
+#pragma unroll
+        for (int k = 0; k < V; ++k) g[q][k] = 0.f;
+        if (vh[a] && vw[b]) {
+          const long long o = (((long long)n * OH + ohs[a]) * OW + ows[b]) * C + cv * V;
+          Vec<bf16>::load(dy + o, g[q]);
+          codes[q] = *reinterpret_cast<const unsigned long long*>(idx + o);
+        }
+      }
+    float acc[V], xv[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int q = a * 2 + b;
+        const unsigned code = (unsigned)((h - (ohs[a] * 2 - 1)) * 3 + (w - (ows[b] * 2 - 1)));
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+          if ((unsigned)((codes[q] >> (8 * k)) & 0xffull) == code) acc[k] += g[q][k];
+      }
+    Vec<bf16>::unpack(xr, xv);
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float xh = (xv[k] - mu[k]) * is[k];
+      const float pre = xh * ga[k] + be[k];
+      const float dpre = pre > 0.f ? acc[k] : acc[k] * sl[k];
+      xv[k] = (dpre - m1[k] - xh * m2[k]) * ga[k] * is[k];
+    }
+    Vec<bf16>::store(dx + i * V, xv);
+  }
+}
+
 __global__ void bn_param_grads_kernel(double* __restrict__ sums, int C, float* __restrict__ dgamma,
                                       float* __restrict__ dbeta, float* __restrict__ dprelu, int rezero, int accumulate) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -467,6 +592,52 @@ int vca_bn_act_bwd(int dtype, const void* dy, const void* x, const void* res, vo
   else { BN_DISPATCH(launch_bwd, VecH4, dy, x, res, dx, dres, R, C, p, train, sums, s) }
   VCA_LAUNCH_CHECK();
   bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, dgamma, dbeta, act == ACT_PRELU ? dprelu : nullptr, flags & 1, (flags >> 1) & 1);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// Fused stem tail (bf16, C % 8 == 0, C / 8 a power of two <= 256): y / idx / xmax are [NF, OH, OW, C] with OH = (H-1)/2+1.
+int vca_bn_prelu_maxpool_fwd(const void* x, void* y, unsigned char* idx, void* xmax, int NF, int H, int W, int C, const float* mean,
+                             const float* invstd, const float* gamma, const float* beta, const float* prelu_w, cudaStream_t s) {
+  VCA_CHECK_ARG(x && y && idx && xmax && mean && invstd && gamma && beta && prelu_w && NF > 0 && H > 0 && W > 0 && C > 0);
+  const int CV = C / 8;
+  if (C % 8 || CV > 256 || (CV & (CV - 1)) || !vca_aligned16(x) || !vca_aligned16(y) || !vca_aligned16(xmax) ||
+      (long long)NF * H * W >= (1LL << 31)) {
+    vca_set_error("vca_bn_prelu_maxpool_fwd: unsupported shape"); return VCA_ERR_UNSUPPORTED;
+  }
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  BnParams p{mean, invstd, gamma, beta, prelu_w, 0.f};
+  const long long total = (long long)NF * OH * OW * CV;
+  long long gx = (total + 255) / 256; if (gx > 148LL * 16) gx = 148LL * 16;
+  bn_prelu_maxpool_fwd_kernel<Vec<bf16>><<<(unsigned)gx, 256, 0, s>>>((const bf16*)x, (bf16*)y, idx, (bf16*)xmax, NF, H, W, C, OH, OW, p);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// Backward of the fused stem tail.  dy / idx / xmax: pooled tensors; x: the raw conv output; dx: its gradient.  sums: fp64
+// scratch [3C] (flags bit 0: persistent and pre-zeroed, left zeroed; bit 1: dgamma / dbeta / dprelu are added to).
+int vca_bn_prelu_maxpool_bwd(const void* dy, const unsigned char* idx, const void* xmax, const void* x, void* dx, int NF, int H, int W,
+                             int C, const float* mean, const float* invstd, const float* gamma, const float* beta, const float* prelu_w,
+                             int train, double* sums, float* dgamma, float* dbeta, float* dprelu, int flags, cudaStream_t s) {
+  VCA_CHECK_ARG(dy && idx && xmax && x && dx && mean && invstd && gamma && beta && prelu_w && sums && NF > 0 && H > 0 && W > 0 && C > 0);
+  const int CV = C / 8;
+  if (C % 8 || CV > 256 || (CV & (CV - 1)) || !vca_aligned16(x) || !vca_aligned16(dy) || !vca_aligned16(xmax) || !vca_aligned16(dx) ||
+      (long long)NF * H * W >= (1LL << 31)) {
+    vca_set_error("vca_bn_prelu_maxpool_bwd: unsupported shape"); return VCA_ERR_UNSUPPORTED;
+  }
+  const int OH = (H - 1) / 2 + 1, OW = (W - 1) / 2 + 1;
+  if (!(flags & 1)) cudaMemsetAsync(sums, 0, sizeof(double) * 3 * C, s);
+  BnParams p{mean, invstd, gamma, beta, prelu_w, 0.f};
+  const long long Rp = (long long)NF * OH * OW;
+  {   // reduction over the pooled gradient and the raw x at its argmax: sum g', sum g'*xhat, PReLU slope gradient
+    RowColGrid g = one_wave_grid<bn_act_bwd_reduce_kernel<VecH4, ACT_PRELU, false>>(Rp, C / 4);
+    bn_act_bwd_reduce_kernel<VecH4, ACT_PRELU, false><<<g.grid, g.block, 0, s>>>((const bf16*)dy, (const bf16*)xmax, nullptr, Rp, C, p, sums);
+  }
+  VCA_LAUNCH_CHECK();
+  const long long total = (long long)NF * H * W * CV;
+  long long gx = (total + 255) / 256; if (gx > 148LL * 16) gx = 148LL * 16;
+  bn_prelu_maxpool_bwd_apply_kernel<<<(unsigned)gx, 256, 0, s>>>((const bf16*)dy, idx, (const bf16*)x, (bf16*)dx, NF, H, W, C, OH, OW, p, sums,
+                                                                train);
+  VCA_LAUNCH_CHECK();
+  bn_param_grads_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, C, dgamma, dbeta, dprelu, flags & 1, (flags >> 1) & 1);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

@@ -169,8 +169,15 @@ class Visual_front(nn.Module):
             x = ops.stem_conv(x, c0.weight, self.frontend[1] if self.frontend[1].training else None)   # im2col(7x7) + (5,1) conv on tcgen05
         else:
             x = _conv(_in_cl(x), c0)                    # generic exact path: (B,T,112,112,1) -> (B,T,56,56,64)
-        x = ops.bn_act(x, self.frontend[1], ACT_PRELU, 0.0, self.frontend[2].weight)
-        x = ops.maxpool3x3s2(x.view(B * T, x.shape[2], x.shape[3], x.shape[4]))   # (B*T,28,28,64)
+        if ops.bn_prelu_maxpool_supported(x, x.shape[-1]):
+            stats = getattr(x, "_vca_bn_sums", None)
+            x = x.view(B * T, x.shape[2], x.shape[3], x.shape[4])
+            if stats is not None:
+                x._vca_bn_sums = stats
+            x = ops.bn_prelu_maxpool(x, self.frontend[1], self.frontend[2].weight)   # BN3d + PReLU + MaxPool3d in one pass
+        else:
+            x = ops.bn_act(x, self.frontend[1], ACT_PRELU, 0.0, self.frontend[2].weight)
+            x = ops.maxpool3x3s2(x.view(B * T, x.shape[2], x.shape[3], x.shape[4]))   # (B*T,28,28,64)
         x = self.resnet(x)                              # (B*T,512)
         fm, gm = self.drop_masks if self.drop_masks is not None else (None, None)
         x = ops.dropout(x, self.dropout.p, self.training, fm)

@@ -32,6 +32,7 @@ class Config:
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
+    fuse_stem_pool = True   # stem BatchNorm3d + PReLU + MaxPool3d as one pass over the raw conv output (bn_prelu_maxpool)
     fuse_bn_stats = True    # train-mode BatchNorm statistics come out of the producing conv's epilogue (vca_conv_fwd_tc_stats)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
     pair_merge_channels = (32,)   # 64 -> 64 as 128 -> 128 over pairs works too but measured no faster (62.2 vs 61.8 ms/step)
@@ -664,6 +665,78 @@ def bn_act(x, bn: torch.nn.Module, act=ACT_NONE, slope=0.0, prelu_w=None, res=No
         raise RuntimeError("BatchNorm statistics were accumulated for a different BatchNorm than the one consuming the tensor")
     return BNActFn.apply(x, res, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu_w, training, act, float(slope),
                          float(bn.eps), float(bn.momentum), None if pre is None else pre[0], 1 if pre is None else pre[1])
+
+
+class BNPReluMaxPoolFn(Function):
+    """maxpool3x3s2(prelu(BN(x))) for the visual front-end stem (visual_front.py:12-14) in ONE pass over the raw conv
+    output (csrc/bn.cu: bn_prelu_maxpool_*): the 963 MB activated tensor is never written.  x (NF,H,W,C) bf16."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, prelu_w, training, eps, momentum, pre_sums=None, fold=1):
+        _require_cuda(x)
+        x = _c(x)
+        NF, H, W, C = x.shape
+        R = NF * H * W
+        dev = x.device
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        invstd = torch.empty(C, dtype=torch.float32, device=dev)
+        if training and pre_sums is not None:
+            lib().call("vca_bn_finalize_stats", pre_sums, R, C, fold, eps, momentum, mean, invstd, running_mean, running_var)
+        elif training:
+            lib().call("vca_bn_stats", _dt(x), x, R, C, eps, momentum, _bn_sums(running_mean, 2 * C, 0), 1, mean, invstd,
+                       running_mean, running_var)
+        else:
+            lib().call("vca_bn_eval_stats", running_mean, running_var, C, eps, mean, invstd)
+        OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((NF, OH, OW, C), dtype=x.dtype, device=dev)
+        xmax = torch.empty_like(y)
+        idx = torch.empty((NF, OH, OW, C), dtype=torch.uint8, device=dev)
+        lib().call("vca_bn_prelu_maxpool_fwd", x, y, idx, xmax, NF, H, W, C, mean, invstd, gamma.detach(), beta.detach(), prelu_w.detach())
+        ctx.save_for_backward(x, idx, xmax, gamma, beta, prelu_w, mean, invstd)
+        ctx.training, ctx.key = training, running_mean
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, idx, xmax, gamma, beta, prelu_w, mean, invstd = ctx.saved_tensors
+        dy = _c(dy)
+        NF, H, W, C = x.shape
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        wanted = [_needed(ctx, 1), _needed(ctx, 2), _needed(ctx, 5, 5)]
+        sinks = [_grad_sink(p) for p in (gamma, beta, prelu_w)]
+        fused = all(wanted) and all(t is not None for t in sinks)
+        if fused:
+            dgamma, dbeta, dprelu = sinks
+        elif any(wanted):
+            dgamma, dbeta, dprelu = (torch.empty(C, dtype=torch.float32, device=x.device) for _ in range(3))
+        else:
+            dgamma = dbeta = dprelu = None
+        if dx is None:
+            dx = torch.empty_like(x)          # the kernel always writes it (the stem conv's wgrad is its only consumer)
+        lib().call("vca_bn_prelu_maxpool_bwd", dy, idx, xmax, x, dx, NF, H, W, C, mean, invstd, gamma.detach(), beta.detach(),
+                   prelu_w.detach(), 1 if ctx.training else 0, _bn_sums(ctx.key, 3 * C, 1), dgamma, dbeta, dprelu, 1 | (2 if fused else 0))
+        if fused or not any(wanted):
+            return (dx,) + (None,) * 10
+        return (dx, dgamma, dbeta, None, None, dprelu) + (None,) * 5
+
+
+def bn_prelu_maxpool_supported(x, C) -> bool:
+    cv = C // 8
+    return cfg.fuse_stem_pool and x.dtype == torch.bfloat16 and C % 8 == 0 and cv <= 256 and (cv & (cv - 1)) == 0
+
+
+def bn_prelu_maxpool(x, bn: torch.nn.Module, prelu_w):
+    """x (NF,H,W,C) raw stem-conv output -> (NF,OH,OW,C); `bn` as for bn_act."""
+    training = bn.training
+    if training and bn.num_batches_tracked is not None:
+        if cfg.deferred_counters is not None:
+            cfg.deferred_counters.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
+    pre = getattr(x, "_vca_bn_sums", None) if training else None
+    return BNPReluMaxPoolFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, prelu_w, training, float(bn.eps),
+                                  float(bn.momentum), None if pre is None else pre[0], 1 if pre is None else pre[1])
 
 
 def flush_deferred_counters():
