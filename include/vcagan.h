@@ -64,6 +64,11 @@ int vca_conv_tc_workspace(const ConvGeom* g, int kind);
 int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, float* ws, long long ws_bytes, cudaStream_t stream);
 /* forward conv that also ADDS the per-output-channel sum / sum of squares of y (as stored) into stats[0..Cout) / stats[Cout..2Cout)
    (fp64): the batch statistics of a BatchNorm that follows (generator.py:115-116, resnet.py:47-48); never split-K */
+/* inference forward with a fused epilogue: y = act(conv(x,w) * scale[c] + shift[c] + res * res_scale); act 0 none, 1 LeakyReLU(slope),
+   2 PReLU(prelu_w[Cout]), 3 ReLU; scale / shift / res may be null.  Eval-mode BatchNorm folded into the conv (test.py:126-141). */
+int vca_conv_fwd_tc_epi(const ConvGeom* g, const void* x, const void* wd, const float* scale, const float* shift, const void* res, float res_scale, int act, float slope, const float* prelu_w, void* y, cudaStream_t stream);
+/* scale[c] = gamma[c] / sqrt(running_var[c] + eps); shift[c] = beta[c] + (bias[c] - running_mean[c]) * scale[c]  (bias may be null) */
+int vca_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, const float* bias, int C, float eps, float* scale, float* shift, cudaStream_t stream);
 int vca_conv_fwd_tc_stats_supported(const ConvGeom* g);
 int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t stream);
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);

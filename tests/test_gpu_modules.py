@@ -310,3 +310,39 @@ def test_generator_train_mode_bf16_long_ragged(V, state_spec, golden, T, lens):
                 assert e_o <= 2.0 * e_r + 1e-2, (k, e_o, e_r)
     finally:
         V.set_precision("fp32")
+
+
+def test_eval_epilogue_fusion_matches_unfused(V, state_spec, golden):
+    """Inference path (test.py:126-141): eval-mode BatchNorm / activation / residual folded into the conv epilogues
+    (ops.conv_epi) and the fused stem tail against the separate kernels, bf16, on the golden inputs: the two differ only
+    by the intermediate bf16 roundings the fusion removes (<= 1e-2), and both stay inside the bf16 bound vs the reference."""
+    vid, mel, spec, noise = golden_inputs()
+    V.set_precision("bf16")
+    try:
+        outs = []
+        for fused in (False, True):
+            V.ops.cfg.fuse_eval_epilogue = fused
+            V.ops.cfg.fuse_stem_pool = fused
+            with torch.no_grad():
+                vf = build(V, state_spec, "v_front", False)
+                gen = build(V, state_spec, "gen", False); gen.fixed_noise = noise
+                post = build(V, state_spec, "post", False)
+                sd = build(V, state_spec, "s_dis", False)
+                n0 = V.lib().launches
+                phon, sent = vf(vid.cuda())
+                g = gen(sent, phon, [20, 13])
+                gs = post(g[2])
+                sy = sd(phon, mel.cuda())
+                torch.cuda.synchronize()
+                outs.append(([t.float().cpu() for t in (phon, sent, *g, gs, sy)], V.lib().launches - n0))
+        names = ("phon", "sent", "g1", "g2", "g3", "gs", "sync")
+        errs = {n: rel_l2(b, a) for n, a, b in zip(names, outs[0][0], outs[1][0])}
+        print("eval epilogue fusion: fused vs separate kernels", errs, "library launches", outs[0][1], "->", outs[1][1])
+        assert max(errs.values()) < 1e-2, errs
+        assert outs[1][1] < outs[0][1]
+        for n, key in (("phon", "eval_phon"), ("sent", "eval_sent"), ("g3", "eval_g3"), ("gs", "eval_gs")):
+            assert rel_l2(outs[1][0][names.index(n)], golden[key]) < BF16_TOL, n
+    finally:
+        V.ops.cfg.fuse_eval_epilogue = True
+        V.ops.cfg.fuse_stem_pool = True
+        V.set_precision("fp32")

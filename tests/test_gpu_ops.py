@@ -679,6 +679,8 @@ def test_bn_prelu_maxpool_fused(V, train):
         names = ("dx", "dgamma", "dbeta", "dprelu", "running_mean", "running_var")
         errs = {n: rel_l2(v, u) for n, u, v in zip(names, a[1:], b[1:])}
         print("fused stem tail vs bn_act + maxpool", train, errs)
-        assert errs["dx"] < 5e-3 and max(errs[k] for k in names[1:4]) < 1e-4 and max(errs[k] for k in names[4:]) < 1e-6, errs
+        # the separate path rounds the scattered pool gradient to bf16 before BatchNorm's backward reads it, the fused one
+        # does not: gradients agree to bf16 rounding (eps = 3.9e-3), forward values and running statistics exactly
+        assert max(errs[k] for k in names[:4]) < 5e-3 and max(errs[k] for k in names[4:]) < 1e-6, errs
     finally:
         V.set_precision("fp32")

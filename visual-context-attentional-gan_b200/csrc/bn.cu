@@ -142,6 +142,15 @@ __global__ void bn_finalize_fold_kernel(double* __restrict__ sums, long long R, 
   }
 }
 
+__global__ void bn_fold_kernel(const float* __restrict__ rm, const float* __restrict__ rv, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, const float* __restrict__ bias, int C, float eps,
+                               float* __restrict__ scale, float* __restrict__ shift) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] / sqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] + ((bias ? bias[c] : 0.f) - rm[c]) * sc;
+}
 __global__ void bn_eval_stats_kernel(const float* __restrict__ rm, const float* __restrict__ rv, int C, float eps,
                                      float* __restrict__ mean, float* __restrict__ invstd) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -549,6 +558,13 @@ int vca_bn_finalize_stats(double* sums, long long R, int C, int fold, float eps,
                           float* running_mean, float* running_var, cudaStream_t s) {
   VCA_CHECK_ARG(sums && mean && invstd && R > 0 && C > 0 && fold >= 1);
   bn_finalize_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, R, C, fold, eps, momentum, mean, invstd, running_mean, running_var);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+int vca_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, const float* bias, int C,
+                float eps, float* scale, float* shift, cudaStream_t s) {
+  VCA_CHECK_ARG(running_mean && running_var && gamma && beta && scale && shift && C > 0);
+  bn_fold_kernel<<<(C + 127) / 128, 128, 0, s>>>(running_mean, running_var, gamma, beta, bias, C, eps, scale, shift);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }

@@ -22,10 +22,10 @@ using namespace tc;
 
 // conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s);
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
 // conv_tc_hs.cu: halo-resident activations + streamed weights for 64..128 output channels (same return convention)
 int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s);
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
 
@@ -52,6 +52,8 @@ struct FwdParams {
   float* ws;                     // split-K only: fp32 [pixels][Cout] partial sums (red.add), finished by splitk_finish_kernel
   const float* bias;             // [Cout] or null
   double* stats;                 // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
+  EpiExtra ex;                   // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
+  int has_ex;
   bf16* y;
 };
 
@@ -179,7 +181,9 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (p.bias && co0 + c < p.Cout) {
+      if (p.has_ex) {
+        epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
+      } else if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
       }
@@ -380,11 +384,11 @@ int plan_splits(long long ctas, int taps) {
 
 int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
              const void* x, const void* wpk, const float* bias, void* y, cudaStream_t s, float* ws = nullptr,
-             size_t ws_bytes = 0, size_t* ws_need = nullptr, double* stats = nullptr) {
+             size_t ws_bytes = 0, size_t* ws_need = nullptr, double* stats = nullptr, const EpiExtra* ex = nullptr) {
   if (ws_need) *ws_need = 0;
   if (!ws_need) {
-    int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, s);
-    if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, s);
+    int r = conv_ws_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, ex, s);
+    if (r == 0) r = conv_hs_try(NF, IH, IW, Kdim, OH, OW, Nout, KH, KW, ph, pw, flip, x, wpk, bias, y, stats, ex, s);
     if (r != 0) return r < 0 ? r : VCA_OK;
   }
   FwdParams p;
@@ -411,6 +415,8 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   p.b_bytes = (uint32_t)bn * 128u;
   p.tmem_cols = pow2_cols(bn);
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
+  p.has_ex = ex != nullptr;
+  if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
   const size_t stage_bytes = A_STAGE_BYTES + (size_t)bn * 128;
   // Two CTAs per SM (100 KB each) hide each other's TMA latency on big grids.  A grid that cannot even fill the SMs
   // once (small feature maps of the discriminator heads) gets one deep pipeline per CTA instead: a stage is only
@@ -444,7 +450,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
     attr_set = true;
   }
   if (p.ws) {
-    if (stats) { vca_set_error("conv forward: BatchNorm statistics are not available on the split-K path"); return VCA_ERR_UNSUPPORTED; }
+    if (stats || ex) { vca_set_error("conv forward: statistics / fused epilogues are not available on the split-K path"); return VCA_ERR_UNSUPPORTED; }
     p.bias = nullptr;   // added by the finishing pass
     if (cudaMemsetAsync(ws, 0, need, s) != cudaSuccess) { vca_set_error("split-K workspace memset failed"); return VCA_ERR_CUDA; }
   }
@@ -500,6 +506,17 @@ int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const f
 int vca_conv_fwd_tc(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, cudaStream_t s) {
   return vca_conv_fwd_tc_ws(g, x, wd, bias, y, nullptr, 0, s);
 }
+// Inference forward with a fused epilogue:  y = act(conv(x, w) * scale[c] + shift[c] + res * res_scale)   (never split-K).
+//   scale / shift: per-output-channel fp32 (either may be null: 1 / 0) -- an eval-mode BatchNorm folded into the conv;
+//   res: bf16 tensor of y's shape or null;  act: 0 none, 1 LeakyReLU(slope), 2 PReLU(prelu_w[Cout]), 3 ReLU.
+int vca_conv_fwd_tc_epi(const ConvGeom* g, const void* x, const void* wd, const float* scale, const float* shift, const void* res,
+                        float res_scale, int act, float slope, const float* prelu_w, void* y, cudaStream_t s) {
+  VCA_CHECK_ARG(g && x && wd && y && vca_conv_tc_supported(g, 0) && act >= 0 && act <= 3 && (act != 2 || prelu_w));
+  VCA_CHECK_ARG(!res || (g->Cout % 8 == 0 && (reinterpret_cast<uintptr_t>(res) & 15) == 0));
+  EpiExtra ex{scale, (const bf16*)res, res_scale, act, slope, prelu_w};
+  return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, shift, y, s, nullptr, 0, nullptr,
+                  nullptr, &ex);
+}
 // 1 when vca_conv_fwd_tc_stats takes this geometry AND the statistics come (almost) for free: the weights-stationary
 // persistent kernel (<= 64 channels in and out: the stem, ResNet layer 1, the 40x150 / 80x300 generator stages -- the
 // large tensors, where the separate statistics pass costs most).  The streaming / halo-resident kernels can emit them too
@@ -508,7 +525,7 @@ int vca_conv_fwd_tc_stats_supported(const ConvGeom* g) {
   if (!g || !vca_conv_tc_supported(g, 0)) return 0;
   static double dummy;
   return conv_ws_try(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, nullptr, nullptr, nullptr, nullptr,
-                     &dummy, nullptr) == 1 ? 1 : 0;
+                     &dummy, nullptr, nullptr) == 1 ? 1 : 0;
 }
 // Forward convolution that also accumulates the per-output-channel sum and sum of squares of y (as stored, i.e. bf16
 // rounded) into stats[0 .. Cout) and stats[Cout .. 2 Cout) (fp64, ADDED to): the batch statistics of a BatchNorm that

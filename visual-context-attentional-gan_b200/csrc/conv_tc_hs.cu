@@ -35,6 +35,8 @@ struct HsParams {
   uint32_t a_stage_bytes, a_tx_bytes, w_tile_bytes, tmem_cols;
   const float* bias;
   double* stats;           // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
+  EpiExtra ex;             // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
+  int has_ex;
   bf16* y;
 };
 
@@ -168,7 +170,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_hs_kernel(const __grid_co
         for (int c = 0; c < p.BN; c += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * p.BN + c), v);
-          if (p.bias && co0 + c < p.Cout) {
+          if (p.has_ex) {
+            epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
+          } else if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
           }
@@ -220,7 +224,7 @@ bool choose_hs_tile(int H, int W, int KH, int KW, int& th, int& tw) {
 // Tries the halo-resident / streamed-weights kernel.  Returns 1 if it was launched, 0 if the geometry does not fit or
 // the streaming kernel is the better choice, negative on error.  Arguments as conv_tc.cu::fwd_like.
 int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s) {
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s) {
   if (g_hs_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
   if (taps < 4 || taps > 256 || KW > 32) return 0;
@@ -261,6 +265,8 @@ int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   p.tmem_cols = pow2_cols(2 * MT * bn);
   if (p.tmem_cols > 512) return 0;
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
+  p.has_ex = ex != nullptr;
+  if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
   const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sw * p.w_tile_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics
 
   CUtensorMap tmA, tmB;

@@ -40,6 +40,8 @@ struct WsParams {
   int base_off_mode;
   const float* bias;
   double* stats;           // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
+  EpiExtra ex;             // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
+  int has_ex;
   bf16* y;
 };
 
@@ -181,7 +183,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
         if (c >= p.BN) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
-        if (p.bias && co0 + c < p.Cout) {
+        if (p.has_ex) {
+          epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
+        } else if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
         }
@@ -245,7 +249,7 @@ void choose_ws_tile(int H, int W, int KH, int KW, int& th, int& tw) {
 // Tries the weights-stationary kernel.  Returns 1 if it was launched, 0 if the geometry does not fit (caller uses the
 // streaming kernel), negative on error.  Arguments as conv_tc.cu::fwd_like.
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                    const void* x, const void* wpk, const float* bias, void* y, double* stats, cudaStream_t s) {
+                    const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s) {
   // x == nullptr: dry run -- 1 when this kernel would take the geometry (and, with stats != nullptr, emit the statistics)
   if (g_ws_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
@@ -285,6 +289,8 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   if (!x) return 1;
   p.base_off_mode = g_ws_base_off;
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
+  p.has_ex = ex != nullptr;
+  if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
   const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics
 
   CUtensorMap tmA, tmB;

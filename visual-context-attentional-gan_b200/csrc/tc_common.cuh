@@ -143,6 +143,57 @@ __device__ __forceinline__ void epi_stats_flush(float* s_sum, float* s_sq, int B
   asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
+// ---- inference epilogue: y = act(acc * scale[c] + shift[c] + res * res_scale) ------------------------------------------
+// Eval-mode BatchNorm is a fixed per-channel affine map: it folds into the producing convolution as
+// scale / shift, the activation that follows and the residual add of a BasicBlock / the shortcut + 1/sqrt(2) of a GenResBlk
+// run on the accumulator row while it is in registers -- the separate normalisation / activation / add passes disappear.
+struct EpiExtra {
+  const float* scale;      // [Cout] or null (1)
+  const bf16* res;         // [pixels][Cout] (the output's layout) or null
+  float res_scale;
+  int act;                 // 0 none, 1 LeakyReLU(slope), 2 PReLU(prelu_w[c]), 3 ReLU
+  float slope;
+  const float* prelu_w;    // [Cout] (act == 2)
+};
+// v: accumulator values of channels [co, co + 16) of one output pixel; `shift` is the conv's bias pointer (or null);
+// res_row = res + pixel * Cout + co (dereferenced only when row_ok)
+__device__ __forceinline__ void epi_apply16(float (&v)[16], const EpiExtra& e, const float* shift, int co, int Cout, const bf16* res_row,
+                                            bool row_ok) {
+  if (co >= Cout) return;
+  const bool full = co + 16 <= Cout;
+  if (e.scale) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] *= (full || co + i < Cout) ? __ldg(e.scale + co + i) : 1.f;
+  }
+  if (shift) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] += (full || co + i < Cout) ? __ldg(shift + co + i) : 0.f;
+  }
+  if (e.res && row_ok) {
+    if (full) {
+      const uint4 r0 = *reinterpret_cast<const uint4*>(res_row), r1 = *reinterpret_cast<const uint4*>(res_row + 8);
+      const uint32_t w[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[2 * i] = fmaf(__uint_as_float(w[i] << 16), e.res_scale, v[2 * i]);
+        v[2 * i + 1] = fmaf(__uint_as_float(w[i] & 0xffff0000u), e.res_scale, v[2 * i + 1]);
+      }
+    } else {
+      for (int i = 0; i < 16 && co + i < Cout; ++i) v[i] = fmaf(__bfloat162float(res_row[i]), e.res_scale, v[i]);
+    }
+  }
+  if (e.act == 1) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * e.slope;
+  } else if (e.act == 2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * ((full || co + i < Cout) ? __ldg(e.prelu_w + co + i) : 0.f);
+  } else if (e.act == 3) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+}
+
 // ---- host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

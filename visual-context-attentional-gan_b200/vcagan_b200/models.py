@@ -73,8 +73,28 @@ class BasicBlock(nn.Module):
         self.stride = stride
         self._prelu = relu_type == 'prelu'
 
+    def _forward_eval_fused(self, x, act):
+        """inference: each conv carries its (eval-mode) BatchNorm, the activation and the residual add in its epilogue"""
+        pw1 = self.relu1.weight if self._prelu else None
+        pw2 = self.relu2.weight if self._prelu else None
+        c1, c2 = self.conv1, self.conv2
+        out = ops.conv_epi(x, c1.weight, None, c1.stride, c1.padding, bn=self.bn1, act=act, prelu_w=pw1)
+        if out is None:
+            return None
+        res = x
+        if self.downsample is not None:
+            d = self.downsample[0]
+            res = ops.conv_epi(x, d.weight, None, d.stride, d.padding, bn=self.downsample[1])
+            if res is None:
+                return None
+        return ops.conv_epi(out, c2.weight, None, c2.stride, c2.padding, bn=self.bn2, act=act, prelu_w=pw2, res=res)
+
     def forward(self, x):
         act = ACT_PRELU if self._prelu else ACT_RELU
+        if not self.training and ops.epi_ok(x) and (self.downsample is None or len(self.downsample) == 2):
+            y = self._forward_eval_fused(x, act)
+            if y is not None:
+                return y
         out = _conv(x, self.conv1, self.bn1)
         out = ops.bn_act(out, self.bn1, act, 0.0, self.relu1.weight if self._prelu else None)
         out = _conv(out, self.conv2, self.bn2)
@@ -265,6 +285,20 @@ class GenResBlk(nn.Module):
         r = ops.bn_act(x, self.norm1, ACT_LRELU, 0.2)
         if self.upsample:
             r = ops.upsample2(r)
+        if not self.training and ops.epi_ok(r) and not (const_channels and not self.upsample and cfg.rowconst):
+            # inference: norm2 + LeakyReLU ride in conv1's epilogue, the shortcut add and 1/sqrt(2) in conv2's
+            c1, c2 = self.conv1, self.conv2
+            r1 = ops.conv_epi(r, c1.weight, c1.bias, c1.stride, c1.padding, bn=self.norm2, act=ACT_LRELU, slope=0.2)
+            if r1 is not None:
+                s = ops.upsample2(x) if self.upsample else x
+                if self.learned_sc:
+                    s = _conv(s, self.conv1x1)
+                y = ops.conv_epi(r1, c2.weight, c2.bias, c2.stride, c2.padding, res=s, res_scale=INV_SQRT2, out_scale=INV_SQRT2)
+                if y is not None:
+                    return y
+                r = r1          # conv2 has no fused route: finish on the separate kernels
+                r = _conv(r, self.conv2)
+                return ops.add_scale(r, s, INV_SQRT2)
         if const_channels and not self.upsample and cfg.rowconst:
             r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding),
                                   zero_bias_grad=self.norm2.training)

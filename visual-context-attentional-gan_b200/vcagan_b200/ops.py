@@ -32,6 +32,7 @@ class Config:
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
+    fuse_eval_epilogue = True   # inference: eval-mode BatchNorm / activation / residual folded into the conv epilogue (conv_epi)
     fuse_stem_pool = True   # stem BatchNorm3d + PReLU + MaxPool3d as one pass over the raw conv output (bn_prelu_maxpool)
     fuse_bn_stats = True    # train-mode BatchNorm statistics come out of the producing conv's epilogue (vca_conv_fwd_tc_stats)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
@@ -542,6 +543,74 @@ def conv(x, w, bias=None, stride=(1, 1), pad=(0, 0), zero_bias_grad=False, bn=No
         if k == (1, 1) and pad == (0, 0):
             return _conv_bn(x[:, ::2, ::2, :].contiguous(), w, bias, (1, 1), (0, 0), zb, bn)   # slicing = data movement
     return _conv_bn(x, w, bias, stride, pad, zb, bn)
+
+
+# ---- inference: eval-mode BatchNorm / activation / residual folded into the conv epilogue (no autograd) -------------------
+def epi_ok(x) -> bool:
+    """The fused inference epilogues apply: bf16 tcgen05 path, and nothing asks for gradients."""
+    return cfg.fuse_eval_epilogue and cfg.use_tc and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+
+
+def _fold(bn, bias, C, device, out_scale=1.0):
+    """(scale, shift) fp32 [C] of `y * scale + shift` == out_scale * BN_eval(y + bias)   (bn may be None)."""
+    if bn is None:
+        if bias is None and out_scale == 1.0:
+            return None, None
+        scale = torch.full((C,), float(out_scale), dtype=torch.float32, device=device) if out_scale != 1.0 else None
+        shift = None if bias is None else (bias.detach().float() * out_scale if out_scale != 1.0 else bias.detach().float())
+        return scale, shift
+    scale = torch.empty(C, dtype=torch.float32, device=device)
+    shift = torch.empty(C, dtype=torch.float32, device=device)
+    lib().call("vca_bn_fold", bn.running_mean, bn.running_var, bn.weight.detach(), bn.bias.detach(),
+               None if bias is None else bias.detach().float(), C, float(bn.eps), scale, shift)
+    if out_scale != 1.0:
+        scale, shift = scale * out_scale, shift * out_scale
+    return scale, shift
+
+
+def _conv_epi_raw(x, w, scale, shift, res, res_scale, act, slope, prelu_w, pad):
+    g, oshape = _geom(x.shape, w.shape, (1, 1), pad)
+    if not _tc_ok(g, 0, x.dtype):
+        return None
+    _, wd = _packed(w, x.dtype)
+    y = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    lib().call("vca_conv_fwd_tc_epi", g, _c(x), wd, scale, shift, None if res is None else _c(res), float(res_scale), int(act), float(slope),
+               None if prelu_w is None else prelu_w.detach().float(), y)
+    return y
+
+
+def conv_epi(x, w, bias=None, stride=(1, 1), pad=(0, 0), bn=None, act=ACT_NONE, slope=0.0, prelu_w=None, res=None, res_scale=1.0,
+             out_scale=1.0):
+    """Inference only:  act(out_scale * BN_eval(conv(x, w) + bias) + res_scale * res)  in ONE kernel (the conv's epilogue);
+    returns None when the geometry has no tcgen05 route (the caller then runs the separate kernels).  Same routes as
+    conv(): pixel-pair merge for 32 channels, space-to-depth / slicing for stride 2."""
+    stride, pad = tuple(stride), tuple(pad)
+    Cout = w.shape[0]
+    scale, shift = _fold(bn, bias, Cout, x.device, out_scale)
+    if (cfg.pair_merge and x.dim() == 4 and stride == (1, 1) and w.dim() == 4 and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1]
+            and w.shape[1] in cfg.pair_merge_channels and pad == (2, 2) and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0
+            and x.is_contiguous()):
+        N, H, W, C = x.shape
+        w2 = PairExpandFn.apply(w)
+        dup = lambda t: None if t is None else torch.cat([t, t])      # noqa: E731  (output channels are [pair position][channel])
+        y2 = _conv_epi_raw(x.view(N, H, W // 2, 2 * C), w2, dup(scale), dup(shift), None if res is None else _c(res).view(N, H, W // 2, 2 * Cout),
+                           res_scale, act, slope, dup(None if prelu_w is None else prelu_w.detach().float()), (w.shape[2] // 2, 1))
+        return None if y2 is None else y2.view(N, H, W, Cout)
+    if stride == (2, 2) and x.dim() == 4 and x.shape[-1] % 8 == 0:
+        k = tuple(w.shape[2:])
+        if k == (3, 3) and pad == (1, 1):
+            N, H, W, C = x.shape
+            OH, OW = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+            xs = S2DFn.apply(x, OH + 1, OW + 1)
+            wp = torch.nn.functional.pad(w, (0, 1, 0, 1))
+            w2 = wp.view(Cout, C, 2, 2, 2, 2).permute(0, 3, 5, 1, 2, 4).reshape(Cout, 4 * C, 2, 2)
+            return _conv_epi_raw(xs, w2, scale, shift, res, res_scale, act, slope, prelu_w, (0, 0))
+        if k == (1, 1) and pad == (0, 0):
+            return _conv_epi_raw(x[:, ::2, ::2, :].contiguous(), w, scale, shift, res, res_scale, act, slope, prelu_w, (0, 0))
+        return None
+    if any(s_ != 1 for s_ in stride) or w.shape[0] % 8 != 0:
+        return None
+    return _conv_epi_raw(x, w, scale, shift, res, res_scale, act, slope, prelu_w, pad)
 
 
 def stem_conv(vid, w, bn=None):
