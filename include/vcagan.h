@@ -158,7 +158,7 @@ int vca_l1_bwd(int dtype, const void* a, const void* b, const float* g, long lon
 int vca_adam_step(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step, float gscale, cudaStream_t stream);
 int vca_rng(int dtype, void* out, long long n, unsigned long long seed, unsigned long long offset, int mode, float param, cudaStream_t stream);
 /* CUDA-graph-replayable variants: step counter, learning rate / RNG stream position live in device memory */
-int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, int* step_dev, float gscale, cudaStream_t stream);
+int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, const float* lr_dev, float beta1, float beta2, float eps, float weight_decay, int* step_dev, float gscale, int bump, cudaStream_t stream);
 int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsigned long long* ctr_dev, int mode, float param, cudaStream_t stream);
 
 /* ---- Griffin-Lim STFT / ISTFT (src/data/stft.py:70-129, src/data/audio_processing.py:51-68) ---------------------- */

@@ -175,7 +175,7 @@ def test_stream_branches_match_serial_step():
             tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)       # D phase incl. backward, no optimizer yet
             torch.cuda.synchronize()
             gd = tr.D.grad.clone()
-            tr._phase_g(); out = tr._phase_end()
+            tr._phase_g_pre(); tr._phase_g(); tr._phase_g2(); tr._phase_end_a(); out = tr._phase_end_b()
             torch.cuda.synchronize()
             res.append((gd, tr.G.grad.clone(), {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
             del tr
@@ -285,6 +285,7 @@ def test_split_g_backward_matches_single_backward():
             tr.split_g_backward = split
             tr.G.zero_grad()
             tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)
+            tr._phase_g_pre()
             tr._phase_g()
             if split:
                 torch.cuda.synchronize()
@@ -293,7 +294,8 @@ def test_split_g_backward_matches_single_backward():
                 tr._phase_g2()
             torch.cuda.synchronize()
             gg = tr.G.grad.clone()
-            out = tr._phase_end()
+            tr._phase_end_a()        # with a split backward: Adam on the gen + post slice, then (_b) on the v_front slice
+            out = tr._phase_end_b()
             torch.cuda.synchronize()
             res.append((gg, {k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}))
             del tr

@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
     const int n = n0 + in, oh = oh0 + ih, ow = ow0 + iw;
     const bool row_ok = (r < p.tn * hw) && n < p.NF && oh < p.OH && ow < p.OW;
     bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
+    if (p.has_ex && p.ex.res && row_ok) epi_prefetch_row(p.ex.res + (yrow - p.y), min(p.BN, p.Cout - co0) * 2);
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (p.ws) {

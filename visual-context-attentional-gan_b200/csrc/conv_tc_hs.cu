@@ -160,6 +160,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_hs_kernel(const __grid_co
       const int tw_i = t % p.tiles_w; t /= p.tiles_w;
       const int hg = t % p.groups_h; const int n = t / p.groups_h;
       const int acc = it & 1;
+      if (p.has_ex && p.ex.res) {
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int oh = (hg * MT + mt) * p.th + r, ow = tw_i * p.tw + wq;
+          if (r < p.th && wq < p.tw && oh < p.OH && ow < p.OW)
+            epi_prefetch_row(p.ex.res + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0, min(p.BN, p.Cout - co0) * 2);
+        }
+      }
       mbar_wait(&t_full[acc], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll

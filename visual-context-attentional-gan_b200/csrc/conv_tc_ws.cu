@@ -45,6 +45,10 @@ struct WsParams {
   bf16* y;
 };
 
+// MODE 0: plain (+bias) epilogue; 1: + BatchNorm statistics; 2: inference epilogue (scale / shift / residual / activation).
+// A template so that each variant gets its own register allocation (the statistics keep 128 running sums per thread, the
+// inference epilogue prefetches the residual row): none of it is paid for by the plain forward / dgrad launches.
+template <int MODE>
 __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB, const WsParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -62,7 +66,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
   uint32_t* s_arel = tmem_slot + 4;   // [taps <= 256] per-tap row shift of the A window, in 16-byte units
   float* s_sum = (float*)(s_arel + 256);   // [BN] + [BN]: BatchNorm statistics of the current tile
   float* s_sq = s_sum + p.BN;
-  if (p.stats) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
+  if (MODE == 1) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.BN;
@@ -164,9 +168,10 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
     int it = 0;
     // BatchNorm statistics (BN <= 64 whenever they are requested): every thread keeps running sums of ITS tile row's
     // 64 columns over all tiles of this persistent CTA -- two FMAs per value; the cross-row reduction happens once, below
-    float rs[64], rq[64];
+    constexpr int NR = MODE == 1 ? 64 : 1;
+    float rs[NR], rq[NR];
 #pragma unroll
-    for (int i = 0; i < 64; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
+    for (int i = 0; i < NR; ++i) { rs[i] = 0.f; rq[i] = 0.f; }
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       int t = tile;
       const int tw_i = t % p.tiles_w; t /= p.tiles_w;
@@ -175,6 +180,21 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       const bool row_ok = r < p.th && wq < p.tw && oh < p.OH && ow < p.OW;
       bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
       const int acc = it & 1;
+      // inference epilogue: the residual row (BN <= 64 channels, 128 B) is fetched BEFORE waiting for the accumulator, so
+      // its DRAM latency hides under this tile's MMAs instead of stalling the epilogue (which would otherwise become the
+      // critical path of these short-K layers)
+      constexpr int NRES = MODE == 2 ? 8 : 1;
+      uint4 rres[NRES];
+      bool res_pref = false;
+      if (MODE == 2) {
+        res_pref = p.ex.res != nullptr && row_ok && co0 + p.BN <= p.Cout && p.BN <= 64;
+        if (res_pref) {
+          const bf16* rrow = p.ex.res + (yrow - p.y);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (j * 8 < p.BN) rres[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
+        }
+      }
       mbar_wait(&t_full[acc], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
 #pragma unroll
@@ -183,15 +203,31 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
         if (c >= p.BN) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
-        if (p.has_ex) {
-          epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
+        if (MODE == 2) {
+          EpiExtra e = p.ex;
+          if (res_pref && cc < 4) {
+            // add the prefetched residual here; epi_apply16 then sees no residual pointer
+            const uint4 r0 = rres[(2 * cc) % NRES], r1 = rres[(2 * cc + 1) % NRES];
+            const uint32_t w8[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            if (e.scale) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= __ldg(e.scale + co0 + c + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[2 * i] = fmaf(__uint_as_float(w8[i] << 16), e.res_scale, v[2 * i]);
+              v[2 * i + 1] = fmaf(__uint_as_float(w8[i] & 0xffff0000u), e.res_scale, v[2 * i + 1]);
+            }
+            e.scale = nullptr; e.res = nullptr;
+          }
+          epi_apply16(v, e, p.bias, co0 + c, p.Cout, e.res ? e.res + (yrow - p.y) + c : nullptr, row_ok);
         } else if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
         }
-        if (p.stats && cc < 4 && row_ok) {
+        if (MODE == 1 && cc < 4 && row_ok) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { const float t = bf16_round(v[i]); rs[(cc & 3) * 16 + i] += t; rq[(cc & 3) * 16 + i] = fmaf(t, t, rq[(cc & 3) * 16 + i]); }
+          for (int i = 0; i < 16; ++i) { const float t = bf16_round(v[i]); rs[((cc & 3) * 16 + i) % NR] += t; rq[((cc & 3) * 16 + i) % NR] = fmaf(t, t, rq[((cc & 3) * 16 + i) % NR]); }
         }
         if (row_ok && co0 + c < p.Cout) {
           if (co0 + c + 16 <= p.Cout) {
@@ -211,13 +247,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
     }
     // BatchNorm statistics: the shared accumulators collect ALL tiles of this persistent CTA (fp32 over a few thousand
     // rows), published once -- a flush per tile would put tens of thousands of fp64 atomics on each channel's address
-    if (p.stats) {
+    if (MODE == 1) {
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         if (cc * 16 < p.BN) {
           float a[16], b[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) { a[i] = rs[cc * 16 + i]; b[i] = rq[cc * 16 + i]; }
+          for (int i = 0; i < 16; ++i) { a[i] = rs[(cc * 16 + i) % NR]; b[i] = rq[(cc * 16 + i) % NR]; }
           const float sa = colsum16(a, lane), sb = colsum16(b, lane);
           const int col = epi_col(lane);
           if (!(lane & 1) && co0 + cc * 16 + col < p.Cout) { atomicAdd(s_sum + cc * 16 + col, sa); atomicAdd(s_sq + cc * 16 + col, sb); }
@@ -301,14 +337,18 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   rc = make_map(&tmB, wpk, 3, dB, bB); if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(conv_tc_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(conv_tc_ws_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_ws_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_ws_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       vca_set_error("cudaFuncSetAttribute(conv_tc_ws_kernel) failed"); return VCA_ERR_CUDA;
     }
     attr_set = true;
   }
   int gx = vca_num_sms() / n_tiles; if (gx < 1) gx = 1; if (gx > p.num_tiles) gx = p.num_tiles;
   dim3 grid((unsigned)gx, (unsigned)n_tiles, 1);
-  conv_tc_ws_kernel<<<grid, 192, smem, s>>>(tmA, tmB, p);
+  if (p.stats) conv_tc_ws_kernel<1><<<grid, 192, smem, s>>>(tmA, tmB, p);
+  else if (p.has_ex) conv_tc_ws_kernel<2><<<grid, 192, smem, s>>>(tmA, tmB, p);
+  else conv_tc_ws_kernel<0><<<grid, 192, smem, s>>>(tmA, tmB, p);
   VCA_LAUNCH_CHECK();
   return 1;
 }

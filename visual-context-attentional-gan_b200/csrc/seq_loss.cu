@@ -492,10 +492,12 @@ int vca_adam_step(float* p, const float* g, float* m, float* v, float* vmax, lon
 // Same, with the step counter AND the learning rate resident on the device: *step_dev is incremented, then used for
 // the bias corrections; *lr_dev is read by the kernel.  This form can be captured in a CUDA graph and replayed (the
 // host never sees the step number, and an lr schedule only has to write one float between replays).
+// bump = 0: *step_dev is used as it is (the second of two calls that update disjoint slices of one parameter group in the
+// same optimizer step, e.g. while the all-reduce of the other slice's gradients is still running).
 int vca_adam_step_dev(float* p, const float* g, float* m, float* v, float* vmax, long long n, const float* lr_dev, float beta1,
-                      float beta2, float eps, float weight_decay, int* step_dev, float gscale, cudaStream_t s) {
+                      float beta2, float eps, float weight_decay, int* step_dev, float gscale, int bump, cudaStream_t s) {
   VCA_CHECK_ARG(p && g && m && v && n > 0 && step_dev && lr_dev);
-  counter_add_i32_kernel<<<1, 1, 0, s>>>(step_dev, 1);
+  if (bump) counter_add_i32_kernel<<<1, 1, 0, s>>>(step_dev, 1);
   adam_kernel<<<vca_grid_1d(n, 256, 4), 256, 0, s>>>(p, g, m, v, vmax, n, 0.f, beta1, beta2, eps, weight_decay, 1.f, 1.f, gscale,
                                                      step_dev, lr_dev);
   VCA_LAUNCH_CHECK();

@@ -194,6 +194,14 @@ __device__ __forceinline__ void epi_apply16(float (&v)[16], const EpiExtra& e, c
   }
 }
 
+// Residual rows are read by the epilogue threads with a dependent load per 16-column chunk; issued only after the
+// accumulator is complete, their DRAM latency would sit on the critical path.  Called BEFORE waiting for the accumulator, this
+// pulls the row (nbytes, from 128-byte aligned-ish `row`) into L2 while the MMAs are still running.
+__device__ __forceinline__ void epi_prefetch_row(const bf16* row, int nbytes) {
+  const char* p = reinterpret_cast<const char*>(row);
+  for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + o));
+}
+
 // ---- host ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,

@@ -150,6 +150,12 @@ def _packed(w: torch.Tensor, dtype: torch.dtype):
         hit = _pack_cache.get(key)
         if hit is not None and hit[0] == tag and hit[3]() is base:   # same live Parameter object, not a recycled address
             return hit[1], hit[2]
+    else:
+        # derived weights (space-to-depth / pixel-pair / zero-padded forms: fresh tensors every forward): the forward's pack is
+        # remembered on the tensor object itself, which autograd hands back to the dgrad of the same convolution
+        pk = getattr(w, "_vca_pk", None)
+        if pk is not None and pk[0] == (w._version, dtype):
+            return pk[1], pk[2]
     wc = _c(w.detach())
     if wc.dtype != torch.float32:
         wc = wc.float()
@@ -163,6 +169,8 @@ def _packed(w: torch.Tensor, dtype: torch.dtype):
         # parameter's own storage in [Cout][Cin][taps] order
         direct = wc.data_ptr() == w.data_ptr() and w.dtype == torch.float32
         _pack_cache[key] = (tag, wf, wd, weakref.ref(base), direct, (cout, cin, taps))
+    else:
+        w._vca_pk = ((w._version, dtype), wf, wd)
     return wf, wd
 
 

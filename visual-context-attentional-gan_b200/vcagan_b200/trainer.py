@@ -84,9 +84,13 @@ class FusedAdam:
     def zero_grad(self):
         self.g.zero_grad()
 
-    def step(self, grad_scale: float = 1.0):
-        lib().call("vca_adam_step_dev", self.g.flat, self.g.grad, self.m, self.v, self.vmax, self.g.numel, self.lr_dev, self.betas[0],
-                   self.betas[1], self.eps, self.wd, self.t_dev, grad_scale)
+    def step(self, grad_scale: float = 1.0, lo: int = 0, hi: Optional[int] = None, bump: bool = True):
+        """One Adam step over flat[lo:hi] (default: the whole group).  A step may be taken in several slices -- the first
+        with bump=True (it advances the step counter), the others with bump=False."""
+        hi = self.g.numel if hi is None else hi
+        vmax = None if self.vmax is None else self.vmax[lo:hi]
+        lib().call("vca_adam_step_dev", self.g.flat[lo:hi], self.g.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], vmax, hi - lo, self.lr_dev,
+                   self.betas[0], self.betas[1], self.eps, self.wd, self.t_dev, grad_scale, 1 if bump else 0)
         self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
 
 
@@ -193,8 +197,11 @@ class Trainer:
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             dp.allreduce_flat(group.grad[lo:group.numel if hi is None else hi], self.pg, bucket_elems)
+            done = torch.cuda.Event()
+            done.record()
         if wait:
             cur.wait_stream(self.comm_stream)
+        return done
 
     def _branches(self, fns):
         """Run independent sub-graphs concurrently: fns[0] on the current stream, the others on side streams that fork
@@ -256,18 +263,48 @@ class Trainer:
     # -- one step -------------------------------------------------------------------------------------------------
     def step(self, vid, mel, spec, vid_len, noise=None):
         """vid (B,1,T,112,112), mel (B,1,80,4T), spec (B,1,321,4T) device fp32; vid_len int32 device tensor or list."""
-        self._phase_d(vid, mel, spec, vid_len, noise)
-        self._allreduce(self.D)
-        self._phase_g()
-        if self.split_g_backward:
-            self._allreduce(self.G, lo=self._vf_numel, wait=False)        # gen + post, underneath ...
-            self._phase_g2()                                              # ... the visual front-end's backward
-            self._allreduce(self.G, hi=self._vf_numel)
-        else:
-            self._allreduce(self.G)
-        out = self._phase_end()
+        phases = [lambda: self._phase_d(vid, mel, spec, vid_len, noise), self._phase_g_pre, self._phase_g, self._phase_g2,
+                  self._phase_end_a, self._phase_end_b]
+        out = self._run_schedule(lambda i: phases[i]())
         self._build_pack_plans()
         return out
+
+    def _run_schedule(self, run):
+        """The step as six phases with the data-parallel exchanges between them; `run(i)` executes phase i (eagerly, or by
+        replaying the CUDA graph it was captured into).  Every all-reduce is issued on the comm stream and only waited for
+        where its result is needed, so each one runs underneath independent work:
+          0 D phase | all-reduce D grads ~ 1 Postnet forward + reconstruction losses (no discriminator involved)
+          2 D optimizer, G phase down to the generator's leaves | all-reduce gen + post grads ~ 3 visual front-end backward
+          | all-reduce v_front grads ~ 4 Adam on gen + post | 5 Adam on v_front, weight re-pack.
+        Single-GPU runs have no exchanges; phases 1+2 and 4+5 then share a graph (3 graphs per step)."""
+        cur = torch.cuda.current_stream()
+        multi = self.world > 1
+        run(0)
+        ev = self._allreduce(self.D, wait=False) if multi else None
+        run(1)
+        if multi:
+            cur.wait_event(ev)
+        run(2)
+        if self.split_g_backward:
+            e1 = self._allreduce(self.G, lo=self._vf_numel, wait=False) if multi else None      # gen + post
+            run(3)
+            e2 = self._allreduce(self.G, hi=self._vf_numel, wait=False) if multi else None      # v_front
+            if multi:
+                cur.wait_event(e1)
+            run(4)
+            if multi:
+                cur.wait_event(e2)
+        else:
+            if multi:
+                self._allreduce(self.G)
+            run(4)
+        return run(5)
+
+    def _phase_groups(self):
+        """phases captured together into one CUDA graph"""
+        if self.world > 1:
+            return [[0], [1], [2], [3], [4], [5]] if self.split_g_backward else [[0], [1], [2], [4, 5]]
+        return [[0], [1, 2, 3], [4, 5]] if self.split_g_backward else [[0], [1, 2], [4, 5]]
 
     def _phase_d(self, vid, mel, spec, vid_len, noise=None):
         """forward of v_front + generator, the whole D phase and its backward (train.py:168-210)."""
@@ -362,6 +399,17 @@ class Trainer:
                         out=dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
                                  fake_loss=fake_loss.detach(), grad_pen=torch.stack([t.detach() for t in gp])))
 
+    def _phase_g_pre(self):
+        """The part of the G phase that involves no discriminator (train.py:215, 226-229): Postnet forward and the four L1
+        reconstruction terms.  In data-parallel runs it executes underneath the all-reduce of the D gradients."""
+        st, m = self._st, self.mods
+        g = st["g"]
+        gs = m["post"](g[2])
+        k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
+        recon = (ops.l1_mean(g[0], st["mel1"], k) + ops.l1_mean(g[1], st["mel2"], k) + ops.l1_mean(g[2], st["mel"], k)) / 3 \
+            + ops.l1_mean(gs, st["spec"])
+        st["gs"], st["recon"] = gs, recon
+
     def _phase_g(self):
         """D optimizer step, then the G phase against the updated discriminators and its backward (train.py:211-236)."""
         st, m = self._st, self.mods
@@ -370,15 +418,12 @@ class Trainer:
         self.d_opt.step(1.0 / self.world)
         if self._pack_d is not None:
             self._pack_d.run()
-        gs = m["post"](g[2])
+        gs, recon = st["gs"], st["recon"]
         res = self._branches([lambda: dis[2](g[2], sdet, T), lambda: dis[1](g[1], sdet, T), lambda: dis[0](g[0], sdet, T),
                               lambda: m["s_dis"](phon.detach(), g[2], True).mean()])
         ug, cg = [res[2][0], res[1][0], res[0][0]], [res[2][1], res[1][1], res[0][1]]
         g_sync = res[3]
         g_adv = sum(M.gan_loss(x, True) for x in ug + cg) / 3
-        k = 1.0 if self.lrs else DENORM_SCALE                              # GRID: L1 on de-normalised mels
-        recon = (ops.l1_mean(g[0], st["mel1"], k) + ops.l1_mean(g[1], st["mel2"], k) + ops.l1_mean(g[2], st["mel"], k)) / 3 \
-            + ops.l1_mean(gs, st["spec"])
         gen_loss = g_adv + g_sync + 50.0 * recon
         if self._gru_stream is not None and not self.split_g_backward:
             self._br_used.append(self._gru_stream)       # the GRU's backward kernels will run there: join it afterwards
@@ -398,14 +443,25 @@ class Trainer:
         """Second half of a split G backward: the visual front-end, fed with d(gen_loss)/d(phon, sent) from the
         generator's leaves and d(dis_loss)/d(phon) from the D phase (autograd sums the two roots on phon)."""
         st = self._st
+        if not self.split_g_backward:
+            return
         if self._gru_stream is not None:
             self._br_used.append(self._gru_stream)
         torch.autograd.backward([st["phon"], st["phon"], st["sent"]],
                                 [st["phon_g"].grad, st["phon_leaf"].grad, st["sent_g"].grad], inputs=self._vf_params)
         self._join_branches()
 
-    def _phase_end(self):
-        self.g_opt.step(1.0 / self.world)
+    def _phase_end_a(self):
+        """G optimizer: with a split backward the gen + post slice first (its gradients were reduced long ago), so that the
+        v_front slice's all-reduce finishes underneath it; otherwise the whole group."""
+        if self.split_g_backward:
+            self.g_opt.step(1.0 / self.world, lo=self._vf_numel, bump=True)
+        else:
+            self.g_opt.step(1.0 / self.world)
+
+    def _phase_end_b(self):
+        if self.split_g_backward:
+            self.g_opt.step(1.0 / self.world, lo=0, hi=self._vf_numel, bump=False)
         if self._pack_g is not None:
             self._pack_g.run()
         out, self._st = self._st["out"], None
@@ -421,8 +477,8 @@ class Trainer:
 
     # -- CUDA-graph replay of the step ----------------------------------------------------------------------------
     def capture(self, vid, mel, spec, vid_len, warmup=3, noise=None):
-        """Capture the step into three CUDA graphs (D phase | G phase | G optimizer) sharing one memory pool; the
-        gradient all-reduces run between them.  Everything that changes from step to step lives in device memory
+        """Capture the step into CUDA graphs sharing one memory pool (3 on one GPU: D phase | G phase | G optimizer; 6 in
+        data-parallel runs, see _run_schedule); the gradient all-reduces run between them.  Everything that changes from step to step lives in device memory
         (Adam step counters, Philox stream positions, BN buffers), so `replay` needs no host-side state.
         `vid_len` must be an int32 device tensor.  Inputs are copied into static buffers on every replay."""
         assert torch.is_tensor(vid_len) and vid_len.is_cuda, "vid_len must be a device tensor for graph capture"
@@ -437,21 +493,22 @@ class Trainer:
         torch.cuda.synchronize()
         ops.clear_pack_cache(keep=(self._pack_g, self._pack_d))   # every other weight (re)pack must be recorded inside the graphs
         pool = torch.cuda.graph_pool_handle()
-        self._graphs = [torch.cuda.CUDAGraph() for _ in range(4 if self.split_g_backward else 3)]
+        groups = self._phase_groups()
+        self._graphs = [torch.cuda.CUDAGraph() for _ in groups]
+        self._graph_of = {grp[0]: i for i, grp in enumerate(groups)}      # first phase of a group -> its graph
         n0 = lib().launches
         # The critical path (main chain + discriminator branches) is captured on high-priority streams, the
         # parameter-gradient side streams keep the default (lowest) priority: when both have CTAs pending, the SMs
         # go to the chain the step is waiting for.
         cap = torch.cuda.Stream(device=self.device, priority=-1)
-        with torch.cuda.graph(self._graphs[0], pool=pool, stream=cap):
-            self._phase_d(*self._sin, noise=self._snoise)
-        with torch.cuda.graph(self._graphs[1], pool=pool, stream=cap):
-            self._phase_g()
-        if self.split_g_backward:
-            with torch.cuda.graph(self._graphs[2], pool=pool, stream=cap):
-                self._phase_g2()
-        with torch.cuda.graph(self._graphs[-1], pool=pool, stream=cap):
-            self._sout = self._phase_end()
+        phases = [lambda: self._phase_d(*self._sin, noise=self._snoise), self._phase_g_pre, self._phase_g, self._phase_g2,
+                  self._phase_end_a, self._phase_end_b]
+        for gi, grp in enumerate(groups):
+            with torch.cuda.graph(self._graphs[gi], pool=pool, stream=cap):
+                for i in grp:
+                    r = phases[i]()
+                    if i == 5:
+                        self._sout = r
         self.launches_per_step = lib().launches - n0
         return self
 
@@ -460,17 +517,12 @@ class Trainer:
         for dst, src in zip(self._sin, (vid, mel, spec, vid_len)):
             if src is not None:
                 dst.copy_(src, non_blocking=True)
-        self._graphs[0].replay()
-        self._allreduce(self.D)
-        self._graphs[1].replay()
-        if self.split_g_backward:
-            self._allreduce(self.G, lo=self._vf_numel, wait=False)
-            self._graphs[2].replay()
-            self._allreduce(self.G, hi=self._vf_numel)
-        else:
-            self._allreduce(self.G)
-        self._graphs[-1].replay()
-        return self._sout
+        def run(i):
+            gi = self._graph_of.get(i)
+            if gi is not None:
+                self._graphs[gi].replay()
+            return self._sout if i == 5 else None
+        return self._run_schedule(run)
 
     # -- pipelined input feed: the host->device copy of step i+1 runs on a copy stream underneath step i ------------
     def stage_inputs(self, vid, mel, spec):
