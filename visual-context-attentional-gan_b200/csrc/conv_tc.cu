@@ -178,13 +178,17 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
             if (co0 + c + i < p.Cout) atomicAdd(wrow + c + i, v[i]);
         }
       }
+    } else if (p.has_ex) {
+      // inference epilogue (scale / shift / residual / activation), 64 columns at a time
+      const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
+      for (int c = 0; c < p.BN; c += 64)
+        epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, p.ex, p.bias, co0 + c, p.BN - c, p.Cout, yrow + c,
+                    rrow ? rrow + c : nullptr, row_ok);
     } else {
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (p.has_ex) {
-        epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
-      } else if (p.bias && co0 + c < p.Cout) {
+      if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
       }

@@ -175,12 +175,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_hs_kernel(const __grid_co
         const int oh = (hg * MT + mt) * p.th + r, ow = tw_i * p.tw + wq;
         const bool row_ok = r < p.th && wq < p.tw && oh < p.OH && ow < p.OW;
         bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
+        if (p.has_ex) {
+          const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
+          for (int c = 0; c < p.BN; c += 64)
+            epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * p.BN + c), p.ex, p.bias, co0 + c, p.BN - c,
+                        p.Cout, yrow + c, rrow ? rrow + c : nullptr, row_ok);
+          continue;
+        }
         for (int c = 0; c < p.BN; c += 16) {
           float v[16];
           tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * p.BN + c), v);
-          if (p.has_ex) {
-            epi_apply16(v, p.ex, p.bias, co0 + c, p.Cout, p.ex.res ? p.ex.res + (yrow - p.y) + c : nullptr, row_ok);
-          } else if (p.bias && co0 + c < p.Cout) {
+          if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
           }

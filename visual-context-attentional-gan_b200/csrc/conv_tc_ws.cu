@@ -180,48 +180,22 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       const bool row_ok = r < p.th && wq < p.tw && oh < p.OH && ow < p.OW;
       bf16* yrow = p.y + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
       const int acc = it & 1;
-      // inference epilogue: the residual row (BN <= 64 channels, 128 B) is fetched BEFORE waiting for the accumulator, so
-      // its DRAM latency hides under this tile's MMAs instead of stalling the epilogue (which would otherwise become the
-      // critical path of these short-K layers)
-      constexpr int NRES = MODE == 2 ? 8 : 1;
-      uint4 rres[NRES];
-      bool res_pref = false;
-      if (MODE == 2) {
-        res_pref = p.ex.res != nullptr && row_ok && co0 + p.BN <= p.Cout && p.BN <= 64;
-        if (res_pref) {
-          const bf16* rrow = p.ex.res + (yrow - p.y);
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j * 8 < p.BN) rres[j] = *reinterpret_cast<const uint4*>(rrow + j * 8);
-        }
-      }
+      if (MODE == 2 && p.ex.res && row_ok) epi_prefetch_row(p.ex.res + (yrow - p.y), min(p.BN, p.Cout - co0) * 2);
       mbar_wait(&t_full[acc], (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
+      if (MODE == 2) {
+        const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
+        for (int c = 0; c < p.BN; c += 64)
+          epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), p.ex, p.bias, co0 + c, p.BN - c, p.Cout,
+                      yrow + c, rrow ? rrow + c : nullptr, row_ok);
+      } else
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) {
         const int c = cc * 16;
         if (c >= p.BN) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
-        if (MODE == 2) {
-          EpiExtra e = p.ex;
-          if (res_pref && cc < 4) {
-            // add the prefetched residual here; epi_apply16 then sees no residual pointer
-            const uint4 r0 = rres[(2 * cc) % NRES], r1 = rres[(2 * cc + 1) % NRES];
-            const uint32_t w8[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-            if (e.scale) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= __ldg(e.scale + co0 + c + i);
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[2 * i] = fmaf(__uint_as_float(w8[i] << 16), e.res_scale, v[2 * i]);
-              v[2 * i + 1] = fmaf(__uint_as_float(w8[i] & 0xffff0000u), e.res_scale, v[2 * i + 1]);
-            }
-            e.scale = nullptr; e.res = nullptr;
-          }
-          epi_apply16(v, e, p.bias, co0 + c, p.Cout, e.res ? e.res + (yrow - p.y) + c : nullptr, row_ok);
-        } else if (p.bias && co0 + c < p.Cout) {
+        if (p.bias && co0 + c < p.Cout) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
         }

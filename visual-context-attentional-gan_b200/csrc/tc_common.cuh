@@ -194,6 +194,55 @@ __device__ __forceinline__ void epi_apply16(float (&v)[16], const EpiExtra& e, c
   }
 }
 
+// One 64-column group of the inference epilogue for this thread's output row: the residual's 128 bytes are requested with
+// eight back-to-back 16-byte loads BEFORE the accumulator columns are read, so their latency is paid once per group (and
+// overlaps the tcgen05.ld's) instead of once per 16-column chunk.  taddr = TMEM address of the group's first column (this
+// thread's lane); co = output channel of that column; bn_left = columns of the CTA's tile from there on.
+__device__ __forceinline__ void epi_group64(uint32_t taddr, const EpiExtra& e, const float* shift, int co, int bn_left, int Cout, bf16* ydst,
+                                            const bf16* rdst, bool row_ok) {
+  uint4 rr[8];
+  const bool res_regs = rdst != nullptr && row_ok && co + 64 <= Cout && bn_left >= 64;
+  if (res_regs) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const uint4*>(rdst + j * 8);
+  }
+#pragma unroll
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = cc * 16;
+    if (c >= bn_left) break;
+    float v[16];
+    tmem_ld16(taddr + (uint32_t)c, v);
+    EpiExtra ee = e;
+    if (res_regs) {
+      if (ee.scale) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] *= __ldg(ee.scale + co + c + i);
+      }
+      const uint4 r0 = rr[2 * cc], r1 = rr[2 * cc + 1];
+      const uint32_t w8[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[2 * i] = fmaf(__uint_as_float(w8[i] << 16), ee.res_scale, v[2 * i]);
+        v[2 * i + 1] = fmaf(__uint_as_float(w8[i] & 0xffff0000u), ee.res_scale, v[2 * i + 1]);
+      }
+      // scale was applied before the residual was added; the shift commutes with the add
+      ee.scale = nullptr; ee.res = nullptr;
+    }
+    epi_apply16(v, ee, shift, co + c, Cout, ee.res ? rdst + c : nullptr, row_ok);
+    if (row_ok && co + c < Cout) {
+      if (co + c + 16 <= Cout) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+        *reinterpret_cast<uint4*>(ydst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(ydst + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+      } else {
+        for (int i = 0; i < 16 && co + c + i < Cout; ++i) ydst[c + i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
+}
+
 // Residual rows are read by the epilogue threads with a dependent load per 16-column chunk; issued only after the
 // accumulator is complete, their DRAM latency would sit on the critical path.  Called BEFORE waiting for the accumulator, this
 // pulls the row (nbytes, from 128-byte aligned-ish `row`) into L2 while the MMAs are still running.
