@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   uint64_t* accum_bar = empty + S;
   uint32_t* tmem_slot = (uint32_t*)(accum_bar + 1);
   float* s_sum = (float*)(tmem_slot + 2);   // [BN] + [BN]: per-channel sum / sum of squares of this tile (BatchNorm statistics)
-  float* s_sq = s_sum + p.BN;
+  float* s_sq = s_sum + p.BN;               // (the same space holds the [3][BN] epilogue vectors of an inference launch)
   if (p.stats) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
+  if (p.has_ex) epi_stage(s_sum, p.BN, blockIdx.y * p.BN, p.Cout, p.ex, p.bias);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // tile coordinates
@@ -182,8 +183,8 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
       // inference epilogue (scale / shift / residual / activation), 64 columns at a time
       const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
       for (int c = 0; c < p.BN; c += 64)
-        epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, p.ex, p.bias, co0 + c, p.BN - c, p.Cout, yrow + c,
-                    rrow ? rrow + c : nullptr, row_ok);
+        epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, s_sum + c, p.BN, p.ex.res_scale, co0 + c, p.BN - c, p.Cout,
+                    yrow + c, rrow ? rrow + c : nullptr, row_ok);
     } else {
     for (int c = 0; c < p.BN; c += 16) {
       float v[16];
@@ -440,7 +441,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   const int max_stages = total_ctas <= vca_num_sms() ? 12 : 6;
   if (stages > max_stages) stages = max_stages; if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + 256 + 2048;   // alignment + barriers + BatchNorm statistic accumulators
+  const size_t smem = stages * stage_bytes + 1024 + 256 + 3072;   // alignment + barriers + statistic accumulators / epilogue vectors
 
   CUtensorMap tmA, tmB;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.tw, p.th, p.tn};

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_hs_kernel(const __grid_co
   float* s_sum = (float*)(s_arel + 256);   // [BN] + [BN]: BatchNorm statistics of the current item
   float* s_sq = s_sum + p.BN;
   if (p.stats) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
+  if (p.has_ex) epi_stage(s_sum, p.BN, blockIdx.y * p.BN, p.Cout, p.ex, p.bias);     // [3][BN] epilogue vectors in the same space
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.BN;
@@ -178,8 +179,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) conv_tc_hs_kernel(const __grid_co
         if (p.has_ex) {
           const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
           for (int c = 0; c < p.BN; c += 64)
-            epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * p.BN + c), p.ex, p.bias, co0 + c, p.BN - c,
-                        p.Cout, yrow + c, rrow ? rrow + c : nullptr, row_ok);
+            epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * p.BN + c), s_sum + c, p.BN, p.ex.res_scale,
+                        co0 + c, p.BN - c, p.Cout, yrow + c, rrow ? rrow + c : nullptr, row_ok);
           continue;
         }
         for (int c = 0; c < p.BN; c += 16) {
@@ -267,7 +268,7 @@ int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   const uint32_t a_need = (uint32_t)((MT - 1) * p.th * p.P + (KH - 1) * p.P + KW + 127) * 128u;   // rows any tap window may touch
   p.a_stage_bytes = ((a_need > p.a_tx_bytes ? a_need : p.a_tx_bytes) + 1023u) & ~1023u;
   p.w_tile_bytes = (uint32_t)bn * 128u;
-  const size_t budget = 220 * 1024 - 4096;
+  const size_t budget = 219 * 1024 - 4096;
   // Two halo stages are enough (the next box is issued half an item / a whole item ahead); everything else goes to
   // the weight ring: a tile is consumed every 8 MMAs (~512 cycles) and a TMA round trip under load is 3-4k cycles.
   const int sa = 2;
@@ -280,7 +281,7 @@ int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
   p.has_ex = ex != nullptr;
   if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
-  const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sw * p.w_tile_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics
+  const size_t smem = (size_t)sa * p.a_stage_bytes + (size_t)sw * p.w_tile_bytes + 1024 + 5120;   // + alignment + barriers/tables/statistics or epilogue vectors
 
   CUtensorMap tmA, tmB;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.P, box_rows, 1};

@@ -67,6 +67,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
   float* s_sum = (float*)(s_arel + 256);   // [BN] + [BN]: BatchNorm statistics of the current tile
   float* s_sq = s_sum + p.BN;
   if (MODE == 1) for (int i = threadIdx.x; i < 2 * p.BN; i += blockDim.x) s_sum[i] = 0.f;
+  if (MODE == 2) epi_stage(s_sum, p.BN, blockIdx.y * p.BN, p.Cout, p.ex, p.bias);     // [3][BN] epilogue vectors in the same space
+  float* s_bias = s_sum + 2 * p.BN;          // the bias of the plain / statistics epilogues, staged once (no global load per chunk)
+  if (MODE != 2) for (int i = threadIdx.x; i < p.BN; i += blockDim.x) s_bias[i] = (p.bias && blockIdx.y * p.BN + i < p.Cout) ? p.bias[blockIdx.y * p.BN + i] : 0.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.BN;
@@ -186,8 +189,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
       if (MODE == 2) {
         const bf16* rrow = p.ex.res ? p.ex.res + (yrow - p.y) : nullptr;
         for (int c = 0; c < p.BN; c += 64)
-          epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), p.ex, p.bias, co0 + c, p.BN - c, p.Cout,
-                      yrow + c, rrow ? rrow + c : nullptr, row_ok);
+          epi_group64(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), s_sum + c, p.BN, p.ex.res_scale, co0 + c,
+                      p.BN - c, p.Cout, yrow + c, rrow ? rrow + c : nullptr, row_ok);
       } else
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) {
@@ -195,9 +198,9 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
         if (c >= p.BN) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
-        if (p.bias && co0 + c < p.Cout) {
+        if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += (co0 + c + i < p.Cout) ? __ldg(p.bias + co0 + c + i) : 0.f;
+          for (int i = 0; i < 16; ++i) v[i] += s_bias[c + i];
         }
         if (MODE == 1 && cc < 4 && row_ok) {
 #pragma unroll
@@ -301,7 +304,7 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
   p.has_ex = ex != nullptr;
   if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
-  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 4096;   // + alignment + barriers/tables/statistics
+  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 1024 + 5120;   // + alignment + barriers/tables/statistics or epilogue vectors
 
   CUtensorMap tmA, tmB;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.P, p.th + KH - 1, 1};

@@ -194,50 +194,63 @@ __device__ __forceinline__ void epi_apply16(float (&v)[16], const EpiExtra& e, c
   }
 }
 
-// One 64-column group of the inference epilogue for this thread's output row: the residual's 128 bytes are requested with
-// eight back-to-back 16-byte loads BEFORE the accumulator columns are read, so their latency is paid once per group (and
-// overlaps the tcgen05.ld's) instead of once per 16-column chunk.  taddr = TMEM address of the group's first column (this
-// thread's lane); co = output channel of that column; bn_left = columns of the CTA's tile from there on.
-__device__ __forceinline__ void epi_group64(uint32_t taddr, const EpiExtra& e, const float* shift, int co, int bn_left, int Cout, bf16* ydst,
-                                            const bf16* rdst, bool row_ok) {
+// Per-channel epilogue vectors staged in shared memory (s_epi = [3][BN] floats: scale, shift, negative-side slope): the
+// epilogue threads read them with broadcast LDS instead of dependent global loads -- with ~200 KB of the SM's memory
+// configured as shared there is next to no L1 left, and a global load per channel and chunk made the epilogue, not the
+// MMAs, the critical path of the short-K layers (measured: 125 instead of 550 TFLOP/s on ResNet layer 1).
+// Called by all threads of the CTA before the first __syncthreads().
+__device__ __forceinline__ void epi_stage(float* s_epi, int BN, int co0, int Cout, const EpiExtra& e, const float* shift) {
+  for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+    const int c = co0 + i;
+    const bool ok = c < Cout;
+    s_epi[i] = (e.scale && ok) ? e.scale[c] : 1.f;
+    s_epi[BN + i] = (shift && ok) ? shift[c] : 0.f;
+    s_epi[2 * BN + i] = e.act == 0 ? 1.f : (e.act == 1 ? e.slope : (e.act == 2 ? (ok ? e.prelu_w[c] : 0.f) : 0.f));
+  }
+}
+// One 64-column group of the inference epilogue for this thread's output row.  The residual's 128 bytes are requested with
+// eight back-to-back 16-byte loads BEFORE the accumulator columns are read, so their latency is paid once per group.
+// taddr = TMEM address of the group's first column (this thread's lane); co = output channel of that column; bn_left =
+// columns of the CTA's tile from there on; se = s_epi + (column offset of the group inside the tile); BN = tile width.
+__device__ __forceinline__ void epi_group64(uint32_t taddr, const float* se, int BN, float res_scale, int co, int bn_left, int Cout,
+                                            bf16* ydst, const bf16* rdst, bool row_ok) {
   uint4 rr[8];
-  const bool res_regs = rdst != nullptr && row_ok && co + 64 <= Cout && bn_left >= 64;
-  if (res_regs) {
+  const bool res_vec = rdst != nullptr && row_ok && co + 64 <= Cout && bn_left >= 64;
+  if (res_vec) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) rr[j] = *reinterpret_cast<const uint4*>(rdst + j * 8);
   }
 #pragma unroll
   for (int cc = 0; cc < 4; ++cc) {
     const int c = cc * 16;
-    if (c >= bn_left) break;
-    float v[16];
-    tmem_ld16(taddr + (uint32_t)c, v);
-    EpiExtra ee = e;
-    if (res_regs) {
-      if (ee.scale) {
+    if (c < bn_left) {
+      float v[16];
+      tmem_ld16(taddr + (uint32_t)c, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] *= __ldg(ee.scale + co + c + i);
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], se[c + i], se[BN + c + i]);
+      if (res_vec) {
+        const uint4 r0 = rr[2 * cc], r1 = rr[2 * cc + 1];
+        const uint32_t w8[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[2 * i] = fmaf(__uint_as_float(w8[i] << 16), res_scale, v[2 * i]);
+          v[2 * i + 1] = fmaf(__uint_as_float(w8[i] & 0xffff0000u), res_scale, v[2 * i + 1]);
+        }
+      } else if (rdst != nullptr && row_ok) {
+        for (int i = 0; i < 16 && co + c + i < Cout; ++i) v[i] = fmaf(__bfloat162float(rdst[c + i]), res_scale, v[i]);
       }
-      const uint4 r0 = rr[2 * cc], r1 = rr[2 * cc + 1];
-      const uint32_t w8[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[2 * i] = fmaf(__uint_as_float(w8[i] << 16), ee.res_scale, v[2 * i]);
-        v[2 * i + 1] = fmaf(__uint_as_float(w8[i] & 0xffff0000u), ee.res_scale, v[2 * i + 1]);
-      }
-      // scale was applied before the residual was added; the shift commutes with the add
-      ee.scale = nullptr; ee.res = nullptr;
-    }
-    epi_apply16(v, ee, shift, co + c, Cout, ee.res ? rdst + c : nullptr, row_ok);
-    if (row_ok && co + c < Cout) {
-      if (co + c + 16 <= Cout) {
-        uint32_t w[8];
+      for (int i = 0; i < 16; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * se[2 * BN + c + i];
+      if (row_ok && co + c < Cout) {
+        if (co + c + 16 <= Cout) {
+          uint32_t w[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
-        *reinterpret_cast<uint4*>(ydst + c) = make_uint4(w[0], w[1], w[2], w[3]);
-        *reinterpret_cast<uint4*>(ydst + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
-      } else {
-        for (int i = 0; i < 16 && co + c + i < Cout; ++i) ydst[c + i] = __float2bfloat16_rn(v[i]);
+          for (int i = 0; i < 8; ++i) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&h); }
+          *reinterpret_cast<uint4*>(ydst + c) = make_uint4(w[0], w[1], w[2], w[3]);
+          *reinterpret_cast<uint4*>(ydst + c + 8) = make_uint4(w[4], w[5], w[6], w[7]);
+        } else {
+          for (int i = 0; i < 16 && co + c + i < Cout; ++i) ydst[c + i] = __float2bfloat16_rn(v[i]);
+        }
       }
     }
   }
