@@ -31,5 +31,5 @@ for fused in (False, True):
     print(f"\n==== fused={fused}: forward {a.elapsed_time(b):.2f} ms; sum of library calls (serialised) {tot:.2f} ms")
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]:
         print(f"  {k:32s} n={v['n']:4d} {v['ms']:8.3f} ms   {v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TF/s")
-        for g in v["top"][:4]:
+        for g in v["top"][:(24 if k.startswith('vca_conv') or k.startswith('vca_bn_act') else 3)]:
             print(f"       {g[0]:60s} x{g[1]:3d} {g[2]:8.3f} ms {g[3]:8.1f} TF/s")

@@ -32,7 +32,12 @@ class Config:
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
-    fuse_eval_epilogue = True   # inference: eval-mode BatchNorm / activation / residual folded into the conv epilogue (conv_epi)
+    # inference: eval-mode BatchNorm / activation / residual folded into the conv epilogue (conv_epi, vca_conv_fwd_tc_epi).
+    # Correct (tests/test_gpu_modules.py::test_eval_epilogue_fusion_matches_unfused) but OFF: measured on B200 (B = 64 + flip
+    # TTA, profiles/infer_profile_r02.txt) every layer gets slower by more than the saved bn_act pass costs -- e.g. ResNet
+    # layer 3: conv 0.448 -> 0.635 ms for a 0.10 ms BatchNorm pass.  The epilogue of these kernels is not hidden behind the
+    # MMAs (one accumulator per CTA, or a mainloop of only ~2k cycles per tile), while the separate pass runs at HBM speed.
+    fuse_eval_epilogue = False
     fuse_stem_pool = True   # stem BatchNorm3d + PReLU + MaxPool3d as one pass over the raw conv output (bn_prelu_maxpool)
     fuse_bn_stats = True    # train-mode BatchNorm statistics come out of the producing conv's epilogue (vca_conv_fwd_tc_stats)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
