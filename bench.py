@@ -384,6 +384,7 @@ def run_train(args):
         run_host = lambda v, m_, s_: tr.step(v.to(dev, non_blocking=True), m_.to(dev, non_blocking=True),  # noqa: E731
                                              s_.to(dev, non_blocking=True), lens)
     else:   # whole step replayed from CUDA graphs (no host launch overhead; optimizer/RNG state is device resident)
+        tr.single_graph = not args.multi_graph
         tr.capture(vid, mel, spec, lens, warmup=max(args.warmup, 3))
         run_resident = lambda: tr.replay()                                         # noqa: E731
         run_host = lambda v, m_, s_: tr.replay(v, m_, s_)                          # noqa: E731
@@ -490,8 +491,10 @@ def run_train(args):
                          + f" on torch CPU, all {os.cpu_count()} threads ({c_sec:.1f} s)"}
     if args.no_graph:
         launch = "eager"
+    elif args.multi_graph:
+        launch = "one CUDA graph per phase (3 on one GPU, 6 data-parallel), all-reduces issued between them"
     elif world == 1:
-        launch = "3 CUDA graphs per step (D phase | G phase | G optimizer)"
+        launch = "1 CUDA graph per step"
     else:
         launch = tr_launch_desc()
     line = {
@@ -514,9 +517,8 @@ def run_train(args):
 
 
 def tr_launch_desc():
-    return ("CUDA graphs per step: D phase (the D-gradient all-reduce starts per discriminator underneath it) | G phase to the "
-            "generator's leaves | visual front-end backward | G optimizer; NCCL all-reduce of gen+post grads underneath graph 3, of "
-            "v_front grads before graph 4")
+    return ("1 CUDA graph per step; the NCCL all-reduces are graph nodes on a comm stream: D grads underneath the Postnet forward + "
+            "L1 terms, gen+post grads underneath the visual front-end backward, v_front grads underneath Adam on gen+post")
 
 
 def run_inference(args):
@@ -633,6 +635,8 @@ def main():
     ap.add_argument("--eager-steps", type=int, default=8)
     ap.add_argument("--ref-autocast", action="store_true", help="--impl reference-gpu under torch.autocast(bfloat16)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying CUDA graphs")
+    ap.add_argument("--multi-graph", action="store_true", help="one CUDA graph per phase with the all-reduces issued between them "
+                                                               "(instead of one graph for the whole step, NCCL nodes included)")
     args = ap.parse_args()
     if args.lrs:
         args.workload = "lrs"

@@ -49,7 +49,10 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
         d_mean = (trs[0].D.grad + trs[1].D.grad) / 2.0
         e = rel_l2(W.sample(d_mean), ranks[0]["D"] / 2.0)
         print(f"{precision}: 2-rank all-reduced D gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
-        tol = 2e-5 if precision == "fp32" else 5e-2      # bf16: split-K / wgrad atomics are not bit-reproducible run to run
+        # fp32: measured 2e-8 (D) / 6e-7 (G).  bf16: the split-K / wgrad atomics are not bit-reproducible, and at this B = 2
+        # train-mode-BatchNorm case two runs of the SAME step differ by ~6e-2 in gradient L2 (their error vs fp64 is 1e-1..5e-1,
+        # test_step_bf16_gradient_bound); the exchange itself is exact, as the fp32 case shows
+        tol = 2e-5 if precision == "fp32" else 0.15
         assert e < tol, e
         for tr in trs:
             tr.D.grad.copy_(d_mean)

@@ -312,7 +312,7 @@ def test_split_g_backward_matches_single_backward():
             tr = Trainer(precision="fp32", state=state, dropout=False)
             tr.split_g_backward = split
             tr.capture(vid.cuda(), mel.cuda(), sp.cuda(), lens, warmup=1, noise=noise)
-            assert len(tr._graphs) == 3      # one GPU: D phase | G phase (+ v_front backward) | G optimizer; 6 graphs only when world > 1
+            assert len(tr._graphs) == 1      # the whole step is one CUDA graph
             o = [{k: float(v) for k, v in tr.replay().items() if torch.is_tensor(v) and v.numel() == 1} for _ in range(2)]
             torch.cuda.synchronize()
             losses.append(o)

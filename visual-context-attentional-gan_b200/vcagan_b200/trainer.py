@@ -114,6 +114,7 @@ class Trainer:
         self.lrs = lrs
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
+        self.single_graph = True            # capture(): the whole step, NCCL all-reduces included, as ONE CUDA graph
         self.overlap_gru = True             # the sentence GRU runs on a side stream underneath the generator's first six blocks
         self._gru_stream = None
         self.batched_pack = True            # one weight re-pack launch per optimizer step (ops.PackPlan) instead of ~75
@@ -493,7 +494,7 @@ class Trainer:
         torch.cuda.synchronize()
         ops.clear_pack_cache(keep=(self._pack_g, self._pack_d))   # every other weight (re)pack must be recorded inside the graphs
         pool = torch.cuda.graph_pool_handle()
-        groups = self._phase_groups()
+        groups = [[0, 1, 2, 3, 4, 5]] if self.single_graph else self._phase_groups()
         self._graphs = [torch.cuda.CUDAGraph() for _ in groups]
         self._graph_of = {grp[0]: i for i, grp in enumerate(groups)}      # first phase of a group -> its graph
         n0 = lib().launches
@@ -503,12 +504,19 @@ class Trainer:
         cap = torch.cuda.Stream(device=self.device, priority=-1)
         phases = [lambda: self._phase_d(*self._sin, noise=self._snoise), self._phase_g_pre, self._phase_g, self._phase_g2,
                   self._phase_end_a, self._phase_end_b]
-        for gi, grp in enumerate(groups):
-            with torch.cuda.graph(self._graphs[gi], pool=pool, stream=cap):
-                for i in grp:
-                    r = phases[i]()
-                    if i == 5:
-                        self._sout = r
+        if self.single_graph:
+            # One graph for the whole step: no drain between phases (the tail of one phase overlaps the head of the next),
+            # and in data-parallel runs the NCCL all-reduces are graph nodes on the comm stream, forked from / joined into
+            # the capture stream exactly where _run_schedule places them.
+            with torch.cuda.graph(self._graphs[0], pool=pool, stream=cap):
+                self._sout = self._run_schedule(lambda i: phases[i]())
+        else:
+            for gi, grp in enumerate(groups):
+                with torch.cuda.graph(self._graphs[gi], pool=pool, stream=cap):
+                    for i in grp:
+                        r = phases[i]()
+                        if i == 5:
+                            self._sout = r
         self.launches_per_step = lib().launches - n0
         return self
 
@@ -517,6 +525,10 @@ class Trainer:
         for dst, src in zip(self._sin, (vid, mel, spec, vid_len)):
             if src is not None:
                 dst.copy_(src, non_blocking=True)
+        if self.single_graph:
+            self._graphs[0].replay()
+            return self._sout
+
         def run(i):
             gi = self._graph_of.get(i)
             if gi is not None:
