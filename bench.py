@@ -384,7 +384,7 @@ def run_train(args):
         run_host = lambda v, m_, s_: tr.step(v.to(dev, non_blocking=True), m_.to(dev, non_blocking=True),  # noqa: E731
                                              s_.to(dev, non_blocking=True), lens)
     else:   # whole step replayed from CUDA graphs (no host launch overhead; optimizer/RNG state is device resident)
-        tr.single_graph = not args.multi_graph
+        tr.single_graph = tr.single_graph and not args.multi_graph
         tr.capture(vid, mel, spec, lens, warmup=max(args.warmup, 3))
         run_resident = lambda: tr.replay()                                         # noqa: E731
         run_host = lambda v, m_, s_: tr.replay(v, m_, s_)                          # noqa: E731
@@ -491,8 +491,8 @@ def run_train(args):
                          + f" on torch CPU, all {os.cpu_count()} threads ({c_sec:.1f} s)"}
     if args.no_graph:
         launch = "eager"
-    elif args.multi_graph:
-        launch = "one CUDA graph per phase (3 on one GPU, 6 data-parallel), all-reduces issued between them"
+    elif args.multi_graph and world == 1:
+        launch = "3 CUDA graphs per step (D phase | G phase | G optimizer)"
     elif world == 1:
         launch = "1 CUDA graph per step"
     else:
@@ -517,8 +517,9 @@ def run_train(args):
 
 
 def tr_launch_desc():
-    return ("1 CUDA graph per step; the NCCL all-reduces are graph nodes on a comm stream: D grads underneath the Postnet forward + "
-            "L1 terms, gen+post grads underneath the visual front-end backward, v_front grads underneath Adam on gen+post")
+    return ("6 CUDA graphs per step (one per phase of Trainer._run_schedule), NCCL all-reduces issued between them on a comm stream: D "
+            "grads underneath the Postnet forward + L1 terms, gen+post grads underneath the visual front-end backward, v_front grads "
+            "underneath Adam on gen+post")
 
 
 def run_inference(args):

@@ -114,7 +114,10 @@ class Trainer:
         self.lrs = lrs
         self.merge_vfront_backward = True   # exact (up to fp re-association); False = the reference's two traversals
         self.parallel_branches = True       # the 3 discriminators + sync discriminator run as concurrent stream branches
-        self.single_graph = True            # capture(): the whole step, NCCL all-reduces included, as ONE CUDA graph
+        # capture(): the whole step as ONE CUDA graph.  Single-GPU only: with the NCCL all-reduces captured as graph nodes a
+        # 2-GPU run hung on this pool (torch 2.11 / NCCL 2.28.9; killed by its timeout, not investigated further), so
+        # data-parallel runs capture one graph per phase and issue the exchanges between them (set after self.world below).
+        self.single_graph = True
         self.overlap_gru = True             # the sentence GRU runs on a side stream underneath the generator's first six blocks
         self._gru_stream = None
         self.batched_pack = True            # one weight re-pack launch per optimizer step (ops.PackPlan) instead of ~75
@@ -139,6 +142,7 @@ class Trainer:
         self.pg = process_group
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
+        self.single_graph = self.world == 1
         if self.world > 1:
             self._sync_replicas()
         # Data-parallel runs split the G backward where the generator's last gradient is written: the all-reduce of the
@@ -505,9 +509,7 @@ class Trainer:
         phases = [lambda: self._phase_d(*self._sin, noise=self._snoise), self._phase_g_pre, self._phase_g, self._phase_g2,
                   self._phase_end_a, self._phase_end_b]
         if self.single_graph:
-            # One graph for the whole step: no drain between phases (the tail of one phase overlaps the head of the next),
-            # and in data-parallel runs the NCCL all-reduces are graph nodes on the comm stream, forked from / joined into
-            # the capture stream exactly where _run_schedule places them.
+            # One graph for the whole step: no drain between phases (the tail of one phase overlaps the head of the next).
             with torch.cuda.graph(self._graphs[0], pool=pool, stream=cap):
                 self._sout = self._run_schedule(lambda i: phases[i]())
         else:
