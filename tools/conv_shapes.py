@@ -25,6 +25,10 @@ SHAPES = [  # name, N, H, W, Cin, Cout, (kh,kw), (ph,pw)
     ("dis3.cond.1", 32, 5, 18, 1024, 512, (5, 5), (2, 2)),
     ("dis3.uncond.1(p0)", 32, 5, 18, 512, 512, (5, 5), (0, 0)),
     ("gru.proj(linear)", 2400, 1, 1, 1024, 1536, (1, 1), (0, 0)),
+    ("gen.g3.pair(5x3)", 32, 80, 150, 64, 64, (5, 3), (2, 1)),
+    ("dis.sc(1x1,32-64)", 32, 80, 300, 32, 64, (1, 1), (0, 0)),
+    ("dis.sc(1x1,64-128)", 32, 40, 150, 64, 128, (1, 1), (0, 0)),
+    ("dis.conv(32-64,5x5)", 32, 40, 150, 32, 64, (5, 5), (2, 2)),
 ]
 
 
@@ -37,7 +41,24 @@ def main():
     ap.add_argument("--hs", type=int, default=1, help="halo-resident / streamed-weights kernel: 0 off, 1 auto, 2 force")
     ap.add_argument("--splitk", type=int, default=1, help="lend the split-K workspace the library asks for (0 = never split)")
     ap.add_argument("--wgws", type=int, default=1, help="multi-tap wgrad kernel: 0 off, 1 auto (Cin <= 128), 2 any Cin")
+    ap.add_argument("--opt", action="append", default=[], help="key=value passed to vca_set_option (repeatable)")
+    ap.add_argument("--tag", default="")
+    ap.add_argument("--sweep", default="", help="key=v1,v2,...: run everything once per value of this vca_set_option key")
     args = ap.parse_args()
+    if args.sweep:
+        key, vals = args.sweep.split("=")
+        for v in vals.split(","):
+            assert lib().cdll.vca_set_option(key.encode(), int(v)) == 0
+            args.tag = f"{key}={v} "
+            run(args)
+        return
+    run(args)
+
+
+def run(args):
+    for kv in args.opt:
+        k, v = kv.split("=")
+        assert lib().cdll.vca_set_option(k.encode(), int(v)) == 0, kv
     assert lib().cdll.vca_set_option(b"ws_mode", args.ws) == 0
     assert lib().cdll.vca_set_option(b"hs_mode", args.hs) == 0
     assert lib().cdll.vca_set_option(b"wgws_mode", args.wgws) == 0
@@ -75,7 +96,7 @@ def main():
                 ms.append(a.elapsed_time(b))
             t = sorted(ms)[len(ms) // 2]
             rows.append(dict(layer=name, kind=kind, ms=round(t, 4), tflops=round(flops / t / 1e9, 1), gflop=round(flops / 1e9, 2)))
-            print(f"{name:22s} {kind:6s} {t:8.3f} ms  {flops / t / 1e9:8.1f} TFLOP/s  ({flops / 1e9:.1f} GFLOP)", flush=True)
+            print(f"{args.tag}{name:22s} {kind:6s} {t:8.3f} ms  {flops / t / 1e9:8.1f} TFLOP/s  ({flops / 1e9:.1f} GFLOP)", flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "conv_shapes.json"), "w"), indent=1)
 

@@ -27,6 +27,8 @@ namespace {
 constexpr int KC = 64;
 int g_ws_mode = 1;       // 0 off, 1 auto, 2 force whenever the geometry fits
 int g_ws_base_off = 0;    // descriptor base-offset mode for shifted A windows (0: none, 1: (addr >> 7) & 7)
+int g_ws_dbg = 0;         // probe switches (tools/ws_bound_probe.py): 1 no global stores, 2 no TMEM reads, 4 no MMAs, 8 / 16 MMA N forced to 128 / 256
+int g_ws_min_taps = 2;    // smallest filter the kernel takes (1: also pointwise convs)
 
 struct WsParams {
   int NF, OH, OW, Cout;
@@ -37,7 +39,7 @@ struct WsParams {
   int BN;
   int sa;
   uint32_t a_stage_bytes, a_tx_bytes, w_bytes, tmem_cols;
-  int base_off_mode;
+  int base_off_mode, dbg;
   const float* bias;
   double* stats;           // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
   EpiExtra ex;             // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
@@ -119,7 +121,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
     for (int t = lane; t < taps; t += 32) s_arel[t] = (uint32_t)((t / p.KW) * p.P + (t % p.KW)) * 8u;   // rows*128 B >> 4
     __syncwarp();
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(128, p.BN, 0, 0);
+      const uint32_t idesc = make_idesc(128, (p.dbg & 8) ? 128 : (p.dbg & 16) ? 256 : p.BN, 0, 0);
       const uint64_t HI = (uint64_t)(64u | (1u << 14) | (2u << 29)) << 32;   // SBO = 1024 B, version 1, SWIZZLE_128B
       const uint32_t w_lo = smem_u32(sW) >> 4, w_step = w_tile >> 4;
       mbar_wait(w_bar, 0);
@@ -137,7 +139,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
           const int ksteps = (kc == p.kchunks - 1) ? p.ksteps_last : 4;
           uint32_t b_lo = w_lo + (uint32_t)kc * w_step;
           const uint32_t b_inc = (uint32_t)p.kchunks * w_step;
-          if (ksteps == 4) {
+          if (p.dbg & 4) {
+          } else if (ksteps == 4) {
             for (int t = 0; t < taps; ++t, b_lo += b_inc) {
               const uint32_t al = a_lo + s_arel[t];
               umma_bf16(d_tmem, HI | al, HI | b_lo, idesc, accum); accum = 1;
@@ -195,7 +198,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
 #pragma unroll
       for (int cc = 0; cc < 16; ++cc) {
         const int c = cc * 16;
-        if (c >= p.BN) break;
+        if (c >= p.BN || (p.dbg & 2)) break;
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.BN + c), v);
         if (p.bias) {
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_ws_kernel(const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) { const float t = bf16_round(v[i]); rs[((cc & 3) * 16 + i) % NR] += t; rq[((cc & 3) * 16 + i) % NR] = fmaf(t, t, rq[((cc & 3) * 16 + i) % NR]); }
         }
-        if (row_ok && co0 + c < p.Cout) {
+        if (row_ok && co0 + c < p.Cout && !((p.dbg & 1) && v[0] != 123.456f)) {
           if (co0 + c + 16 <= p.Cout) {
             uint32_t w[8];
 #pragma unroll
@@ -266,7 +269,7 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   // x == nullptr: dry run -- 1 when this kernel would take the geometry (and, with stats != nullptr, emit the statistics)
   if (g_ws_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
-  if (taps < 2 || taps > 256 || kchunks > 2 || KW > 64) return 0;
+  if (taps < g_ws_min_taps || taps > 256 || kchunks > 2 || KW > 64) return 0;
   int bn = ((Nout + 15) / 16) * 16; if (bn > 256) bn = 256;
   const size_t W_BUDGET = 120 * 1024;
   while ((size_t)taps * kchunks * bn * 128 > W_BUDGET && bn > 32) bn = (bn / 2 + 15) / 16 * 16;
@@ -297,10 +300,10 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   if (sa > 4) sa = 4;
   if (sa < 2) return 0;
   p.sa = sa;
-  p.tmem_cols = pow2_cols(2 * bn);
+  p.tmem_cols = g_ws_dbg & 24 ? 512 : pow2_cols(2 * bn);
   if (stats && bn > 64) return 0;          // the epilogue keeps the statistics of at most 64 columns in registers
   if (!x) return 1;
-  p.base_off_mode = g_ws_base_off;
+  p.base_off_mode = g_ws_base_off; p.dbg = g_ws_dbg;
   p.bias = bias; p.y = (bf16*)y; p.stats = stats;
   p.has_ex = ex != nullptr;
   if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
@@ -338,6 +341,8 @@ int vca_set_option(const char* key, int value) {
   auto eq = [&](const char* s) { const char* a = k; while (*a && *s && *a == *s) { ++a; ++s; } return *a == 0 && *s == 0; };
   if (eq("ws_mode")) { g_ws_mode = value; return VCA_OK; }
   if (eq("ws_base_off")) { g_ws_base_off = value; return VCA_OK; }
+  if (eq("ws_dbg")) { g_ws_dbg = value; return VCA_OK; }
+  if (eq("ws_min_taps")) { g_ws_min_taps = value < 1 ? 1 : value; return VCA_OK; }
   if (eq("wgws_mode")) { g_wgws_mode = value; return VCA_OK; }
   if (eq("bn_vec")) { g_bn_vec = value; return VCA_OK; }
   if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
