@@ -606,7 +606,7 @@ def test_attention_tc(V, Tq, S, lens):
     # N, Cin, H, W, Cout, k, pad, stride, hs_mode
     # N, Cin, H, W, Cout, k, pad, stride, expect the fused path (weights-stationary kernel: <= 64 channels in and out)
     (16, 64, 40, 46, 64, 3, 1, 1, True),      # several tiles per persistent CTA, ragged tiles
-    (16, 64, 40, 46, 64, 5, 2, 1, False),     # 64 -> 64 5x5: the weights do not fit next to the halo ring -> streaming kernel
+    (16, 64, 40, 46, 64, 5, 2, 1, True),      # 64 -> 64 5x5: two 32-channel CTAs columns, filter rows stacked (N = 160)
     (300, 64, 28, 28, 64, 3, 1, 1, True),     # ResNet layer 1 at 4 clips: ~600 tiles, 4 per CTA
     (16, 32, 24, 50, 32, 5, 2, 1, True),      # pixel-pair merged: statistics arrive as two column groups per channel
     (9, 48, 11, 30, 40, 3, 1, 1, True),       # ragged channels: Cout = 40 (three 16-column chunks, the last half empty), K chunk 48
@@ -683,4 +683,69 @@ def test_bn_prelu_maxpool_fused(V, train):
         # does not: gradients agree to bf16 rounding (eps = 3.9e-3), forward values and running statistics exactly
         assert max(errs[k] for k in names[:4]) < 5e-3 and max(errs[k] for k in names[4:]) < 1e-6, errs
     finally:
+        V.set_precision("fp32")
+
+
+WS_STACK_CASES = [
+    # N, Cin, H, W, Cout, (kh, kw), (ph, pw)
+    (3, 64, 28, 28, 64, (3, 3), (1, 1)),      # ResNet layer 1: pitch 32, three taps per MMA (N = 192)
+    (2, 64, 20, 50, 64, (5, 5), (2, 2)),      # 5x5: two 32-channel CTA columns, N = 160, ragged tiles along W
+    (3, 32, 9, 13, 48, (3, 3), (1, 1)),       # pitch 16; 96-byte rows: plain-store epilogue
+    (2, 64, 12, 6, 64, (3, 3), (1, 1)),       # pitch 8
+    (2, 32, 11, 30, 64, (5, 5), (2, 2)),      # half-filled K chunk (32 input channels)
+    (2, 64, 9, 30, 64, (5, 3), (2, 1)),       # the pixel-pair merged 5x3 geometry
+    (2, 64, 7, 40, 64, (1, 4), (0, 1)),       # KW = 4, one filter row
+    (2, 64, 10, 21, 32, (2, 2), (0, 0)),      # KW = 2, no padding, 64-byte rows
+    (2, 32, 10, 30, 64, (1, 1), (0, 0)),      # pointwise conv on the persistent kernel (no stacking)
+    (2, 64, 9, 50, 64, (5, 1), (2, 0)),       # (5,1) temporal stem conv: KW = 1
+    (2, 64, 6, 31, 32, (3, 3), (1, 1)),       # 64-byte rows (SWIZZLE_64B staging), three taps per MMA
+]
+
+
+@pytest.mark.parametrize("case", WS_STACK_CASES)
+def test_conv_ws_stacked_and_tma_store(V, case):
+    """Weights-stationary kernel: filter-row stacking (KW taps per MMA, shuffle combine) and the TMA-store epilogue, each
+    on and off, forward (+bias) and dgrad against fp32 math on the same bf16 inputs; the statistics epilogue against
+    column sums of the stored tensor."""
+    from vcagan_b200.ops import _geom, _packed
+    N, Cin, H, W, Cout, k, p = case
+    L = V.lib()
+    g = torch.Generator().manual_seed(sum(case[:5]) + k[0] * 7 + k[1])
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *k, generator=g) / math.sqrt(Cin * k[0] * k[1])).bfloat16().float()
+    b = torch.randn(Cout, generator=g)
+    y = F.conv2d(x, w, b, 1, p)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    dx = torch.autograd.grad(F.conv2d(x.requires_grad_(True), w, None, 1, p), x, dy)[0]
+    V.set_precision("bf16")
+    try:
+        xd = cl(x.detach()).cuda().bfloat16()
+        dyd = cl(dy).cuda().bfloat16()
+        wp = torch.nn.Parameter(w.cuda())
+        geom, oshape = _geom(xd.shape, wp.shape, (1, 1), p)
+        wf, wd = _packed(wp, torch.bfloat16)
+        assert L.cdll.vca_set_option(b"ws_mode", 2) == 0
+        for stack, tma in ((1, 1), (1, 0), (0, 1), (0, 0)):
+            assert L.cdll.vca_set_option(b"ws_stack", stack) == 0 and L.cdll.vca_set_option(b"ws_tma_out", tma) == 0
+            yd = torch.full(oshape, float("nan"), dtype=torch.bfloat16, device="cuda")
+            L.call("vca_conv_fwd_tc", geom, xd, wd, b.cuda(), yd)
+            dxd = torch.full_like(xd, float("nan"))
+            L.call("vca_conv_dgrad_tc", geom, dyd, wf, dxd)
+            sums = torch.zeros(2 * Cout, dtype=torch.float64, device="cuda")
+            ys = torch.empty_like(yd)
+            has_stats = Cout <= 64 and L.query("vca_conv_fwd_tc_stats_supported", geom) == 1
+            if has_stats:
+                L.call("vca_conv_fwd_tc_stats", geom, xd, wd, b.cuda(), ys, sums)
+            torch.cuda.synchronize()
+            ef = rel_l2(nchw(yd.float().cpu()), y)
+            ed = rel_l2(nchw(dxd.float().cpu()), dx)
+            print("ws case", case, "stack", stack, "tma", tma, "fwd", ef, "dgrad", ed)
+            assert ef < BF16_TOL and ed < BF16_TOL, (case, stack, tma, ef, ed)
+            if has_stats:
+                assert torch.equal(ys, yd)
+                ref = torch.cat([ys.double().sum((0, 1, 2)), ys.double().square().sum((0, 1, 2))])
+                assert rel_l2(sums.cpu(), ref.cpu()) < 1e-5
+    finally:
+        for key, v in ((b"ws_mode", 1), (b"ws_stack", 1), (b"ws_tma_out", 1)):
+            L.cdll.vca_set_option(key, v)
         V.set_precision("fp32")

@@ -133,14 +133,14 @@ __device__ __forceinline__ void epi_stats16(const float (&v)[16], bool row_ok, i
   const int col = epi_col(lane);
   if (!(lane & 1) && co + col < Cout) { atomicAdd(s_sum + col, sa); atomicAdd(s_sq + col, sb); }
 }
-// All 128 epilogue threads (tid128 = 0..127): publish the tile's sums and leave the shared accumulators zeroed.
-__device__ __forceinline__ void epi_stats_flush(float* s_sum, float* s_sq, int BN, int co0, int Cout, double* sums, int tid128) {
-  asm volatile("bar.sync 1, 128;" ::: "memory");
-  for (int c = tid128; c < BN; c += 128) {
+// All epilogue threads (tid128 = 0..nthr-1): publish the tile's sums and leave the shared accumulators zeroed.
+__device__ __forceinline__ void epi_stats_flush(float* s_sum, float* s_sq, int BN, int co0, int Cout, double* sums, int tid128, int nthr = 128) {
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+  for (int c = tid128; c < BN; c += nthr) {
     if (co0 + c < Cout) { atomicAdd(sums + co0 + c, (double)s_sum[c]); atomicAdd(sums + Cout + co0 + c, (double)s_sq[c]); }
     s_sum[c] = 0.f; s_sq[c] = 0.f;
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
 }
 
 // ---- inference epilogue: y = act(acc * scale[c] + shift[c] + res * res_scale) ------------------------------------------
@@ -278,9 +278,14 @@ static inline EncodeTiledFn get_encode() {
   }
   return fn;
 }
-// bf16 tensor map with a 64-channel (128 B) inner box, SWIZZLE_128B, zero OOB fill; dims/box innermost-first.
-static inline int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box) {
+// bf16 tensor map (default: 64-channel = 128 B inner box, SWIZZLE_128B), zero OOB fill; dims/box innermost-first.
+static inline int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box,
+                           CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
+  // the driver entry point needs the primary context bound to THIS thread; a fresh thread (autograd's backward worker)
+  // that has made no context-binding runtime call yet gets CUDA_ERROR_INVALID_CONTEXT otherwise
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   if (!enc) { vca_set_error("cuTensorMapEncodeTiled entry point unavailable"); return VCA_ERR_CUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   long long stride = 2;
@@ -290,7 +295,7 @@ static inline int make_map(CUtensorMap* m, const void* base, int rank, const lon
     stride *= dims[i];
   }
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { vca_set_error("cuTensorMapEncodeTiled failed (CUresult %d)", (int)r); return VCA_ERR_CUDA; }
   return VCA_OK;
