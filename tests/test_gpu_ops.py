@@ -699,6 +699,8 @@ WS_STACK_CASES = [
     (2, 32, 10, 30, 64, (1, 1), (0, 0)),      # pointwise conv on the persistent kernel (no stacking)
     (2, 64, 9, 50, 64, (5, 1), (2, 0)),       # (5,1) temporal stem conv: KW = 1
     (2, 64, 6, 31, 32, (3, 3), (1, 1)),       # 64-byte rows (SWIZZLE_64B staging), three taps per MMA
+    (2, 64, 13, 19, 48, (4, 3), (2, 1)),      # even KH: two full filter-row pairs in the stacked wgrad
+    (3, 64, 16, 16, 64, (3, 1), (1, 0)),      # (3,1): wgrad taps {1,2} over {0,-}
 ]
 
 
@@ -717,13 +719,23 @@ def test_conv_ws_stacked_and_tma_store(V, case):
     y = F.conv2d(x, w, b, 1, p)
     dy = torch.randn(y.shape, generator=g).bfloat16().float()
     dx = torch.autograd.grad(F.conv2d(x.requires_grad_(True), w, None, 1, p), x, dy)[0]
+    dwr = torch.autograd.grad(F.conv2d(x.detach(), w.requires_grad_(True), None, 1, p), w, dy)[0]
     V.set_precision("bf16")
     try:
         xd = cl(x.detach()).cuda().bfloat16()
         dyd = cl(dy).cuda().bfloat16()
-        wp = torch.nn.Parameter(w.cuda())
+        wp = torch.nn.Parameter(w.detach().cuda())
         geom, oshape = _geom(xd.shape, wp.shape, (1, 1), p)
         wf, wd = _packed(wp, torch.bfloat16)
+        # multi-tap wgrad: filter rows stacked along M (rows 64..127 = the dY tile one filter row down) on and off
+        for ms in (1, 0):
+            assert L.cdll.vca_set_option(b"wgws_mstack", ms) == 0
+            dwd = torch.zeros_like(wp.data)
+            L.call("vca_conv_wgrad_tc", geom, dyd, xd, dwd)
+            torch.cuda.synchronize()
+            ew = rel_l2(dwd.cpu(), dwr)
+            print("ws case", case, "wgrad mstack", ms, ew)
+            assert ew < BF16_TOL, (case, ms, ew)
         assert L.cdll.vca_set_option(b"ws_mode", 2) == 0
         for stack, tma in ((1, 1), (1, 0), (0, 1), (0, 0)):
             assert L.cdll.vca_set_option(b"ws_stack", stack) == 0 and L.cdll.vca_set_option(b"ws_tma_out", tma) == 0
@@ -746,6 +758,6 @@ def test_conv_ws_stacked_and_tma_store(V, case):
                 ref = torch.cat([ys.double().sum((0, 1, 2)), ys.double().square().sum((0, 1, 2))])
                 assert rel_l2(sums.cpu(), ref.cpu()) < 1e-5
     finally:
-        for key, v in ((b"ws_mode", 1), (b"ws_stack", 1), (b"ws_tma_out", 1)):
+        for key, v in ((b"ws_mode", 1), (b"ws_stack", 1), (b"ws_tma_out", 1), (b"wgws_mstack", 1)):
             L.cdll.vca_set_option(key, v)
         V.set_precision("fp32")

@@ -28,6 +28,7 @@ int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
                 const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
+extern int g_wg_dbg;
 
 namespace {
 
@@ -255,6 +256,7 @@ struct WgradParams {
   uint32_t ksteps;               // ceil(box pixels / 16)
   uint32_t tmem_cols;
   float* dw;                     // [Cout][Cin][taps] fp32, accumulated with red.add
+  int dbg;
 };
 
 __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
@@ -352,7 +354,7 @@ __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constan
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const int ci = ci0 + c + i;
-            if (ci < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.taps + tap, v[i]);
+            if (ci < p.Cin && !(p.dbg && v[i] != 123.456f)) atomicAdd(p.dw + ((long long)co * p.Cin + ci) * p.taps + tap, v[i]);
           }
         }
       }
@@ -576,7 +578,7 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
   p.atom_bytes = (uint32_t)box_px * 128u;
   p.ksteps = (uint32_t)((box_px + 15) / 16);
   p.tmem_cols = pow2_cols(p.BNc);
-  p.dw = dw;
+  p.dw = dw; p.dbg = g_wg_dbg;
   const size_t stage_bytes = 2 * A_STAGE_BYTES + (size_t)p.b_atoms * A_STAGE_BYTES;
   int stages = (int)((190 * 1024) / stage_bytes);
   if (stages > 4) stages = 4; if (stages < 2) stages = 2;

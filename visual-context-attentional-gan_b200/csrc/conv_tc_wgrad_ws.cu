@@ -14,6 +14,15 @@
 //     tap spacing (128 B or P*128 B): atom g of the descriptor *is* tap g's shifted window.  A single MMA therefore
 //     produces N = 64 * taps_in_group columns (up to 256) -- 4-5 taps per A-operand read instead of one.
 // TMEM holds the group's accumulators (<= 320 columns); split-K over pixel tiles; fp32 red.add epilogue.
+//
+// Round 2 -- FILTER-ROW STACKING ALONG M for Cout <= 64: the MMA is 128 rows tall whatever Cout is, so a 64-channel layer
+// left rows 64..127 computing garbage.  The A operand is MN-major with 64-channel atoms a leading-dimension offset apart:
+// with that offset set to `mshift` image rows of the pitched dY tile, atom 1 IS the dY tile shifted down by mshift rows, and
+//     D[64 + co] = sum_p dY[p + mshift rows][co] . X[p + tap]  =  sum_q dY[q][co] . X[q + tap - mshift rows]
+// is the gradient of the tap `mshift` filter rows ABOVE the one rows 0..63 compute.  One pass therefore yields two filter
+// rows (KW > 1) or 2 x 3 taps of a (5,1) filter: 3 -> 2 passes for 3x3, 5 -> 3 for 5x5, N = 320 -> 192 for the stem.
+// The tile grid starts mshift rows above the image so that both halves see every dY row exactly once (rows outside the
+// image are zero-filled by the TMA unit).
 #include "tc_common.cuh"
 
 using namespace tc;
@@ -33,10 +42,16 @@ struct WgWsParams {
   int along_kh;          // 1: group = the KH taps of a (KH,1) filter, spacing P rows; 0: group = KW taps of row kh, spacing 1
   int x_rows;            // image rows in the X box
   int a_atoms;           // 64-channel atoms of dY actually loaded (1 or 2)
+  int mstack;            // 1: rows 64..127 = the dY tile shifted by `mshift` image rows (Cout <= 64)
+  int mshift;            // filter rows between the taps of the two halves
+  int dy_rows;           // image rows of dY per tile (th + mshift when stacked)
+  int x_row0[8];         // per group: first image row of the X box relative to (tile origin - ph)
+  signed char top_tap[8][5], bot_tap[8][5];   // per group and N-slot: tap index whose gradient rows 0..63 / 64..127 hold (-1: none)
   int ksteps;            // ceil(th*P / 16)
   int stages;
   uint32_t x_stage_bytes, a_stage_bytes, x_tx_bytes, a_row_tx_bytes, tmem_cols;
   float* dw;
+  int dbg;               // probe: 1 = no atomics (tools/conv_shapes.py --opt wg_dbg=1)
 };
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_constant__ CUtensorMap tmDY,
@@ -58,7 +73,6 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
   const int t_beg = blockIdx.x * p.tiles_per_split;
   const int t_end = min(t_beg + p.tiles_per_split, p.num_tiles);
   const int iters = t_end - t_beg;
-  const int kh0 = p.along_kh ? 0 : grp;                      // first tap of the group is (kh0, 0)
 
   {  // gap rows / never-written rows must read as zero (they are part of the K reduction)
     uint4 z = make_uint4(0, 0, 0, 0);
@@ -85,16 +99,16 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
         int tw_i, th_i, n;                                           // tile coordinates, advanced without divisions
         { int t = t_beg; tw_i = t % p.tiles_w; t /= p.tiles_w; th_i = t % p.tiles_h; n = t / p.tiles_h; }
         for (int it = 0; it < iters; ++it) {
-          const int ow0 = tw_i * p.tw, oh0 = th_i * p.th;
+          const int ow0 = tw_i * p.tw, oh0 = th_i * p.th - (p.mstack ? p.mshift : 0);
           const int n_cur = n;
           if (++tw_i == p.tiles_w) { tw_i = 0; if (++th_i == p.tiles_h) { th_i = 0; ++n; } }
           mbar_wait(&empty[stage], phase ^ 1);
-          mbar_expect_tx(&full[stage], p.x_tx_bytes + (uint32_t)(p.a_atoms * p.th) * p.a_row_tx_bytes);
-          // X halo: rows oh0 - ph + kh0 ... (+ x_rows), columns ow0 - pw ... (+ P)
-          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], ci0, ow0 - p.pw, oh0 - p.ph + kh0, n_cur);
+          mbar_expect_tx(&full[stage], p.x_tx_bytes + (uint32_t)(p.a_atoms * p.dy_rows) * p.a_row_tx_bytes);
+          // X halo: rows oh0 - ph + x_row0 ... (+ x_rows), columns ow0 - pw ... (+ P)
+          tma_load_4d(sX + (size_t)stage * p.x_stage_bytes, &tmX, &full[stage], ci0, ow0 - p.pw, oh0 - p.ph + p.x_row0[grp], n_cur);
           // dY: one box per image row, written at pitch P so that tile row r*P + w is pixel (oh0 + r, ow0 + w)
           for (int a = 0; a < p.a_atoms; ++a)
-            for (int r = 0; r < p.th; ++r)
+            for (int r = 0; r < p.dy_rows; ++r)
               tma_load_4d(sA + (size_t)stage * p.a_stage_bytes + (size_t)a * ATOM_BYTES + (size_t)r * p.P * 128, &tmDY, &full[stage],
                           co0 + a * KC, ow0, oh0 + r, n_cur);
           if (++stage == S) { stage = 0; phase ^= 1; }
@@ -108,6 +122,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
         const uint32_t idesc1 = make_idesc(128, g1 * KC, 1, 1);
         const uint32_t idesc2 = g2 > 0 ? make_idesc(128, g2 * KC, 1, 1) : 0u;
         const uint32_t tap_lbo = (uint32_t)(p.along_kh ? p.P : 1) * 128u;   // byte distance between consecutive taps' windows
+        const uint32_t a_lbo = p.mstack ? (uint32_t)(p.mshift * p.P) * 128u : (uint32_t)ATOM_BYTES;   // distance between the two M atoms
         int stage = 0; uint32_t phase = 0, accum = 0;
         for (int it = 0; it < iters; ++it) {
           mbar_wait(&full[stage], phase);
@@ -115,7 +130,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
           const uint32_t a0 = smem_u32(sA + (size_t)stage * p.a_stage_bytes);
           const uint32_t x0 = smem_u32(sX + (size_t)stage * p.x_stage_bytes);
           for (int k = 0; k < p.ksteps; ++k) {
-            const uint64_t ad = make_desc(a0 + k * 2048, ATOM_BYTES, 1024);
+            const uint64_t ad = make_desc(a0 + k * 2048, a_lbo, 1024);
             const uint64_t bd1 = make_desc(x0 + k * 2048, tap_lbo, 1024);
             umma_bf16(tmem_base, ad, bd1, idesc1, accum);
             if (g2 > 0) {
@@ -132,11 +147,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
       __syncwarp();
     } else {
       const int q = warp & 3;
-      const int co = co0 + q * 32 + lane;
+      const bool bottom = p.mstack && q >= 2;                          // rows 64..127: the shifted dY tile
+      const int co = p.mstack ? (q & 1) * 32 + lane : co0 + q * 32 + lane;
       mbar_wait(accum_bar, 0);
       tc_fence_after();
       for (int g = 0; g < p.G; ++g) {
-        const int tap = p.along_kh ? g * p.KW : kh0 * p.KW + g;       // (kh = g, kw = 0)  or  (kh0, kw = g)
+        const int tap = bottom ? p.bot_tap[grp][g] : p.top_tap[grp][g];
+        if (tap < 0) continue;                                         // warp-uniform
         for (int c = 0; c < KC; c += 16) {
           if (ci0 + c >= p.Cin) break;                                // warp-uniform
           float v[16];
@@ -144,7 +161,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
           if (co < p.Cout) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (ci0 + c + i < p.Cin) atomicAdd(p.dw + ((long long)co * p.Cin + ci0 + c + i) * p.taps + tap, v[i]);
+              if (ci0 + c + i < p.Cin && !(p.dbg && v[i] != 123.456f)) atomicAdd(p.dw + ((long long)co * p.Cin + ci0 + c + i) * p.taps + tap, v[i]);
           }
         }
       }
@@ -158,6 +175,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
 }  // namespace
 
 int g_wgws_mode = 1;   // 0 off, 1 auto, 2 any Cin
+int g_wg_dbg = 0;       // probe switch shared by both wgrad kernels: 1 = skip the red.add epilogue
+int g_wgws_mstack = 1; // filter-row stacking along M for Cout <= 64
 int g_wgws_waves = 1;  // "wgws_waves": CTAs per SM over the kernel's life (more = shorter CTAs, friendlier to concurrent streams)
 
 // 1 = launched, 0 = not applicable, < 0 error.  dw fp32 [Cout][Cin][taps], zero on entry.
@@ -195,8 +214,45 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   const long long nt = (long long)g.N * p.tiles_w * p.tiles_h;
   if (nt > 0x7fffffff) return 0;
   p.num_tiles = (int)nt;
-  p.x_rows = p.along_kh ? p.th + g.KH - 1 : p.th;
   p.a_atoms = g.Cout > KC ? 2 : 1;
+  // filter-row stacking along M (see the header): the groups and what each accumulator block holds
+  // (the K range of an MMA is whole 16-row steps: the tile must end on one, or the top half would also sum the first
+  //  pixels of the extra dY row)
+  p.mstack = g_wgws_mstack && g.Cout <= KC && g.KH >= 2 && (p.th * p.P) % 16 == 0;
+  p.mshift = 0;
+  for (int gi = 0; gi < 8; ++gi) { p.x_row0[gi] = 0; for (int j = 0; j < 5; ++j) { p.top_tap[gi][j] = -1; p.bot_tap[gi][j] = -1; } }
+  if (!p.mstack) {
+    if (p.groups > 8) return 0;
+    for (int gi = 0; gi < p.groups; ++gi) {
+      p.x_row0[gi] = p.along_kh ? 0 : gi;
+      for (int j = 0; j < p.G; ++j) p.top_tap[gi][j] = (signed char)(p.along_kh ? j * g.KW : gi * g.KW + j);
+    }
+  } else if (!p.along_kh) {
+    // KW > 1: rows 0..63 filter row kt, rows 64..127 filter row kt - 1;  kt = 1, 3, ..., and KH - 1 alone when KH is odd
+    p.mshift = 1;
+    p.groups = (g.KH + 1) / 2;
+    if (p.groups > 8) return 0;
+    for (int gi = 0; gi < p.groups; ++gi) {
+      const int kt = 2 * gi + 1 < g.KH ? 2 * gi + 1 : g.KH - 1;
+      const bool pair = 2 * gi + 1 < g.KH;
+      p.x_row0[gi] = kt;
+      for (int j = 0; j < p.G; ++j) { p.top_tap[gi][j] = (signed char)(kt * g.KW + j); p.bot_tap[gi][j] = (signed char)(pair ? (kt - 1) * g.KW + j : -1); }
+    }
+  } else {
+    // (KH,1) filter: N slots = taps t0 .. KH-1, rows 64..127 the taps t0 rows above them (0 .. t0-1)
+    const int Gn = (g.KH + 1) / 2, t0 = g.KH - Gn;
+    p.mshift = t0; p.G = Gn; p.groups = 1;
+    p.x_row0[0] = t0;
+    for (int j = 0; j < Gn; ++j) { p.top_tap[0][j] = (signed char)((t0 + j) * g.KW); p.bot_tap[0][j] = (signed char)(j < t0 ? j * g.KW : -1); }
+  }
+  p.dy_rows = p.th + p.mshift;
+  p.x_rows = p.along_kh ? p.th + p.G - 1 : p.th;
+  if (p.mstack) p.tiles_h = (g.OH + p.mshift + p.th - 1) / p.th;
+  {
+    const long long nt2 = (long long)g.N * p.tiles_w * p.tiles_h;
+    if (nt2 > 0x7fffffff) return 0;
+    p.num_tiles = (int)nt2;
+  }
   p.ksteps = (p.th * p.P + 15) / 16;
   p.x_tx_bytes = (uint32_t)(p.P * p.x_rows) * 128u;
   p.a_row_tx_bytes = (uint32_t)p.tw * 128u;
@@ -206,14 +262,14 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   p.x_stage_bytes = ((x_need > p.x_tx_bytes ? x_need : p.x_tx_bytes) + 1023u) & ~1023u;
   // Cout <= 64: only atom 0 is loaded; the M = 128 MMA then also reads the 16 KB behind it (the next stage / the X
   // buffers -- valid shared memory) into accumulator rows 64..127, which the epilogue never stores.
-  p.a_stage_bytes = (uint32_t)p.a_atoms * ATOM_BYTES;
+  p.a_stage_bytes = p.mstack ? (((uint32_t)(p.ksteps * 16 + p.mshift * p.P) * 128u + 1023u) & ~1023u) : (uint32_t)p.a_atoms * ATOM_BYTES;
   const size_t stage_bytes = (size_t)p.x_stage_bytes + p.a_stage_bytes;
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > 8) stages = 8;
   if (stages < 2) return 0;
   p.stages = stages;
   p.tmem_cols = pow2_cols(p.G * KC);
-  p.dw = dw;
+  p.dw = dw; p.dbg = g_wg_dbg;
   const int co_tiles = (g.Cout + 127) / 128;
   const long long base_ctas = (long long)co_tiles * p.ci_tiles * p.groups;
   extern int g_wgws_waves;

@@ -33,6 +33,7 @@ extern int g_bn_vec;        // bn.cu
 extern int g_gru_cluster, g_gru_bs;   // gru_cluster.cu
 extern int g_hs_mode;       // conv_tc_hs.cu
 extern int g_wgws_waves;    // conv_tc_wgrad_ws.cu
+extern int g_wgws_mstack, g_wg_dbg;
 extern int g_gl_fpw;        // stft.cu
 
 namespace {
@@ -504,6 +505,8 @@ int vca_set_option(const char* key, int value) {
   if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
   if (eq("gru_bs")) { g_gru_bs = value; return VCA_OK; }
   if (eq("hs_mode")) { g_hs_mode = value; return VCA_OK; }
+  if (eq("wg_dbg")) { g_wg_dbg = value; return VCA_OK; }
+  if (eq("wgws_mstack")) { g_wgws_mstack = value; return VCA_OK; }
   if (eq("wgws_waves")) { g_wgws_waves = value < 1 ? 1 : value; return VCA_OK; }
   if (eq("gl_fpw")) { g_gl_fpw = value < 1 ? 1 : value; return VCA_OK; }
   vca_set_error("vca_set_option: unknown key %s", key);

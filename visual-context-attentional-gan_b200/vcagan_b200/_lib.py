@@ -133,7 +133,7 @@ class _Lib:
                 g = d["by_geom"].setdefault(t, [0, 0.0, 0])
                 g[0] += 1; g[1] += ms; g[2] += f
         for d in agg.values():
-            top = sorted(d.pop("by_geom").items(), key=lambda kv: -kv[1][1])[:24]
+            top = sorted(d.pop("by_geom").items(), key=lambda kv: -kv[1][1])[:200]
             d["top"] = [(k, v[0], round(v[1], 3), round(v[2] / max(v[1], 1e-9) / 1e9, 2)) for k, v in top]
         return agg
 
