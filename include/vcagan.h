@@ -73,6 +73,11 @@ int vca_conv_fwd_tc_stats_supported(const ConvGeom* g);
 int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t stream);
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);
 int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t stream);
+/* the same weight gradient ADDED to a TAP-MAJOR fp32 tensor [taps][Cout][Cin] (16-byte aligned, Cin % 4 == 0) through shared
+ * memory + TMA reduce-add (no scattered atomics); vca_grad_unslab_batched folds the slabs of an optimizer group back into
+ * the parameter layout ([Cout][Cin][taps], what torch.autograd leaves in train.py:210,236's .grad) and zeroes them */
+int vca_conv_wgrad_tc_tm(const ConvGeom* g, const void* dy, const void* x, float* dw_tm, cudaStream_t stream);
+int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, cudaStream_t stream);
 
 
 /* ---- GEMM (nn.Linear: visual_front.py:21, generator.py:147-152,293,303,336; torch.bmm: generator.py:161,167,354;

@@ -761,3 +761,59 @@ def test_conv_ws_stacked_and_tma_store(V, case):
         for key, v in ((b"ws_mode", 1), (b"ws_stack", 1), (b"ws_tma_out", 1), (b"wgws_mstack", 1)):
             L.cdll.vca_set_option(key, v)
         V.set_precision("fp32")
+
+
+TM_CASES = [
+    # N, Cin, H, W, Cout, (kh, kw), (ph, pw)
+    (3, 64, 28, 28, 64, (3, 3), (1, 1)),       # multi-tap kernel, filter rows stacked along M
+    (2, 64, 12, 30, 64, (5, 5), (2, 2)),       # ... 5x5: three passes
+    (2, 128, 20, 25, 128, (5, 5), (2, 2)),     # multi-tap kernel, two 64-channel chunks of Cin, Cout = 128 (no stacking)
+    (2, 256, 20, 19, 512, (3, 3), (1, 1)),     # streaming kernel, 256-wide input-channel tiles, four output-channel tiles
+    (9, 512, 4, 4, 512, (3, 3), (1, 1)),       # ResNet layer 4
+    (2, 96, 10, 21, 64, (5, 5), (2, 2)),       # Cin = 96: a ragged 32-column box
+    (3, 40, 9, 11, 48, (3, 3), (1, 1)),        # ragged channels both ways (Cin % 4 == 0)
+    (300, 128, 1, 1, 256, (1, 1), (0, 0)),     # linear layer: tap-major == parameter layout
+    (5, 128, 5, 9, 128, (5, 5), (0, 0)),       # discriminator head: pad 0, 1 x 5 output map
+]
+
+
+@pytest.mark.parametrize("case", TM_CASES)
+def test_wgrad_tap_major_and_unslab(V, case):
+    """vca_conv_wgrad_tc_tm (TMA reduce-add epilogue into a tap-major slab) == vca_conv_wgrad_tc (scattered atomics into the
+    parameter layout) == fp32 math; two calls accumulate; vca_grad_unslab_batched adds the slab into a parameter-layout
+    gradient that already holds something, and leaves the slab zeroed."""
+    from vcagan_b200.ops import _geom
+    N, Cin, H, W, Cout, k, p = case
+    L = V.lib()
+    g = torch.Generator().manual_seed(sum(case[:5]) + 3 * k[0] + k[1])
+    x = torch.randn(N, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, *k, generator=g) / math.sqrt(Cin * k[0] * k[1])).requires_grad_(True)
+    y = F.conv2d(x, w, None, 1, p)
+    dy = torch.randn(y.shape, generator=g).bfloat16().float()
+    dwr = torch.autograd.grad(y, w, dy)[0]
+    V.set_precision("bf16")
+    try:
+        xd, dyd = cl(x).cuda().bfloat16(), cl(dy).cuda().bfloat16()
+        geom, oshape = _geom(xd.shape, w.shape, (1, 1), p)
+        taps = k[0] * k[1]
+        slab = torch.zeros(taps, Cout, Cin, device="cuda")
+        L.call("vca_conv_wgrad_tc_tm", geom, dyd, xd, slab)
+        L.call("vca_conv_wgrad_tc_tm", geom, dyd, xd, slab)       # accumulates
+        torch.cuda.synchronize()
+        got = slab.permute(1, 2, 0).reshape(Cout, Cin, *k).cpu() / 2
+        e = rel_l2(got, dwr)
+        print("tm case", case, e)
+        assert e < BF16_TOL, (case, e)
+        # un-slab: grad (parameter layout, pre-filled) += slab^T, slab = 0; a second, unrelated job in the same launch
+        grad = torch.full((Cout, Cin, *k), 0.5, device="cuda")
+        slab2 = torch.randn(4, 24, 20, device="cuda"); grad2 = torch.zeros(24, 20, 2, 2, device="cuda"); ref2 = slab2.permute(1, 2, 0).reshape(24, 20, 2, 2).clone()
+        rows, cta = [], 0
+        for gr, sl, co, ci, tp in ((grad, slab, Cout, Cin, taps), (grad2, slab2, 24, 20, 4)):
+            rows.append([gr.data_ptr(), sl.data_ptr(), 0, co, ci, tp, cta, 0]); cta += L.query("vca_pack_job_ctas", co, ci, tp)
+        L.call("vca_grad_unslab_batched", torch.tensor(rows, dtype=torch.int64, device="cuda"), 2, cta)
+        torch.cuda.synchronize()
+        assert rel_l2((grad.cpu() - 0.5) / 2, dwr) < BF16_TOL
+        assert torch.equal(grad2, ref2)
+        assert float(slab.abs().max()) == 0.0 and float(slab2.abs().max()) == 0.0
+    finally:
+        V.set_precision("fp32")

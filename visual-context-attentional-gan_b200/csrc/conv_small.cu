@@ -243,9 +243,73 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const long long* __re
   }
 }
 
+// ---- batched un-slab: tap-major gradient slabs folded back into the parameter layout, ONE launch per optimizer group ----
+// The tcgen05 wgrad kernels add a filter's gradient to a TAP-MAJOR fp32 slab [taps][Cout][Cin] (vca_conv_wgrad_tc_tm: TMA
+// reduce-add boxes instead of scattered 4-byte atomics).  Job table as above with j[0] = the parameter's .grad
+// ([Cout][Cin][taps], ADDED to), j[1] = its slab (read, then left ZEROED for the next step), j[2] unused.
+__global__ void __launch_bounds__(256) unslab_batched_kernel(const long long* __restrict__ jobs, int njobs) {
+  __shared__ float s[PK_T][PK][PK + 1];
+  int lo = 0, hi = njobs - 1;
+  const long long me = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (jobs[(long long)mid * 8 + 6] <= me) lo = mid; else hi = mid - 1;
+  }
+  const long long* j = jobs + (long long)lo * 8;
+  float* __restrict__ grad = reinterpret_cast<float*>(j[0]);
+  float* __restrict__ slab = reinterpret_cast<float*>(j[1]);
+  const int Cout = (int)j[3], Cin = (int)j[4], taps = (int)j[5];
+  int local = (int)(me - j[6]);
+  const int tiles_ci = (Cin + PK - 1) / PK, tiles_co = (Cout + PK - 1) / PK;
+  const int bx = local % tiles_ci; local /= tiles_ci;
+  const int by = local % tiles_co; const int bz = local / tiles_co;
+  const int co0 = by * PK, ci0 = bx * PK, t0 = bz * PK_T;
+  const int tc = min(PK_T, taps - t0);
+  const int n = PK * PK * tc;
+  constexpr int IT = PK * PK * PK_T / 256;       // 32 elements per thread: ALL loads of a phase are issued before the first
+  float v[IT];                                   // dependent store (a load-store chain per element ran at 170 GB/s)
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int a = i % PK; int r = i / PK; const int b = r % PK; const int t = r / PK;
+    v[k] = (i < n && co0 + b < Cout && ci0 + a < Cin) ? slab[((long long)(t0 + t) * Cout + co0 + b) * Cin + ci0 + a] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int a = i % PK; int r = i / PK; const int b = r % PK; const int t = r / PK;
+    if (i < n) {
+      s[t][b][a] = v[k];
+      if (co0 + b < Cout && ci0 + a < Cin) slab[((long long)(t0 + t) * Cout + co0 + b) * Cin + ci0 + a] = 0.f;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
+    v[k] = (i < n && co0 + co < Cout && ci0 + ci < Cin) ? grad[((long long)(co0 + co) * Cin + ci0 + ci) * taps + t0 + t] : 0.f;
+  }
+#pragma unroll
+  for (int k = 0; k < IT; ++k) {
+    const int i = threadIdx.x + k * 256;
+    const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
+    if (i < n && co0 + co < Cout && ci0 + ci < Cin) grad[((long long)(co0 + co) * Cin + ci0 + ci) * taps + t0 + t] = v[k] + s[t][co][ci];
+  }
+}
+
 }  // namespace
 
 extern "C" {
+// jobs: device table (8 x int64 per job: grad, slab, 0, Cout, Cin, taps, first CTA, 0); total_ctas = sum of
+// vca_pack_job_ctas over the jobs.  grad += slab (transposed), slab = 0.  Must be ordered after every kernel that adds to
+// either buffer (it is a plain read-modify-write).
+int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, cudaStream_t s) {
+  VCA_CHECK_ARG(jobs && njobs > 0 && total_ctas > 0 && total_ctas < 0x7fffffffLL);
+  unslab_batched_kernel<<<(unsigned)total_ctas, 256, 0, s>>>(jobs, njobs);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
 // CTAs a job of this shape occupies in vca_pack_conv_weights_batched (the host builds the CTA offsets of the table with it)
 int vca_pack_job_ctas(int Cout, int Cin, int taps) {
   if (Cout <= 0 || Cin <= 0 || taps <= 0) return 0;

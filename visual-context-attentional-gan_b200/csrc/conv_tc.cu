@@ -27,7 +27,7 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
 int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
                 const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
-int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s);
+int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s, int tm);
 extern int g_wg_dbg;
 
 namespace {
@@ -257,10 +257,12 @@ struct WgradParams {
   uint32_t tmem_cols;
   float* dw;                     // [Cout][Cin][taps] fp32, accumulated with red.add
   int dbg;
+  int tm;                        // 1: the destination is TAP-MAJOR [taps][Cout][Cin] and is added to by TMA reduce (tmW)
 };
 
 __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY,
-                                                            const __grid_constant__ CUtensorMap tmX, const WgradParams p) {
+                                                            const __grid_constant__ CUtensorMap tmX,
+                                                            const __grid_constant__ CUtensorMap tmW, const WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
@@ -347,6 +349,23 @@ __global__ void __launch_bounds__(192) conv_tc_wgrad_kernel(const __grid_constan
       const int co = co0 + q * 32 + lane;
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+      if (p.tm) {
+        // tap-major destination: stage the tile in the (now idle) pipeline buffers, add it with TMA reduce boxes
+        for (int c = 0; c < p.BNc; c += 16) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+          dw_stage16(smem + (size_t)(c >> 5) * 16384, q * 32 + lane, c & 16, v);
+        }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64 && !p.dbg) {
+          for (int c = 0; c < p.BNc && ci0 + c < p.Cin; c += 32)
+            for (int h = 0; h < 2 && co0 + 64 * h < p.Cout; ++h)
+              tma_reduce_add_3d(&tmW, smem + (size_t)(c >> 5) * 16384 + h * 8192, ci0 + c, co0 + 64 * h, tap);
+          bulk_commit();
+          bulk_wait_all();
+        }
+      } else
       for (int c = 0; c < p.BNc; c += 16) {
         float v[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
@@ -552,11 +571,11 @@ int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void
 int vca_conv_dgrad_tc(const ConvGeom* g, const void* dy, const void* wf, void* dx, cudaStream_t s) {
   return vca_conv_dgrad_tc_ws(g, dy, wf, dx, nullptr, 0, s);
 }
-// dw fp32 [Cout][Cin][taps], zero on entry (accumulated with red.add across pixel splits).
-int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t s) {
+static int wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, int tm, cudaStream_t s) {
   VCA_CHECK_ARG(g && dy && x && dw && vca_conv_tc_supported(g, 2));
+  VCA_CHECK_ARG(!tm || (g->Cin % 4 == 0 && (reinterpret_cast<uintptr_t>(dw) & 15) == 0));
   {
-    const int r = conv_wgrad_ws_try(*g, dy, x, dw, s);   // multi-tap halo-resident kernel for <= 64 input channels
+    const int r = conv_wgrad_ws_try(*g, dy, x, dw, s, tm);   // multi-tap halo-resident kernel for <= 64 input channels
     if (r != 0) return r < 0 ? r : VCA_OK;
   }
   WgradParams p;
@@ -578,7 +597,7 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
   p.atom_bytes = (uint32_t)box_px * 128u;
   p.ksteps = (uint32_t)((box_px + 15) / 16);
   p.tmem_cols = pow2_cols(p.BNc);
-  p.dw = dw; p.dbg = g_wg_dbg;
+  p.dw = dw; p.dbg = g_wg_dbg; p.tm = tm;
   const size_t stage_bytes = 2 * A_STAGE_BYTES + (size_t)p.b_atoms * A_STAGE_BYTES;
   int stages = (int)((190 * 1024) / stage_bytes);
   if (stages > 4) stages = 4; if (stages < 2) stages = 2;
@@ -590,11 +609,15 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
   p.ptiles_per_split = (p.num_ptiles + split - 1) / split;
   split = (p.num_ptiles + p.ptiles_per_split - 1) / p.ptiles_per_split;
 
-  CUtensorMap tmDY, tmX;
+  CUtensorMap tmDY, tmX, tmW;
   long long dY[4] = {g->Cout, g->OW, g->OH, g->N}; int bx[4] = {KC, p.tw, p.th, p.tn};
   long long dX[4] = {g->Cin, g->IW, g->IH, g->N};
   int rc = make_map(&tmDY, dy, 4, dY, bx); if (rc) return rc;
   rc = make_map(&tmX, x, 4, dX, bx); if (rc) return rc;
+  if (tm) {
+    if ((size_t)stages * stage_bytes < (size_t)((p.BNc + 31) / 32) * 16384) { vca_set_error("wgrad: staging does not fit"); return VCA_ERR_UNSUPPORTED; }
+    rc = make_map_dw(&tmW, dw, g->Cin, g->Cout, p.taps); if (rc) return rc;
+  } else tmW = tmX;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
@@ -604,9 +627,16 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
   }
   VCA_CHECK_ARG((long long)co_tiles * p.ci_tiles <= 65535 && p.taps <= 65535);
   dim3 grid((unsigned)split, (unsigned)(co_tiles * p.ci_tiles), (unsigned)p.taps);
-  conv_tc_wgrad_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, p);
+  conv_tc_wgrad_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, tmW, p);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
+// dw fp32 [Cout][Cin][taps] (the parameter layout), ADDED to with red.add across pixel splits.
+int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw, cudaStream_t s) { return wgrad_tc(g, dy, x, dw, 0, s); }
+// Same gradient ADDED to a TAP-MAJOR fp32 tensor [taps][Cout][Cin] (16-byte aligned, Cin % 4 == 0) through shared memory and
+// TMA reduce-add boxes -- full-line adds in L2 instead of one scattered 4-byte atomic per element.  For a pointwise
+// conv / linear layer (taps = 1) the two layouts coincide; otherwise vca_grad_unslab_batched folds the slabs of an
+// optimizer group back into the parameter layout in one launch.
+int vca_conv_wgrad_tc_tm(const ConvGeom* g, const void* dy, const void* x, float* dw_tm, cudaStream_t s) { return wgrad_tc(g, dy, x, dw_tm, 1, s); }
 
 }  // extern "C"

@@ -52,10 +52,12 @@ struct WgWsParams {
   uint32_t x_stage_bytes, a_stage_bytes, x_tx_bytes, a_row_tx_bytes, tmem_cols;
   float* dw;
   int dbg;               // probe: 1 = no atomics (tools/conv_shapes.py --opt wg_dbg=1)
+  int tm;                // 1: tap-major destination [taps][Cout][Cin], added to by TMA reduce (tmW)
 };
 
 __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_constant__ CUtensorMap tmDY,
-                                                                  const __grid_constant__ CUtensorMap tmX, const WgWsParams p) {
+                                                                  const __grid_constant__ CUtensorMap tmX,
+                                                                  const __grid_constant__ CUtensorMap tmW, const WgWsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   const int S = p.stages;
@@ -151,6 +153,33 @@ __global__ void __launch_bounds__(192, 1) conv_tc_wgrad_ws_kernel(const __grid_c
       const int co = p.mstack ? (q & 1) * 32 + lane : co0 + q * 32 + lane;
       mbar_wait(accum_bar, 0);
       tc_fence_after();
+      if (p.tm) {
+        // tap-major destination: stage every tap's [128 x 64] block (two 32-column blocks) in the idle pipeline buffers,
+        // then one TMA reduce-add box per (tap, 32 input channels, 64 output channels)
+        for (int g = 0; g < p.G; ++g)
+          for (int c = 0; c < KC; c += 16) {
+            if (ci0 + c >= p.Cin) break;                                // warp-uniform
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * KC + c), v);
+            dw_stage16(smem + (size_t)(g * 2 + (c >> 5)) * 16384, q * 32 + lane, c & 16, v);
+          }
+        fence_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64 && !p.dbg) {
+          for (int g = 0; g < p.G; ++g)
+            for (int c = 0; c < KC && ci0 + c < p.Cin; c += 32)
+              for (int h = 0; h < 2; ++h) {
+                // rows 0..63 / 64..127 of the block: output channels co0 + 64 h of the top tap, or (stacked) all 64 output
+                // channels of the top / bottom tap
+                const int tap = p.mstack ? (h ? p.bot_tap[grp][g] : p.top_tap[grp][g]) : p.top_tap[grp][g];
+                const int cob = p.mstack ? 0 : co0 + 64 * h;
+                if (tap < 0 || cob >= p.Cout) continue;
+                tma_reduce_add_3d(&tmW, smem + (size_t)(g * 2 + (c >> 5)) * 16384 + h * 8192, ci0 + c, cob, tap);
+              }
+          bulk_commit();
+          bulk_wait_all();
+        }
+      } else
       for (int g = 0; g < p.G; ++g) {
         const int tap = bottom ? p.bot_tap[grp][g] : p.top_tap[grp][g];
         if (tap < 0) continue;                                         // warp-uniform
@@ -180,7 +209,7 @@ int g_wgws_mstack = 1; // filter-row stacking along M for Cout <= 64
 int g_wgws_waves = 1;  // "wgws_waves": CTAs per SM over the kernel's life (more = shorter CTAs, friendlier to concurrent streams)
 
 // 1 = launched, 0 = not applicable, < 0 error.  dw fp32 [Cout][Cin][taps], zero on entry.
-int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s) {
+int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s, int tm) {
   if (!g_wgws_mode) return 0;
   const int taps = g.KH * g.KW;
   // Cin > 64 runs as 64-channel chunks (one CTA column each): the dY tile is then re-read per chunk, but a stage still
@@ -269,7 +298,7 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   if (stages < 2) return 0;
   p.stages = stages;
   p.tmem_cols = pow2_cols(p.G * KC);
-  p.dw = dw; p.dbg = g_wg_dbg;
+  p.dw = dw; p.dbg = g_wg_dbg; p.tm = tm;
   const int co_tiles = (g.Cout + 127) / 128;
   const long long base_ctas = (long long)co_tiles * p.ci_tiles * p.groups;
   extern int g_wgws_waves;
@@ -279,12 +308,14 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   split = (p.num_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
   const size_t smem = (size_t)stages * stage_bytes + ATOM_BYTES + 1024 + 512;   // + one atom of read-only slack
 
-  CUtensorMap tmDY, tmX;
+  if (tm && (size_t)stages * stage_bytes < (size_t)p.G * 2 * 16384) return 0;   // no room to stage the tile: streaming kernel
+  CUtensorMap tmDY, tmX, tmW;
   long long dY[4] = {g.Cout, g.OW, g.OH, g.N}; int bY[4] = {KC, p.tw, 1, 1};
   long long dX[4] = {g.Cin, g.IW, g.IH, g.N}; int bX[4] = {KC, p.P, p.x_rows, 1};
   if (bX[1] > 256 || bX[2] > 256 || bY[1] > 256) return 0;
   int rc = make_map(&tmDY, dy, 4, dY, bY); if (rc) return rc;
   rc = make_map(&tmX, x, 4, dX, bX); if (rc) return rc;
+  if (tm) { rc = make_map_dw(&tmW, dw, g.Cin, g.Cout, taps); if (rc) return rc; } else tmW = tmX;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(conv_tc_wgrad_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -294,7 +325,7 @@ int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* d
   }
   if ((long long)co_tiles * p.ci_tiles > 65535) return 0;
   dim3 grid((unsigned)split, (unsigned)(co_tiles * p.ci_tiles), (unsigned)p.groups);
-  conv_tc_wgrad_ws_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, p);
+  conv_tc_wgrad_ws_kernel<<<grid, 192, smem, s>>>(tmDY, tmX, tmW, p);
   VCA_LAUNCH_CHECK();
   return 1;
 }

@@ -29,6 +29,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
+    grad_slab = True        # ... tcgen05 wgrads through a tap-major slab + TMA reduce-add (trainer.FlatGroup.flush_slabs)
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
@@ -298,12 +299,22 @@ def _conv_dgrad_raw(dy, w, stride, pad, xshape):
     return dx
 
 
-def _conv_wgrad_raw(x, dy, stride, pad, wshape, out=None):
-    """dw (fp32, parameter layout); every wgrad kernel ADDS into its destination, so `out` may be a live .grad view."""
+def _conv_wgrad_raw(x, dy, stride, pad, wshape, out=None, param=None):
+    """dw (fp32, parameter layout); every wgrad kernel ADDS into its destination, so `out` may be a live .grad view.
+    param: the re-homed parameter `out` is the .grad of.  Its tcgen05 wgrad then goes through the TMA reduce-add epilogue
+    (vca_conv_wgrad_tc_tm) into the parameter's TAP-MAJOR slab (FlatGroup.flush_slabs folds it into .grad before the
+    gradients are consumed), or straight into .grad for a pointwise conv / linear layer, where the two layouts coincide."""
     g, oshape = _geom(x.shape, wshape, stride, pad)
     assert tuple(dy.shape) == tuple(oshape), (dy.shape, oshape)
     dw = torch.zeros(wshape, dtype=torch.float32, device=x.device) if out is None else out
     if _tc_ok(g, 2, x.dtype):
+        taps = g.KD * g.KH * g.KW
+        slab = None
+        if cfg.grad_slab and g.Cin % 4 == 0 and out is not None and param is not None:
+            slab = out if taps == 1 else getattr(param, "_vca_slab", None)
+        if slab is not None and slab.data_ptr() % 16 == 0:
+            lib().call("vca_conv_wgrad_tc_tm", g, dy, x, slab)
+            return dw
         lib().call("vca_conv_wgrad_tc", g, dy, x, dw)
     else:
         lib().call("vca_conv_wgrad_simt", _dt(x), g, dy, x, dw)
@@ -344,7 +355,7 @@ class ConvFn(Function):
             # they run on a side stream and overlap the dgrad chain (joined by Trainer._join_branches before Adam).
             with _param_grad_stream(x, dy):
                 if w_sink is not None:
-                    _conv_wgrad_raw(x, dy, ctx.stride, ctx.pad, tuple(w.shape), out=w_sink)   # dw stays None
+                    _conv_wgrad_raw(x, dy, ctx.stride, ctx.pad, tuple(w.shape), out=w_sink, param=w)   # dw stays None
                 if b_sink is not None:
                     _colsum_raw(dy, out=b_sink, accumulate=True)
         if _needed(ctx, 0):
@@ -380,7 +391,7 @@ class ConvDgradFn(Function):
             sink = _grad_sink(w)
             if sink is not None:
                 with _param_grad_stream(ggx, dy):
-                    _conv_wgrad_raw(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape), out=sink)
+                    _conv_wgrad_raw(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape), out=sink, param=w)
             else:
                 g_w = ConvWgradFn.apply(ggx, dy, ctx.stride, ctx.pad, tuple(w.shape))
         return g_dy, g_w, None, None, None

@@ -46,6 +46,35 @@ class FlatGroup:
             p.grad = self.grad[o:o + n].view(p.shape)
             p._vca_epoch = self.epoch
             p._vca_flat = True   # ops._grad_sink: backward kernels may accumulate straight into p.grad
+        # Tap-major gradient slabs for the conv filters (ops._conv_wgrad_raw): the tcgen05 wgrad kernels add [taps][Cout][Cin]
+        # tiles with TMA reduce boxes instead of scattering 4-byte atomics over the [Cout][Cin][taps] parameter layout;
+        # flush_slabs() folds them into .grad (one launch) and leaves them zeroed.
+        self.slab = torch.zeros(off, dtype=torch.float32, device=dev)
+        self._slab_jobs = []     # (param index, row of the job table without the CTA offset)
+        for i, (p, o, n) in enumerate(zip(self.params, self.offsets, self.sizes)):
+            if p.dim() == 4 and p.shape[2] * p.shape[3] > 1 and p.shape[1] % 4 == 0:
+                taps = p.shape[2] * p.shape[3]
+                p._vca_slab = self.slab[o:o + n].view(taps, p.shape[0], p.shape[1])
+                self._slab_jobs.append((i, [self.grad.data_ptr() + 4 * o, self.slab.data_ptr() + 4 * o, 0, p.shape[0], p.shape[1], taps]))
+        self._slab_tables = {}
+
+    def flush_slabs(self, lo: int = 0, hi: Optional[int] = None):
+        """grad += slab (transposed into the parameter layout), slab = 0, for the parameters whose flat offset lies in
+        [lo, hi) -- the same element ranges FusedAdam.step / the data-parallel all-reduce take.  Call it on a stream that
+        is ordered after every backward kernel of those parameters (Trainer: right after _join_branches)."""
+        hi = self.numel if hi is None else hi
+        key = (lo, hi)
+        tab = self._slab_tables.get(key)
+        if tab is None:
+            rows, cta = [], 0
+            for i, row in self._slab_jobs:
+                if lo <= self.offsets[i] < hi:
+                    rows.append(row + [cta, 0])
+                    cta += lib().query("vca_pack_job_ctas", row[3], row[4], row[5])
+            tab = (torch.tensor(rows, dtype=torch.int64, device=self.grad.device) if rows else None, len(rows), cta)
+            self._slab_tables[key] = tab
+        if tab[0] is not None:
+            lib().call("vca_grad_unslab_batched", tab[0], tab[1], tab[2])
 
     def zero_grad(self):
         self.grad.zero_()
@@ -399,6 +428,7 @@ class Trainer:
         else:
             dis_loss.backward(retain_graph=True, inputs=self.D.params + self._vf_cnn_params())
         self._join_branches()
+        self.D.flush_slabs()         # tap-major wgrad slabs -> .grad (the all-reduce / Adam that follow read .grad)
         self._st = dict(mel=mel, mel1=mel1, mel2=mel2, spec=spec, phon=phon, phon_leaf=phon_leaf, sdet=sdet, g=g, T=T,
                         sent=sent, phon_g=phon_g, sent_g=sent_g,
                         out=dict(dis_loss=dis_loss.detach(), sync_loss=sync_loss.detach(), real_loss=real_loss.detach(),
@@ -440,6 +470,10 @@ class Trainer:
         else:
             gen_loss.backward(inputs=self.G.params)
         self._join_branches()
+        if self.split_g_backward:
+            self.G.flush_slabs(lo=self._vf_numel)       # gen + post: reduced / stepped first
+        else:
+            self.G.flush_slabs()
         ops.flush_deferred_counters()
         st["out"].update(gen_loss=gen_loss.detach(), g_sync=g_sync.detach(), recon=recon.detach(), g1=g[0].detach(),
                          g2=g[1].detach(), g3=g[2].detach(), gs=gs.detach())
@@ -455,6 +489,7 @@ class Trainer:
         torch.autograd.backward([st["phon"], st["phon"], st["sent"]],
                                 [st["phon_g"].grad, st["phon_leaf"].grad, st["sent_g"].grad], inputs=self._vf_params)
         self._join_branches()
+        self.G.flush_slabs(hi=self._vf_numel)
 
     def _phase_end_a(self):
         """G optimizer: with a split backward the gen + post slice first (its gradients were reduced long ago), so that the
