@@ -450,7 +450,7 @@ def run_train(args):
         return
     pk = peaks()
     roof, exec_gf = None, None
-    fam = {k: v for k, v in prof.items() if k.startswith("vca_conv_") and (k.endswith("_tc") or k.endswith("_tc_ws"))}
+    fam = {k: v for k, v in prof.items() if k.startswith("vca_conv_") and k.endswith(("_tc", "_tc_ws", "_tc_tm", "_tc_stats", "_tc_epi"))}
     flops = sum(v["flops"] for v in fam.values()); tms = sum(v["ms"] for v in fam.values())
     n_l = sum(v["n"] for v in fam.values())
     total_ms = sum(v["ms"] for v in prof.values())

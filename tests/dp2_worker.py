@@ -52,6 +52,8 @@ def main():
     res = dict(G=sample(tr.G.grad), D=sample(tr.D.grad), Gw=float(tr.G.flat.double().sum()), Dw=float(tr.D.flat.double().sum()),
                losses={k: float(v) for k, v in out.items() if torch.is_tensor(v) and v.numel() == 1}, in_sync=tr.replicas_in_sync())
     torch.save(res, os.path.join(out_dir, f"rank{rank}.pt"))
+    if rank == 0:      # the exchanged D gradient in full: the per-shard oracle applies exactly this one (see the test)
+        torch.save(tr.D.grad.cpu(), os.path.join(out_dir, "d_grad_sum.pt"))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -54,11 +54,31 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
         # test_step_bf16_gradient_bound); the exchange itself is exact, as the fp32 case shows
         tol = 2e-5 if precision == "fp32" else 0.15
         assert e < tol, e
+        # The G phase runs against discriminators stepped with the EXCHANGED gradient.  Adam's first step moves every weight
+        # by +-lr whatever the gradient's size, so the bf16 noise in d_mean (e above: ~1e-1) would flip thousands of update
+        # signs and hand the oracle a different discriminator than the ranks trained against (measured: G mismatch 0.4).
+        # The oracle therefore applies the ranks' own reduced D gradient, which the D check above has just validated.
+        d_used = torch.load(os.path.join(tmp_path, "d_grad_sum.pt")).cuda() / 2.0
+        assert rel_l2(d_used, d_mean) < tol
+        # bf16 yard-stick, measured live: a third single-GPU trainer repeats shard 0 with the same D gradient.  At this B = 2
+        # random-init case bf16-ulp differences (fp32 atomics order in split-K / wgrad) are amplified by the train-mode
+        # BatchNorms to 3-6e-2 in the forward outputs and ~0.35 in the G gradient BETWEEN TWO IDENTICAL RUNS
+        # (tools/g_noise_probe.py; the reference under autocast is 4-10e-2 away from its own fp32 forward).  The bf16 bound
+        # on the exchanged G gradient is therefore 2 x that run-to-run figure; the fp32 case pins the exchange itself.
+        g_noise = None
+        if precision != "fp32":
+            tr3 = Trainer(precision=precision, state={m: make_state(spec, m) for m in O.MODULES}, dropout=False)
+            vid, mel, sp, noise, lens = W.shard_inputs(0)
+            tr3._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), lens, noise)
+            trs.append(tr3)
         for tr in trs:
-            tr.D.grad.copy_(d_mean)
+            tr.D.grad.copy_(d_used)
             tr._phase_g_pre(); tr._phase_g(); tr._phase_g2(); tr._phase_end_a()
             outs.append(tr._phase_end_b())
         torch.cuda.synchronize()
+        if precision != "fp32":
+            g_noise = rel_l2(W.sample(trs[2].G.grad), W.sample(trs[0].G.grad))
+            print(f"{precision}: run-to-run noise of the single-GPU G gradient (same shard, same D gradient): {g_noise:.3e}")
         for i in range(2):      # each rank's losses are its own shard's losses
             for k, v in outs[i].items():
                 if torch.is_tensor(v) and v.numel() == 1:
@@ -66,7 +86,12 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
         g_mean = (trs[0].G.grad + trs[1].G.grad) / 2.0
         e = rel_l2(W.sample(g_mean), ranks[0]["G"] / 2.0)
         print(f"{precision}: 2-rank all-reduced G gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
-        assert e < tol, e
+        # by slice: the visual front-end (train-mode BatchNorm at B = 2: ill-conditioned) and generator + Postnet
+        n_s, cut = ranks[0]["G"].numel(), int(round(trs[0]._vf_numel / trs[0].G.numel * ranks[0]["G"].numel()))
+        sm, sr = W.sample(g_mean), ranks[0]["G"] / 2.0
+        e_vf, e_gp = rel_l2(sm[:cut], sr[:cut]), rel_l2(sm[cut:], sr[cut:])
+        print(f"{precision}:   v_front slice {e_vf:.3e}  (|g| {float(sr[:cut].norm()):.3e}), gen+post slice {e_gp:.3e} (|g| {float(sr[cut:].norm()):.3e})")
+        assert e < (tol if g_noise is None else max(tol, 2.0 * g_noise)), (e, g_noise)
         # ... and therefore the same weights after the step (both single-GPU oracles applied g_mean? no: each applied its own
         # shard's G gradient -- only the D weights are comparable)
         if precision == "fp32":

@@ -817,3 +817,26 @@ def test_wgrad_tap_major_and_unslab(V, case):
         assert float(slab.abs().max()) == 0.0 and float(slab2.abs().max()) == 0.0
     finally:
         V.set_precision("fp32")
+
+
+def test_first_backward_op_on_fresh_autograd_thread(V):
+    """Regression: cuTensorMapEncodeTiled needs the primary context bound to the calling thread.  In a fresh process the
+    autograd worker thread has made no runtime call when its first node is one of our TMA kernels (attention backward, a
+    pointwise conv's dgrad); it used to fail with CUDA_ERROR_INVALID_CONTEXT (201)."""
+    import os, subprocess, sys
+    from conftest import ROOT
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {os.path.join(ROOT, 'visual-context-attentional-gan_b200')!r})\n"
+        "import vcagan_b200 as V\n"
+        "V.set_precision('bf16')\n"
+        "q, k, v = (torch.randn(2, n, 256, device='cuda').bfloat16().requires_grad_(True) for n in (40, 20, 20))\n"
+        "lens = torch.tensor([20, 13], dtype=torch.int32, device='cuda')\n"
+        "o = V.ops.attention(q, k, v, lens, 1 / 16)\n"
+        "o.backward(torch.randn_like(o))\n"
+        "x = torch.randn(8, 1, 1, 64, device='cuda').bfloat16().requires_grad_(True)\n"
+        "w = torch.randn(64, 64, 1, 1, device='cuda').requires_grad_(True)\n"
+        "V.ops.conv(x, w, None, (1, 1), (0, 0)).float().sum().backward()\n"
+        "torch.cuda.synchronize(); print('ok')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

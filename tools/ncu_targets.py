@@ -32,9 +32,9 @@ def conv_case(N, H, W, Cin, Cout, k, p, stats=False, wgrad=False):
     y = torch.empty(oshape, dtype=torch.bfloat16, device=dev)
     wf, wd = _packed(w, torch.bfloat16)
     sums = torch.zeros(2 * Cout, dtype=torch.float64, device=dev)
-    for _ in range(2):
-        if wgrad:
-            L.call("vca_conv_wgrad_tc", g, torch.randn(oshape, device=dev).bfloat16(), x, torch.zeros_like(w))
+    for _ in range(1 if os.environ.get("VCA_NCU") else 2):
+        if wgrad:   # the production path: TMA reduce-add epilogue into the tap-major slab
+            L.call("vca_conv_wgrad_tc_tm", g, torch.randn(oshape, device=dev).bfloat16(), x, torch.zeros(k[0] * k[1], Cout, Cin, device=dev))
         elif stats:
             L.call("vca_conv_fwd_tc_stats", g, x, wd, None, y, sums)
         else:
@@ -45,6 +45,9 @@ def conv_case(N, H, W, Cin, Cout, k, p, stats=False, wgrad=False):
 conv_case(2400, 28, 28, 64, 64, (3, 3), (1, 1), stats=True)
 conv_case(32, 20, 75, 512, 512, (5, 5), (2, 2))
 conv_case(2400, 28, 28, 64, 64, (3, 3), (1, 1), wgrad=True)
+conv_case(32, 40, 150, 64, 64, (5, 5), (2, 2))                 # 64-ch 5x5: two 32-channel CTA columns, five taps per MMA (N = 160)
+conv_case(2400, 14, 14, 128, 128, (3, 3), (1, 1), stats=False)  # ResNet layer 2 on the stacked weights-stationary kernel
+conv_case(32, 20, 75, 512, 512, (5, 5), (2, 2), wgrad=True)     # streaming wgrad, 256-wide tiles, TMA reduce-add epilogue
 B, Tq, S = 16, 500, 250
 q, k, v = (torch.randn(B, n, 256, device=dev).bfloat16().requires_grad_(True) for n in (Tq, S, S))
 lens = torch.randint(S // 2, S + 1, (B,), device=dev, dtype=torch.int32)

@@ -349,6 +349,10 @@ __global__ void __launch_bounds__(256) bn_prelu_maxpool_bwd_apply_kernel(const b
                                                                          const bf16* __restrict__ x, bf16* __restrict__ dx, int NF, int H,
                                                                          int W, int C, int OH, int OW, BnParams p,
                                                                          const double* __restrict__ sums, int train) {
+  // One thread = 8 channels of a 2 x 2 block of positions  h in {2a-1, 2a}, w in {2b-1, 2b}.  Those four positions lie in
+  // (at most) the four pooling windows (a-1 | a) x (b-1 | b), whose pooled gradient + argmax codes are fetched ONCE: 4 window
+  // loads + 4 x loads for 4 outputs, all issued before the first use (the one-position-per-thread version gathered 4 windows
+  // per output, one dependent batch at a time: 1.3 TB/s).
   constexpr int V = 8;
   const int CV = C / V;
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -362,51 +366,61 @@ __global__ void __launch_bounds__(256) bn_prelu_maxpool_bwd_apply_kernel(const b
     m1[i] = train ? (float)(sums[c] * invR) : 0.f;
     m2[i] = train ? (float)(sums[C + c] * invR) : 0.f;
   }
-  const long long total = (long long)NF * H * W * CV;
+  const int AB = H / 2 + 1, BB = W / 2 + 1;
+  const long long total = (long long)NF * AB * BB * CV;
   for (long long i = tid; i < total; i += (long long)gridDim.x * blockDim.x) {
     unsigned r = (unsigned)(i / CV);
-    const int w = (int)(r % (unsigned)W); r /= (unsigned)W;
-    const int h = (int)(r % (unsigned)H); const int n = (int)(r / (unsigned)H);
-    const int ohs[2] = {h >> 1, (h + 1) >> 1}, ows[2] = {w >> 1, (w + 1) >> 1};
-    const bool vh[2] = {ohs[0] < OH, ohs[1] < OH && ohs[1] != ohs[0]}, vw[2] = {ows[0] < OW, ows[1] < OW && ows[1] != ows[0]};
-    const uint4 xr = *reinterpret_cast<const uint4*>(x + i * V);
-    float g[4][V]; unsigned long long codes[4];
+    const int bb = (int)(r % (unsigned)BB); r /= (unsigned)BB;
+    const int aa = (int)(r % (unsigned)AB); const int n = (int)(r / (unsigned)AB);
+    const int hs[2] = {2 * aa - 1, 2 * aa}, ws[2] = {2 * bb - 1, 2 * bb};
+    const bool hv[2] = {hs[0] >= 0, hs[1] < H}, wv[2] = {ws[0] >= 0, ws[1] < W};
+    // windows q = 2 * i + j: (aa - 1 + i, bb - 1 + j)
+    uint4 gr[4]; unsigned long long codes[4]; uint4 xr[4];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int q = a * 2 + b;
-        codes[q] = 0xffffffffffffffffull;
-#pragma unroll
-        for (int k = 0; k < V; ++k) g[q][k] = 0.f;
-        if (vh[a] && vw[b]) {
-          const long long o = (((long long)n * OH + ohs[a]) * OW + ows[b]) * C + cv * V;
-          Vec<bf16>::load(dy + o, g[q]);
-          codes[q] = *reinterpret_cast<const unsigned long long*>(idx + o);
-        }
+    for (int q = 0; q < 4; ++q) {
+      const int oh = aa - 1 + (q >> 1), ow = bb - 1 + (q & 1);
+      codes[q] = 0xffffffffffffffffull; gr[q] = make_uint4(0, 0, 0, 0);
+      if (oh >= 0 && oh < OH && ow >= 0 && ow < OW) {
+        const long long o = (((long long)n * OH + oh) * OW + ow) * C + cv * V;
+        gr[q] = *reinterpret_cast<const uint4*>(dy + o);
+        codes[q] = *reinterpret_cast<const unsigned long long*>(idx + o);
       }
-    float acc[V], xv[V];
+    }
 #pragma unroll
-    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int q = 0; q < 4; ++q) {
+      xr[q] = make_uint4(0, 0, 0, 0);
+      if (hv[q >> 1] && wv[q & 1]) xr[q] = *reinterpret_cast<const uint4*>(x + (((long long)n * H + hs[q >> 1]) * W + ws[q & 1]) * C + cv * V);
+    }
+    float g[4][V];
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+    for (int q = 0; q < 4; ++q) Vec<bf16>::unpack(gr[q], g[q]);
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int q = a * 2 + b;
-        const unsigned code = (unsigned)((h - (ohs[a] * 2 - 1)) * 3 + (w - (ows[b] * 2 - 1)));
+    for (int pq = 0; pq < 4; ++pq) {                   // position (hs[pi], ws[pj])
+      const int pi = pq >> 1, pj = pq & 1;
+      if (!(hv[pi] && wv[pj])) continue;
+      float acc[V], xv[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) acc[k] = 0.f;
+      // an odd coordinate (index 0) lies in windows (-1 | 0) at in-window offsets (2 | 0); an even one only in window 0 at offset 1
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int qi = q >> 1, qj = q & 1;
+        if ((pi == 1 && qi == 0) || (pj == 1 && qj == 0)) continue;
+        const unsigned code = (unsigned)((pi == 1 ? 1 : (qi == 0 ? 2 : 0)) * 3 + (pj == 1 ? 1 : (qj == 0 ? 2 : 0)));
 #pragma unroll
         for (int k = 0; k < V; ++k)
           if ((unsigned)((codes[q] >> (8 * k)) & 0xffull) == code) acc[k] += g[q][k];
       }
-    Vec<bf16>::unpack(xr, xv);
+      Vec<bf16>::unpack(xr[pq], xv);
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-      const float xh = (xv[k] - mu[k]) * is[k];
-      const float pre = xh * ga[k] + be[k];
-      const float dpre = pre > 0.f ? acc[k] : acc[k] * sl[k];
-      xv[k] = (dpre - m1[k] - xh * m2[k]) * ga[k] * is[k];
+      for (int k = 0; k < V; ++k) {
+        const float xh = (xv[k] - mu[k]) * is[k];
+        const float pre = xh * ga[k] + be[k];
+        const float dpre = pre > 0.f ? acc[k] : acc[k] * sl[k];
+        xv[k] = (dpre - m1[k] - xh * m2[k]) * ga[k] * is[k];
+      }
+      Vec<bf16>::store(dx + (((long long)n * H + hs[pi]) * W + ws[pj]) * C + cv * V, xv);
     }
-    Vec<bf16>::store(dx + i * V, xv);
   }
 }
 
@@ -648,7 +662,7 @@ int vca_bn_prelu_maxpool_bwd(const void* dy, const unsigned char* idx, const voi
     bn_act_bwd_reduce_kernel<VecH4, ACT_PRELU, false><<<g.grid, g.block, 0, s>>>((const bf16*)dy, (const bf16*)xmax, nullptr, Rp, C, p, sums);
   }
   VCA_LAUNCH_CHECK();
-  const long long total = (long long)NF * H * W * CV;
+  const long long total = (long long)NF * (H / 2 + 1) * (W / 2 + 1) * CV;
   long long gx = (total + 255) / 256; if (gx > 148LL * 16) gx = 148LL * 16;
   bn_prelu_maxpool_bwd_apply_kernel<<<(unsigned)gx, 256, 0, s>>>((const bf16*)dy, idx, (const bf16*)x, (bf16*)dx, NF, H, W, C, OH, OW, p, sums,
                                                                 train);

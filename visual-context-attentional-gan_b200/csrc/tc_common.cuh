@@ -288,6 +288,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static inline EncodeTiledFn get_encode() {
+  // The driver entry point needs the primary context bound to THIS thread.  A fresh thread that has made no context-binding
+  // runtime call yet -- autograd's backward worker when one of our kernels is the first thing it runs -- otherwise gets
+  // CUDA_ERROR_INVALID_CONTEXT (201) from cuTensorMapEncodeTiled.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   static EncodeTiledFn fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -301,10 +306,6 @@ static inline EncodeTiledFn get_encode() {
 static inline int make_map(CUtensorMap* m, const void* base, int rank, const long long* dims, const int* box,
                            CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = get_encode();
-  // the driver entry point needs the primary context bound to THIS thread; a fresh thread (autograd's backward worker)
-  // that has made no context-binding runtime call yet gets CUDA_ERROR_INVALID_CONTEXT otherwise
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   if (!enc) { vca_set_error("cuTensorMapEncodeTiled entry point unavailable"); return VCA_ERR_CUDA; }
   cuuint64_t gd[5]; cuuint64_t gs[4]; cuuint32_t bx[5]; cuuint32_t es[5];
   long long stride = 2;
@@ -323,8 +324,6 @@ static inline int make_map(CUtensorMap* m, const void* base, int rank, const lon
 // x 64 output channels, the unit of the TMA reduce-add epilogue of the wgrad kernels
 static inline int make_map_dw(CUtensorMap* m, const float* base, int Cin, int Cout, int taps) {
   EncodeTiledFn enc = get_encode();
-  static thread_local bool ctx_bound = false;
-  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   if (!enc) { vca_set_error("cuTensorMapEncodeTiled entry point unavailable"); return VCA_ERR_CUDA; }
   cuuint64_t gd[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)taps};
   cuuint64_t gs[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cin * Cout * 4};

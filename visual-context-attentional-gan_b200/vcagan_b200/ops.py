@@ -9,6 +9,7 @@ Internal activation layout is channels-last: (N, H, W, C) or (N, D, H, W, C), co
 torch is used for memory, streams, views/permutes/cat (data movement) only.
 """
 import math
+import os
 import weakref
 from typing import Optional, Tuple
 
@@ -29,7 +30,7 @@ class Config:
     skip_unneeded_wgrad = True
     gru_persistent = True   # one cooperative launch per GRU layer and pass (falls back to per-step kernels)
     fuse_grad_accum = True  # conv weight / bias gradients are accumulated straight into the FlatGroup .grad views
-    grad_slab = True        # ... tcgen05 wgrads through a tap-major slab + TMA reduce-add (trainer.FlatGroup.flush_slabs)
+    grad_slab = os.environ.get("VCA_GRAD_SLAB", "1") != "0"   # ... tcgen05 wgrads through a tap-major slab + TMA reduce-add (trainer.FlatGroup.flush_slabs)
     deferred_counters = None  # list collecting BatchNorm.num_batches_tracked tensors to bump in one launch (trainer)
     splitk = True           # small-grid / long-K convs (discriminator heads) run split-K with a lent fp32 workspace
     rowconst = True         # decode.0.conv1: the tiled (row-constant) phoneme channels collapse to one row (conv_rowconst)
@@ -306,9 +307,15 @@ def _conv_wgrad_raw(x, dy, stride, pad, wshape, out=None, param=None):
     gradients are consumed), or straight into .grad for a pointwise conv / linear layer, where the two layouts coincide."""
     g, oshape = _geom(x.shape, wshape, stride, pad)
     assert tuple(dy.shape) == tuple(oshape), (dy.shape, oshape)
+    tc = _tc_ok(g, 2, x.dtype)
+    taps = g.KD * g.KH * g.KW
+    if tc and out is None and cfg.grad_slab and g.Cin % 4 == 0:
+        # a fresh gradient tensor: accumulate it TAP-MAJOR (TMA reduce-add epilogue) and hand back the parameter-layout view
+        dw_tm = torch.zeros((taps, wshape[0], wshape[1]), dtype=torch.float32, device=x.device)
+        lib().call("vca_conv_wgrad_tc_tm", g, dy, x, dw_tm)
+        return dw_tm.view(wshape) if taps == 1 else dw_tm.permute(1, 2, 0).reshape(wshape)
     dw = torch.zeros(wshape, dtype=torch.float32, device=x.device) if out is None else out
-    if _tc_ok(g, 2, x.dtype):
-        taps = g.KD * g.KH * g.KW
+    if tc:
         slab = None
         if cfg.grad_slab and g.Cin % 4 == 0 and out is not None and param is not None:
             slab = out if taps == 1 else getattr(param, "_vca_slab", None)
