@@ -12,6 +12,8 @@ computed in the G phase (the reference computes and discards them, train.py:235-
 import math
 from typing import Dict, Iterable, List, Optional
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -113,14 +115,17 @@ class FusedAdam:
     def zero_grad(self):
         self.g.zero_grad()
 
-    def step(self, grad_scale: float = 1.0, lo: int = 0, hi: Optional[int] = None, bump: bool = True):
+    def step(self, grad_scale: float = 1.0, lo: int = 0, hi: Optional[int] = None, bump: bool = True, invalidate: bool = True):
         """One Adam step over flat[lo:hi] (default: the whole group).  A step may be taken in several slices -- the first
-        with bump=True (it advances the step counter), the others with bump=False."""
+        with bump=True (it advances the step counter), the others with bump=False.  invalidate=False leaves the group's
+        packed-weight cache tag alone: for an EARLY slice whose weights nobody reads before the last slice (which
+        invalidates) -- otherwise the other slice's still-valid packs would be redone mid-backward."""
         hi = self.g.numel if hi is None else hi
         vmax = None if self.vmax is None else self.vmax[lo:hi]
         lib().call("vca_adam_step_dev", self.g.flat[lo:hi], self.g.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], vmax, hi - lo, self.lr_dev,
                    self.betas[0], self.betas[1], self.eps, self.wd, self.t_dev, grad_scale, 1 if bump else 0)
-        self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
+        if invalidate:
+            self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
 
 
 def bilinear_down(mel: torch.Tensor, factor: int) -> torch.Tensor:
@@ -178,6 +183,19 @@ class Trainer:
         # gen + post gradients (62 % of the G buffer) then runs on the comm stream underneath the visual front-end's
         # backward.  Single-GPU runs keep the backward in one piece (no all-reduce to hide, one graph less).
         self.split_g_backward = self.world > 1
+        # Single GPU: the optimizer passes (Adam over 36 B / parameter, weight re-pack -- pure HBM streaming) run on a side
+        # stream underneath compute-bound work that does not touch what they write: the D optimizer + re-pack under the
+        # Postnet forward / reconstruction losses, Adam on the gen + post slice under the visual front-end's backward (which
+        # needs the G backward split where data-parallel runs split it).  Set before the first step / capture().
+        # Measured (1 x B200, same box, B = 32): 47.50 ms with, 47.48 ms without -- the HBM-streaming optimizer kernels take from
+        # the concurrent compute kernels what they gain.  Negative result: off by default (VCA_OVERLAP_OPT=1 turns it on).
+        self.overlap_opt = self.world == 1 and os.environ.get("VCA_OVERLAP_OPT", "0") == "1"
+        if os.environ.get("VCA_SPLIT_G") == "1":
+            self.split_g_backward = True
+        if self.overlap_opt:
+            self.split_g_backward = True
+        self._opt_stream = None
+        self._d_done = self._ga_done = False
         n_vf = sum(1 for _ in self.mods["v_front"].parameters())
         self._vf_params = self.G.params[:n_vf]
         self._genpost_params = self.G.params[n_vf:]
@@ -303,7 +321,7 @@ class Trainer:
         self._build_pack_plans()
         return out
 
-    def _run_schedule(self, run):
+    def _run_schedule(self, run, replaying=False):
         """The step as six phases with the data-parallel exchanges between them; `run(i)` executes phase i (eagerly, or by
         replaying the CUDA graph it was captured into).  Every all-reduce is issued on the comm stream and only waited for
         where its result is needed, so each one runs underneath independent work:
@@ -313,18 +331,38 @@ class Trainer:
         Single-GPU runs have no exchanges; phases 1+2 and 4+5 then share a graph (3 graphs per step)."""
         cur = torch.cuda.current_stream()
         multi = self.world > 1
+        ovl = self.overlap_opt and not multi and not replaying and self.split_g_backward
+        if ovl and self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(device=self.device)
+        side = self._opt_stream
         run(0)
         ev = self._allreduce(self.D, wait=False) if multi else None
+        if ovl:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._d_update()
+            self._d_done = True
         run(1)
         if multi:
             cur.wait_event(ev)
+        if ovl:
+            cur.wait_stream(side)
         run(2)
         if self.split_g_backward:
             e1 = self._allreduce(self.G, lo=self._vf_numel, wait=False) if multi else None      # gen + post
+            if ovl:
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    # (no cache invalidation yet: the visual front-end's backward is about to use ITS packed weights, which
+                    #  share the group's tag; _phase_end_b's slice invalidates before the batched re-pack)
+                    self.g_opt.step(1.0 / self.world, lo=self._vf_numel, bump=True, invalidate=False)
+                self._ga_done = True
             run(3)
             e2 = self._allreduce(self.G, hi=self._vf_numel, wait=False) if multi else None      # v_front
             if multi:
                 cur.wait_event(e1)
+            if ovl:
+                cur.wait_stream(side)
             run(4)
             if multi:
                 cur.wait_event(e2)
@@ -445,14 +483,21 @@ class Trainer:
             + ops.l1_mean(gs, st["spec"])
         st["gs"], st["recon"] = gs, recon
 
+    def _d_update(self):
+        """D optimizer step on the (exchanged) gradients + one batched re-pack of the weights it changed"""
+        self.d_opt.step(1.0 / self.world)
+        if self._pack_d is not None:
+            self._pack_d.run()
+
     def _phase_g(self):
         """D optimizer step, then the G phase against the updated discriminators and its backward (train.py:211-236)."""
         st, m = self._st, self.mods
         dis = (m["dis1"], m["dis2"], m["dis3"])
         g, sdet, T, phon = st["g"], st["sdet"], st["T"], st["phon"]
-        self.d_opt.step(1.0 / self.world)
-        if self._pack_d is not None:
-            self._pack_d.run()
+        if self._d_done:
+            self._d_done = False             # already stepped on the optimizer side stream (underneath _phase_g_pre)
+        else:
+            self._d_update()
         gs, recon = st["gs"], st["recon"]
         res = self._branches([lambda: dis[2](g[2], sdet, T), lambda: dis[1](g[1], sdet, T), lambda: dis[0](g[0], sdet, T),
                               lambda: m["s_dis"](phon.detach(), g[2], True).mean()])
@@ -494,7 +539,9 @@ class Trainer:
     def _phase_end_a(self):
         """G optimizer: with a split backward the gen + post slice first (its gradients were reduced long ago), so that the
         v_front slice's all-reduce finishes underneath it; otherwise the whole group."""
-        if self.split_g_backward:
+        if self._ga_done:
+            self._ga_done = False            # gen + post slice already stepped on the side stream (underneath _phase_g2)
+        elif self.split_g_backward:
             self.g_opt.step(1.0 / self.world, lo=self._vf_numel, bump=True)
         else:
             self.g_opt.step(1.0 / self.world)
@@ -571,7 +618,7 @@ class Trainer:
             if gi is not None:
                 self._graphs[gi].replay()
             return self._sout if i == 5 else None
-        return self._run_schedule(run)
+        return self._run_schedule(run, replaying=True)
 
     # -- pipelined input feed: the host->device copy of step i+1 runs on a copy stream underneath step i ------------
     def stage_inputs(self, vid, mel, spec):
