@@ -29,6 +29,10 @@ SHAPES = [  # name, N, H, W, Cin, Cout, (kh,kw), (ph,pw)
     ("dis.sc(1x1,32-64)", 32, 80, 300, 32, 64, (1, 1), (0, 0)),
     ("dis.sc(1x1,64-128)", 32, 40, 150, 64, 128, (1, 1), (0, 0)),
     ("dis.conv(32-64,5x5)", 32, 40, 150, 32, 64, (5, 5), (2, 2)),
+    ("gen.g2.0.conv1(128-64)", 32, 40, 150, 128, 64, (5, 5), (2, 2)),
+    ("gen.g3.0.conv1(64-32)", 32, 80, 300, 64, 32, (5, 5), (2, 2)),
+    ("gen.attconv2(96-64)", 32, 40, 150, 96, 64, (5, 5), (2, 2)),
+    ("gen.g1.x(256-128)", 32, 20, 75, 256, 128, (5, 5), (2, 2)),
 ]
 
 

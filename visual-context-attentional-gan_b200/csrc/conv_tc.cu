@@ -29,6 +29,8 @@ int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
 // conv_tc_wgrad_ws.cu: multi-tap weight-gradient kernel for <= 64 input channels (same return convention)
 int conv_wgrad_ws_try(const ConvGeom& g, const void* dy, const void* x, float* dw, cudaStream_t s, int tm);
 extern int g_wg_dbg;
+int g_wg_smem_kb = 190;    // shared-memory budget per CTA of the streaming wgrad kernel
+int g_fwd_smem_kb = 100;   // shared-memory budget per CTA of the streaming forward kernel on multi-wave grids (100: two CTAs per SM)
 
 namespace {
 
@@ -457,7 +459,10 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   splits = (KH * KW + taps_per_split - 1) / taps_per_split;
   p.splits = splits; p.taps_per_split = taps_per_split; p.ws = splits > 1 ? ws : nullptr;
   total_ctas *= splits;
-  const size_t budget = total_ctas <= vca_num_sms() ? 196 * 1024 : 100 * 1024;
+  // multi-wave grids: two CTAs per SM (100 KB each) hide each other's pipeline fill / epilogue; tiles of <= 128 columns leave
+  // TMEM room for THREE (72 KB each), of <= 64 for FOUR (52 KB) -- measured: 128-channel 5x5 at 20 x 75 600 -> 756 TFLOP/s,
+  // 128 -> 64 5x5 at 40 x 150 533 -> 670; wider tiles unchanged
+  const size_t budget = total_ctas <= vca_num_sms() ? 196 * 1024 : (size_t)(g_fwd_smem_kb != 100 ? g_fwd_smem_kb : bn <= 64 ? 52 : bn <= 128 ? 72 : 100) * 1024;
   int stages = (int)(budget / stage_bytes);
   const int max_stages = total_ctas <= vca_num_sms() ? 12 : 6;
   if (stages > max_stages) stages = max_stages; if (stages < 2) stages = 2;
@@ -599,7 +604,7 @@ static int wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* dw,
   p.tmem_cols = pow2_cols(p.BNc);
   p.dw = dw; p.dbg = g_wg_dbg; p.tm = tm;
   const size_t stage_bytes = 2 * A_STAGE_BYTES + (size_t)p.b_atoms * A_STAGE_BYTES;
-  int stages = (int)((190 * 1024) / stage_bytes);
+  int stages = (int)(((size_t)g_wg_smem_kb * 1024) / stage_bytes);
   if (stages > 4) stages = 4; if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = stages * stage_bytes + 1024 + 256;

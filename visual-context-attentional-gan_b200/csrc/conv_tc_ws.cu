@@ -34,6 +34,7 @@ extern int g_gru_cluster, g_gru_bs;   // gru_cluster.cu
 extern int g_hs_mode;       // conv_tc_hs.cu
 extern int g_wgws_waves;    // conv_tc_wgrad_ws.cu
 extern int g_wgws_mstack, g_wg_dbg;
+extern int g_fwd_smem_kb, g_wg_smem_kb;   // conv_tc.cu
 extern int g_gl_fpw;        // stft.cu
 
 namespace {
@@ -505,6 +506,8 @@ int vca_set_option(const char* key, int value) {
   if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
   if (eq("gru_bs")) { g_gru_bs = value; return VCA_OK; }
   if (eq("hs_mode")) { g_hs_mode = value; return VCA_OK; }
+  if (eq("wg_smem_kb")) { g_wg_smem_kb = value; return VCA_OK; }
+  if (eq("fwd_smem_kb")) { g_fwd_smem_kb = value; return VCA_OK; }
   if (eq("wg_dbg")) { g_wg_dbg = value; return VCA_OK; }
   if (eq("wgws_mstack")) { g_wgws_mstack = value; return VCA_OK; }
   if (eq("wgws_waves")) { g_wgws_waves = value < 1 ? 1 : value; return VCA_OK; }
