@@ -1,4 +1,2 @@
-for i in 1 2; do
-for o in "fwd_smem_kb=101" "fwd_smem_kb=100"; do
-  echo -n "$o: "; VCA_OPTS=$o python bench.py --steps 10 --warmup 3 --no-gpu-eager --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'])"
-done; done
+python bench.py > gpurun_out/bench_1gpu_r02_final.json 2> gpurun_out/bench_err.log; cat gpurun_out/bench_1gpu_r02_final.json; tail -3 gpurun_out/bench_err.log | cut -c1-200
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference_cpu_r02.json 2>> gpurun_out/bench_err.log; cat gpurun_out/bench_reference_cpu_r02.json | cut -c1-600
