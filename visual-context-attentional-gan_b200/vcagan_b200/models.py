@@ -109,38 +109,38 @@ class BasicBlock(nn.Module):
 class ResNet(nn.Module):
     """resnet.py:69-123: four stages of BasicBlocks + AvgPool2d(4) + flatten.  Channels-last in, (N,512) out."""
 
+    STAGES = ((64, 1), (128, 2), (256, 2), (512, 2))      # (planes, stride of the stage's first block): layer1 .. layer4
+
     def __init__(self, block, layers, num_classes=1000, relu_type='relu', gamma_zero=False, avg_pool_downsample=False):
-        self.inplanes = 64
-        self.relu_type = relu_type
-        self.gamma_zero = gamma_zero
-        self.downsample_block = downsample_basic_block_v2 if avg_pool_downsample else downsample_basic_block
         super().__init__()
-        self.layer1 = self._make_layer(block, 64, layers[0])
-        self.layer2 = self._make_layer(block, 128, layers[1], stride=2)
-        self.layer3 = self._make_layer(block, 256, layers[2], stride=2)
-        self.layer4 = self._make_layer(block, 512, layers[3], stride=2)
+        self.relu_type, self.gamma_zero = relu_type, gamma_zero
+        shortcut = downsample_basic_block_v2 if avg_pool_downsample else downsample_basic_block
+        width = 64
+        # the state_dict keys (`layer{i}.{j}.conv1.weight`, `layer{i}.0.downsample.0.weight`, ...) are the interface: built
+        # from the stage table, one nn.Sequential per stage
+        for i, ((planes, stride), depth) in enumerate(zip(self.STAGES, layers), start=1):
+            out = planes * block.expansion
+            proj = shortcut(inplanes=width, outplanes=out, stride=stride) if (stride != 1 or width != out) else None
+            stage = [block(width, planes, stride, proj, relu_type=relu_type)]
+            stage += [block(out, planes, relu_type=relu_type) for _ in range(depth - 1)]
+            setattr(self, f"layer{i}", nn.Sequential(*stage))
+            width = out
         self.avgpool = nn.AvgPool2d(4)
-        for m in self.modules():  # resnet.py:85-91
+        self._init_parameters()
+
+    def _init_parameters(self):
+        """default initialisation of resnet.py:85-97 (He-normal conv weights by fan-out, unit BatchNorm, optional zero gamma)"""
+        for m in self.modules():
             if isinstance(m, nn.Conv2d):
-                n = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
-                m.weight.data.normal_(0, math.sqrt(2. / n))
+                fan_out = m.kernel_size[0] * m.kernel_size[1] * m.out_channels
+                nn.init.normal_(m.weight, 0.0, math.sqrt(2.0 / fan_out))
             elif isinstance(m, nn.BatchNorm2d):
-                m.weight.data.fill_(1)
-                m.bias.data.zero_()
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
         if self.gamma_zero:
             for m in self.modules():
                 if isinstance(m, BasicBlock):
-                    m.bn2.weight.data.zero_()
-
-    def _make_layer(self, block, planes, blocks, stride=1):
-        downsample = None
-        if stride != 1 or self.inplanes != planes * block.expansion:
-            downsample = self.downsample_block(inplanes=self.inplanes, outplanes=planes * block.expansion, stride=stride)
-        layers = [block(self.inplanes, planes, stride, downsample, relu_type=self.relu_type)]
-        self.inplanes = planes * block.expansion
-        for _ in range(1, blocks):
-            layers.append(block(self.inplanes, planes, relu_type=self.relu_type))
-        return nn.Sequential(*layers)
+                    nn.init.zeros_(m.bn2.weight)
 
     def forward(self, x):
         for layer in (self.layer1, self.layer2, self.layer3, self.layer4):
