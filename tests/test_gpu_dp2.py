@@ -49,10 +49,12 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
         d_mean = (trs[0].D.grad + trs[1].D.grad) / 2.0
         e = rel_l2(W.sample(d_mean), ranks[0]["D"] / 2.0)
         print(f"{precision}: 2-rank all-reduced D gradients vs mean of per-shard single-GPU gradients: rel L2 {e:.3e}")
-        # fp32: measured 2e-8 (D) / 6e-7 (G).  bf16: the split-K / wgrad atomics are not bit-reproducible, and at this B = 2
-        # train-mode-BatchNorm case two runs of the SAME step differ by ~6e-2 in gradient L2 (their error vs fp64 is 1e-1..5e-1,
-        # test_step_bf16_gradient_bound); the exchange itself is exact, as the fp32 case shows
-        tol = 2e-5 if precision == "fp32" else 0.15
+        # fp32: measured 2e-8 (D) / 1e-7 (G).  bf16: the forward of the tcgen05 path is bit-reproducible since round 2 (split-K
+        # into per-split slabs added in order, BatchNorm-statistic partials reduced in a fixed order inside the CTA), and what
+        # is left in the gradients is the fp32 summation order of the wgrad reduce-adds: measured 2e-8 (D) / 1e-7 (G) between
+        # two identical runs (tools/g_noise_probe.py; it was 8e-2 / 3.6e-1 while shared-slab atomics flipped bf16 roundings in
+        # front of the train-mode BatchNorms), so the bf16 exchange is held to 1e-4 too
+        tol = 2e-5 if precision == "fp32" else 1e-4
         assert e < tol, e
         # The G phase runs against discriminators stepped with the EXCHANGED gradient.  Adam's first step moves every weight
         # by +-lr whatever the gradient's size, so the bf16 noise in d_mean (e above: ~1e-1) would flip thousands of update
@@ -60,11 +62,8 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
         # The oracle therefore applies the ranks' own reduced D gradient, which the D check above has just validated.
         d_used = torch.load(os.path.join(tmp_path, "d_grad_sum.pt")).cuda() / 2.0
         assert rel_l2(d_used, d_mean) < tol
-        # bf16 yard-stick, measured live: a third single-GPU trainer repeats shard 0 with the same D gradient.  At this B = 2
-        # random-init case bf16-ulp differences (fp32 atomics order in split-K / wgrad) are amplified by the train-mode
-        # BatchNorms to 3-6e-2 in the forward outputs and ~0.35 in the G gradient BETWEEN TWO IDENTICAL RUNS
-        # (tools/g_noise_probe.py; the reference under autocast is 4-10e-2 away from its own fp32 forward).  The bf16 bound
-        # on the exchanged G gradient is therefore 2 x that run-to-run figure; the fp32 case pins the exchange itself.
+        # bf16 yard-stick, measured live: a third single-GPU trainer repeats shard 0 with the same D gradient (run-to-run
+        # figure of the G gradient; ~1e-7 now that the forward is bit-reproducible -- printed for the record, the bound is tol)
         g_noise = None
         if precision != "fp32":
             tr3 = Trainer(precision=precision, state={m: make_state(spec, m) for m in O.MODULES}, dropout=False)

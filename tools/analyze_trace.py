@@ -13,6 +13,8 @@ def fam(n):
     n = re.sub(r"^void\s+", "", n)
     n = re.sub(r"<.*", "", n)
     n = n.replace("(anonymous namespace)::", "").replace("<unnamed>::", "")
+    if n.startswith("torch:"):
+        return n[:40]
     if n.startswith("at::native") or "at::" in n:
         return "torch:" + n.split("::")[-1][:30]
     return n[:40]

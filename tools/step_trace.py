@@ -43,7 +43,17 @@ ks = [(x["name"], x["args"].get("stream", -1), x["ts"], x["dur"]) for x in tr_js
       if x.get("cat") in ("kernel", "gpu_memcpy", "gpu_memset") and "dur" in x]
 ks.sort(key=lambda k: k[2])
 t0 = ks[0][2]
-out = [(n[:60], s, round(ts - t0, 3), round(d, 3)) for n, s, ts, d in ks]
+import re
+
+
+def short(n):   # torch's templated kernels: keep the functor that says what they do
+    if "at::" in n:
+        m = re.findall(r"(\w+Functor\w*|\w*[Cc]opy\w*|CatArray\w*|\w+_kernel_cuda\w*|reduce_kernel|multi_tensor_apply\w*)", n)
+        return ("torch:" + "/".join(dict.fromkeys(m[:3])))[:60] if m else n[:60]
+    return n[:60]
+
+
+out = [(short(n), s, round(ts - t0, 3), round(d, 3)) for n, s, ts, d in ks]
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"step_trace_{tag}.json"), "w"))
 os.remove(path)
 end = max(ts + d for _, _, ts, d in out)

@@ -52,7 +52,7 @@ struct FwdParams {
   uint32_t a_bytes, b_bytes;     // bytes the two TMA loads of one stage deliver
   uint32_t tmem_cols;
   int splits, taps_per_split;    // split-K over the filter taps: blockIdx.z takes taps [z*per, (z+1)*per)
-  float* ws;                     // split-K only: fp32 [pixels][Cout] partial sums (red.add), finished by splitk_finish_kernel
+  float* ws;                     // split-K only: fp32 [splits][pixels][Cout] partial sums, added in order by splitk_finish_kernel
   const float* bias;             // [Cout] or null
   double* stats;                 // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
   EpiExtra ex;                   // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
@@ -165,21 +165,31 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
     mbar_wait(accum_bar, 0);
     tc_fence_after();
     if (p.ws) {
-      // split-K: add this CTA's partial sums (if it executed any tap at all) into the fp32 workspace
+      // split-K: this CTA's partial sums go to ITS OWN slab ws[split][pixel][Cout] with plain vector stores (zeros if every
+      // tap of the split was padding); splitk_finish_kernel adds the slabs in split order -- deterministic, no atomics, no
+      // memset (fp32 red.add into one shared slab made identical forward passes differ in the last bit, which the bf16
+      // rounding and the train-mode BatchNorms downstream amplify)
       bool any = false;
       for (int tap = tap_beg; tap < tap_end; ++tap) {
         const int a = tap / p.KW, b = tap % p.KW;
         const int r0 = oh0 + a - p.ph, c0 = ow0 + b - p.pw;
         any = any || !(r0 >= p.IH || r0 + p.th <= 0 || c0 >= p.IW || c0 + p.tw <= 0);
       }
-      float* wrow = p.ws + (((long long)n * p.OH + oh) * p.OW + ow) * p.Cout + co0;
-      for (int c = 0; c < p.BN && any; c += 16) {
+      float* wrow = p.ws + ((long long)blockIdx.z * p.NF * p.OH * p.OW + (((long long)n * p.OH + oh) * p.OW + ow)) * p.Cout + co0;
+      for (int c = 0; c < p.BN; c += 16) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        if (row_ok) {
+        if (any) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (co0 + c + i < p.Cout) atomicAdd(wrow + c + i, v[i]);
+          for (int i = 0; i < 16; ++i) v[i] = 0.f;
+        }
+        if (row_ok && co0 + c < p.Cout) {
+          if (co0 + c + 16 <= p.Cout && (p.Cout & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(wrow + c + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            for (int i = 0; i < 16 && co0 + c + i < p.Cout; ++i) wrow[c + i] = v[i];
+          }
         }
       }
     } else if (p.has_ex) {
@@ -220,13 +230,16 @@ __global__ void __launch_bounds__(192) conv_tc_fwd_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
-// y[m][c] = bf16(ws[m][c] + bias[c]): finishes a split-K convolution
+// y[m][c] = bf16(sum_s ws[s][m][c] + bias[c]), slabs added in split order: finishes a split-K convolution
 __global__ void splitk_finish_kernel(const float* __restrict__ ws, const float* __restrict__ bias, bf16* __restrict__ y,
-                                     long long total, int Cout) {
+                                     long long total, int Cout, int splits) {
   for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 8; i < total; i += (long long)gridDim.x * blockDim.x * 8) {
     if (i + 8 <= total && Cout % 8 == 0) {
-      const float4 a = *reinterpret_cast<const float4*>(ws + i), b = *reinterpret_cast<const float4*>(ws + i + 4);
-      float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int sp = 0; sp < splits; ++sp) {
+        const float4 a = *reinterpret_cast<const float4*>(ws + sp * total + i), b = *reinterpret_cast<const float4*>(ws + sp * total + i + 4);
+        v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w; v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+      }
       const int c = (int)(i % Cout);
       uint32_t w[4];
 #pragma unroll
@@ -236,7 +249,11 @@ __global__ void splitk_finish_kernel(const float* __restrict__ ws, const float* 
       }
       *reinterpret_cast<uint4*>(y + i) = make_uint4(w[0], w[1], w[2], w[3]);
     } else {
-      for (long long j = i; j < total && j < i + 8; ++j) y[j] = __float2bfloat16_rn(ws[j] + (bias ? bias[j % Cout] : 0.f));
+      for (long long j = i; j < total && j < i + 8; ++j) {
+        float a = 0.f;
+        for (int sp = 0; sp < splits; ++sp) a += ws[sp * total + j];
+        y[j] = __float2bfloat16_rn(a + (bias ? bias[j % Cout] : 0.f));
+      }
     }
   }
 }
@@ -436,8 +453,9 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   long long ptiles = (long long)p.tiles_w * p.tiles_h * tiles_n;
   // (with enough filter taps and a workspace on offer, splitting K keeps the MMA N wide instead: a 64-wide tile caps
   //  the tensor pipe at 50 %)
-  const bool can_split = (ws_need != nullptr || ws != nullptr) && plan_splits(ptiles * ((Nout + bn - 1) / bn), KH * KW) > 1 &&
-                         (ws_need != nullptr || ws_bytes >= (size_t)NF * OH * OW * Nout * sizeof(float));
+  const int planned0 = plan_splits(ptiles * ((Nout + bn - 1) / bn), KH * KW);
+  const bool can_split = (ws_need != nullptr || ws != nullptr) && planned0 > 1 &&
+                         (ws_need != nullptr || ws_bytes >= (size_t)planned0 * NF * OH * OW * Nout * sizeof(float));
   while (!can_split && bn > 64 && ptiles * ((Nout + bn - 1) / bn) < vca_num_sms() && bn % 32 == 0) bn /= 2;
   p.BN = bn;
   p.a_bytes = (uint32_t)(p.tn * p.th * p.tw) * 128u;
@@ -452,7 +470,7 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   // 4 MMAs (~0.15-0.3 us) while a TMA round trip is ~1.5 us.
   long long total_ctas = ptiles * ((Nout + bn - 1) / bn);
   int splits = plan_splits(total_ctas, KH * KW);
-  const size_t need = (size_t)NF * OH * OW * Nout * sizeof(float);
+  const size_t need = (size_t)splits * NF * OH * OW * Nout * sizeof(float);      // one fp32 slab per split
   if (ws_need) { *ws_need = splits > 1 ? need : 0; return VCA_OK; }   // planning query only
   if (splits > 1 && (!ws || ws_bytes < need)) splits = 1;
   const int taps_per_split = (KH * KW + splits - 1) / splits;
@@ -484,14 +502,13 @@ int fwd_like(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH,
   if (p.ws) {
     if (stats || ex) { vca_set_error("conv forward: statistics / fused epilogues are not available on the split-K path"); return VCA_ERR_UNSUPPORTED; }
     p.bias = nullptr;   // added by the finishing pass
-    if (cudaMemsetAsync(ws, 0, need, s) != cudaSuccess) { vca_set_error("split-K workspace memset failed"); return VCA_ERR_CUDA; }
   }
   dim3 grid((unsigned)ptiles, (unsigned)((Nout + bn - 1) / bn), (unsigned)splits);
   conv_tc_fwd_kernel<<<grid, 192, smem, s>>>(tmA, tmB, p);
   VCA_LAUNCH_CHECK();
   if (p.ws) {
     const long long total = (long long)NF * OH * OW * Nout;
-    splitk_finish_kernel<<<vca_grid_1d(total, 256, 8), 256, 0, s>>>(ws, bias, (bf16*)y, total, Nout);
+    splitk_finish_kernel<<<vca_grid_1d(total, 256, 8), 256, 0, s>>>(ws, bias, (bf16*)y, total, Nout, splits);
     VCA_LAUNCH_CHECK();
   }
   return VCA_OK;

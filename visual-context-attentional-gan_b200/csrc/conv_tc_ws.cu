@@ -328,6 +328,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(const __grid_
     // BatchNorm statistics: the shared accumulators collect ALL tiles of this persistent CTA (fp32 over a few thousand
     // rows), published once -- a flush per tile would put tens of thousands of fp64 atomics on each channel's address
     if (MODE == 1) {
+      // DETERMINISTIC within the CTA: every warp writes its partial sums into its own slot of the (now idle) first A stage,
+      // and the four TMEM lane quarters are added in a fixed order -- shared-memory atomics here made two identical
+      // forward passes differ in the last fp32 bit of the batch statistics, which the bf16 rounding of the normalised
+      // activations and the train-mode BatchNorms downstream amplified to 4e-3 at the visual front-end's output.
+      float* s_part = reinterpret_cast<float*>(sA);        // [4 quarters][sum | sum of squares][BN]
 #pragma unroll
       for (int ci = 0; ci < 2; ++ci) {
         const int cc = 2 * ci + half;
@@ -337,10 +342,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(const __grid_
           for (int i = 0; i < 16; ++i) { a[i] = rs[(ci * 16 + i) % NR]; b[i] = rq[(ci * 16 + i) % NR]; }
           const float sa = colsum16(a, lane), sb = colsum16(b, lane);
           const int col = epi_col(lane);
-          if (!(lane & 1) && co0 + cc * 16 + col < p.Cout) { atomicAdd(s_sum + cc * 16 + col, sa); atomicAdd(s_sq + cc * 16 + col, sb); }
+          if (!(lane & 1)) { s_part[(q * 2) * p.BN + cc * 16 + col] = sa; s_part[(q * 2 + 1) * p.BN + cc * 16 + col] = sb; }
         }
       }
-      epi_stats_flush(s_sum, s_sq, p.BN, co0, p.Cout, p.stats, (int)threadIdx.x - 64, 32 * WS_EPI_WARPS);
+      asm volatile("bar.sync 1, %0;" ::"r"(32 * WS_EPI_WARPS) : "memory");
+      for (int c = (int)threadIdx.x - 64; c < p.BN; c += 32 * WS_EPI_WARPS) {
+        if (co0 + c < p.Cout) {
+          double ts = 0.0, tq = 0.0;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) { ts += (double)s_part[(qq * 2) * p.BN + c]; tq += (double)s_part[(qq * 2 + 1) * p.BN + c]; }
+          atomicAdd(p.stats + co0 + c, ts); atomicAdd(p.stats + p.Cout + co0 + c, tq);
+        }
+      }
     }
   }
   tc_fence_before();
