@@ -169,6 +169,11 @@ int vca_rng_dev(int dtype, void* out, long long n, unsigned long long seed, unsi
 /* ---- Griffin-Lim STFT / ISTFT (src/data/stft.py:70-129, src/data/audio_processing.py:51-68) ---------------------- */
 int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float* mag_t, float* frames, float* spec_out, int B, int T, int L, cudaStream_t stream);
 int vca_gl_ola(const float* frames, float* sig_out, int B, int T, int L, cudaStream_t stream);
+/* one whole Griffin-Lim iteration (audio_processing.py:62-66: transform -> angles -> inverse) in one kernel: sig_in normalised
+ * (in_norm != 0) or the un-normalised overlap-add sums of a previous call; acc_out (ZERO on entry) receives the new sums;
+ * vca_gl_normalize divides by the window envelope (stft.py:110-127) */
+int vca_gl_iter(const float* sig_in, int in_norm, const float* mag_p, float* acc_out, int B, int T, int L, cudaStream_t stream);
+int vca_gl_normalize(const float* acc, float* sig_out, int B, int T, int L, cudaStream_t stream);
 /* out[row][k1*32 + lane] = in[row][k1 + 10*bitrev5(lane)], bin 320 last: the bin order vca_gl_frames reads with unit stride when (mode & 2) */
 int vca_gl_permute_bins(const float* in, float* out, long long rows, cudaStream_t stream);
 

@@ -174,6 +174,109 @@ __device__ __forceinline__ int reflect_idx(int j, int L) {   // F.pad(mode='refl
   return j;
 }
 
+// window sum-of-squares envelope at padded position n = m + 320 (audio_processing.py:7-48 with T frames): the <= 4 frames covering it
+__device__ __forceinline__ float gl_wss(int n, int T, const float* __restrict__ win) {
+  const int t_hi = min(n / HOP, T - 1);
+  const int t_lo = n < NFFT - HOP ? 0 : (n - (NFFT - HOP)) / HOP;     // ceil((n - 639) / 160)
+  float wss = 0.f;
+  for (int t = t_lo; t <= t_hi; ++t) { const float w = win[n - t * HOP]; wss = fmaf(w, w, wss); }
+  return wss;
+}
+
+// v / envelope at signal position j -- the rare path (frames within three hops of either end): kept out of line so that it
+// does not cost the common path registers
+__device__ __noinline__ float gl_env_div(float v, int j, int T, const float* __restrict__ win) {
+  const float e = gl_wss(j + NFFT / 2, T, win);
+  return e > 1.1754944e-38f ? v / e : v;
+}
+
+// The 640 reflect-padded, windowed samples of frame t as z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane.
+// ENV: sb holds UN-normalised overlap-add sums (gl_iter_kernel's output): divide by the window envelope on the way in --
+// 1.5 for every sample at least 480 away from both ends (periodic Hann, hop = N/4), the exact <= 4-term sum elsewhere.
+template <bool ENV>
+__device__ __forceinline__ void gl_load_frame(const float* __restrict__ sb, int t, int T, int L, const float2* __restrict__ win2,
+                                              const float* __restrict__ win, int lane, cpx (&r)[10]) {
+  const int base = t * HOP - NFFT / 2;
+  const bool interior = base >= 0 && base + NFFT <= L;            // no reflection: aligned float2 loads
+  const bool deep = base >= NFFT - HOP && base + NFFT <= L - (NFFT - HOP);
+#pragma unroll
+  for (int n1 = 0; n1 < 10; ++n1) {
+    const int n = 32 * n1 + lane;
+    const float2 w = win2[n];
+    float2 x;
+    if (interior) {
+      x = *reinterpret_cast<const float2*>(sb + base + 2 * n);
+      if (ENV) {
+        if (deep) { x.x *= (2.f / 3.f); x.y *= (2.f / 3.f); }
+        else { x.x = gl_env_div(x.x, base + 2 * n, T, win); x.y = gl_env_div(x.y, base + 2 * n + 1, T, win); }
+      }
+    } else {
+      const int j0 = reflect_idx(base + 2 * n, L), j1 = reflect_idx(base + 2 * n + 1, L);
+      x = make_float2(sb[j0], sb[j1]);
+      if (ENV) { x.x = gl_env_div(x.x, j0, T, win); x.y = gl_env_div(x.y, j1, T, win); }
+    }
+    r[n1] = {x.x * w.x, x.y * w.y};
+  }
+}
+
+// rFFT of the frame in r, then Y[k] = mag[k] * X[k] / |X[k]| (the phase of the signal, the target magnitude).
+// spec_out (optional): X itself as (re, im) at spec_out[(fo * 321 + k) * 2].
+__device__ __forceinline__ void gl_analyze(cpx (&r)[10], const LaneConst& c, int lane, const cpx* __restrict__ tw2p,
+                                           const float* __restrict__ mg, bool lane_major, float* __restrict__ spec_out, long long fo,
+                                           cpx (&y)[10], cpx& y320) {
+  fft320<false>(r, c, lane);
+  // X[k] = E[k] + W640^k O[k];  E = (Z[k] + conj Z[N-k])/2, O = (Z[k] - conj Z[N-k])/(2i).  Then Y[k] = mag * X/|X|.
+#pragma unroll
+  for (int k1 = 0; k1 < 10; ++k1) {
+    const cpx zn = cconj(k1 == 0 ? shfl_idx(r[0], c.src0) : shfl_xor(r[10 - k1], 31));
+    const cpx zk = r[k1];
+    const cpx e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y)};
+    const cpx d = csub(zk, zn);
+    const cpx o = {0.5f * d.y, -0.5f * d.x};          // d / (2i)
+    const int k = k1 + 10 * c.k2;
+    const cpx X = cadd(e, cmul(tw2p[k1 * 32 + lane], o));
+    if (spec_out) { spec_out[(fo * NBIN + k) * 2] = X.x; spec_out[(fo * NBIN + k) * 2 + 1] = X.y; }
+    const float r2 = X.x * X.x + X.y * X.y;
+    const float m = __ldg(mg + (lane_major ? k1 * 32 + lane : k));
+    const float sc = m * rsqrtf(r2);                                  // mag / |X|
+    y[k1] = r2 > 0.f ? cpx{sc * X.x, sc * X.y} : cpx{m, 0.f};         // atan2(0,0) = 0
+    if (k1 == 0) {                                                    // Nyquist bin from the same pair (k = 0, lane 0)
+      const cpx Xn = csub(e, o);
+      if (spec_out && lane == 0) { spec_out[(fo * NBIN + NH) * 2] = Xn.x; spec_out[(fo * NBIN + NH) * 2 + 1] = Xn.y; }
+      const float q2 = Xn.x * Xn.x + Xn.y * Xn.y;
+      const float mn = __ldg(mg + NH);
+      const float sn = mn * rsqrtf(q2);
+      y320 = q2 > 0.f ? cpx{sn * Xn.x, sn * Xn.y} : cpx{mn, 0.f};
+    }
+  }
+}
+
+// inverse real FFT of the Hermitian spectrum Y[0..320] (imaginary parts of DC / Nyquist ignored, as in the reference's
+// basis), windowed and scaled: z[n1] = the frame's samples (2n, 2n+1), n = 32 n1 + lane
+//      Z[k] = E[k] + i O[k],  E = (Y[k] + conj Y[N-k])/2,  O = (Y[k] - conj Y[N-k])/2 * W640^{-k}
+__device__ __forceinline__ void gl_synthesize(cpx (&y)[10], cpx y320, const LaneConst& c, int lane, const cpx* __restrict__ tw2p,
+                                              const float2* __restrict__ win2, cpx (&z)[10]) {
+  if (lane == 0) y[0].y = 0.f;
+  y320.y = 0.f;
+#pragma unroll
+  for (int k1 = 0; k1 < 10; ++k1) {
+    cpx yn = cconj(k1 == 0 ? shfl_idx(y[0], c.src0) : shfl_xor(y[10 - k1], 31));
+    if (k1 == 0 && lane == 0) yn = y320;                 // k = 0 pairs with Y[320] (real)
+    const cpx yk = y[k1];
+    const cpx e = {0.5f * (yk.x + yn.x), 0.5f * (yk.y + yn.y)};
+    const cpx d = {0.5f * (yk.x - yn.x), 0.5f * (yk.y - yn.y)};
+    const cpx o = cmul(d, cconj(tw2p[k1 * 32 + lane]));
+    z[k1] = {e.x - o.y, e.y + o.x};                      // e + i o
+  }
+  fft320<true>(z, c, lane);
+  const float sc = 1.f / (float)NH;
+#pragma unroll
+  for (int n1 = 0; n1 < 10; ++n1) {
+    const float2 w = win2[32 * n1 + lane];
+    z[n1] = {z[n1].x * sc * w.x, z[n1].y * sc * w.y};
+  }
+}
+
 // mode 0: phases from angles_t [B][T][321] (radians);  mode 1: phases from the STFT of sig [B][L].
 // mag_t [B][T][321]; frames [B][T][640].  Optional spec_out [B][T][321][2] = STFT (re, im) of sig (mode 1 only).
 __global__ void __launch_bounds__(WARPS * 32, 3) gl_frames_kernel(int mode, const float* __restrict__ sig,
@@ -210,44 +313,9 @@ __global__ void __launch_bounds__(WARPS * 32, 3) gl_frames_kernel(int mode, cons
     cpx y320;        // Y[320]; meaningful on lane 0 only
 
     if (mode == 1) {
-      // ---- forward: windowed frame -> z[n] = x[2n] + i x[2n+1], n = 32 n1 + lane -> FFT320 -> split to X[0..320]
       cpx r[10];
-      const int base = t * HOP - NFFT / 2;
-      const bool interior = base >= 0 && base + NFFT <= L;            // no reflection: aligned float2 loads
-#pragma unroll
-      for (int n1 = 0; n1 < 10; ++n1) {
-        const int n = 32 * n1 + lane;
-        const float2 w = win2[n];
-        float2 x;
-        if (interior) x = *reinterpret_cast<const float2*>(sb + base + 2 * n);
-        else x = make_float2(sb[reflect_idx(base + 2 * n, L)], sb[reflect_idx(base + 2 * n + 1, L)]);
-        r[n1] = {x.x * w.x, x.y * w.y};
-      }
-      fft320<false>(r, c, lane);
-      // X[k] = E[k] + W640^k O[k];  E = (Z[k] + conj Z[N-k])/2, O = (Z[k] - conj Z[N-k])/(2i).  Then Y[k] = mag * X/|X|.
-#pragma unroll
-      for (int k1 = 0; k1 < 10; ++k1) {
-        const cpx zn = cconj(k1 == 0 ? shfl_idx(r[0], c.src0) : shfl_xor(r[10 - k1], 31));
-        const cpx zk = r[k1];
-        const cpx e = {0.5f * (zk.x + zn.x), 0.5f * (zk.y + zn.y)};
-        const cpx d = csub(zk, zn);
-        const cpx o = {0.5f * d.y, -0.5f * d.x};          // d / (2i)
-        const int k = k1 + 10 * c.k2;
-        const cpx X = cadd(e, cmul(tw2p[k1 * 32 + lane], o));
-        if (spec_out) { spec_out[(fo * NBIN + k) * 2] = X.x; spec_out[(fo * NBIN + k) * 2 + 1] = X.y; }
-        const float r2 = X.x * X.x + X.y * X.y;
-        const float m = __ldg(mg + (lane_major ? k1 * 32 + lane : k));
-        const float sc = m * rsqrtf(r2);                                  // mag / |X|
-        y[k1] = r2 > 0.f ? cpx{sc * X.x, sc * X.y} : cpx{m, 0.f};         // atan2(0,0) = 0
-        if (k1 == 0) {                                                    // Nyquist bin from the same pair (k = 0, lane 0)
-          const cpx Xn = csub(e, o);
-          if (spec_out && lane == 0) { spec_out[(fo * NBIN + NH) * 2] = Xn.x; spec_out[(fo * NBIN + NH) * 2 + 1] = Xn.y; }
-          const float q2 = Xn.x * Xn.x + Xn.y * Xn.y;
-          const float mn = __ldg(mg + NH);
-          const float sn = mn * rsqrtf(q2);
-          y320 = q2 > 0.f ? cpx{sn * Xn.x, sn * Xn.y} : cpx{mn, 0.f};
-        }
-      }
+      gl_load_frame<false>(sb, t, T, L, win2, tab + TAB_WIN, lane, r);
+      gl_analyze(r, c, lane, tw2p, mg, lane_major, spec_out, fo, y, y320);
     } else {
       const float* an = angles_t + fo * NBIN;
 #pragma unroll
@@ -263,31 +331,86 @@ __global__ void __launch_bounds__(WARPS * 32, 3) gl_frames_kernel(int mode, cons
       const float mn = __ldg(mg + NH);
       y320 = {mn * co, mn * s};
     }
-    // ---- inverse: Hermitian spectrum Y[0..320] (imaginary parts of DC / Nyquist ignored, as in the reference's basis)
-    //      Z[k] = E[k] + i O[k],  E = (Y[k] + conj Y[N-k])/2,  O = (Y[k] - conj Y[N-k])/2 * W640^{-k}
-    if (lane == 0) y[0].y = 0.f;
-    y320.y = 0.f;
     cpx z[10];
-#pragma unroll
-    for (int k1 = 0; k1 < 10; ++k1) {
-      cpx yn = cconj(k1 == 0 ? shfl_idx(y[0], c.src0) : shfl_xor(y[10 - k1], 31));
-      if (k1 == 0 && lane == 0) yn = y320;                 // k = 0 pairs with Y[320] (real)
-      const cpx yk = y[k1];
-      const cpx e = {0.5f * (yk.x + yn.x), 0.5f * (yk.y + yn.y)};
-      const cpx d = {0.5f * (yk.x - yn.x), 0.5f * (yk.y - yn.y)};
-      const cpx o = cmul(d, cconj(tw2p[k1 * 32 + lane]));
-      z[k1] = {e.x - o.y, e.y + o.x};                      // e + i o
-    }
-    fft320<true>(z, c, lane);
+    gl_synthesize(y, y320, c, lane, tw2p, win2, z);
     float* fr = frames + fo * NFFT;
-    const float sc = 1.f / (float)NH;
 #pragma unroll
-    for (int n1 = 0; n1 < 10; ++n1) {
-      const int n = 32 * n1 + lane;
-      const float2 w = win2[n];
-      *reinterpret_cast<float2*>(fr + 2 * n) = make_float2(z[n1].x * sc * w.x, z[n1].y * sc * w.y);
+    for (int n1 = 0; n1 < 10; ++n1) *reinterpret_cast<float2*>(fr + 2 * (32 * n1 + lane)) = make_float2(z[n1].x, z[n1].y);
+  }
+}
+
+// One WHOLE Griffin-Lim iteration in one kernel: STFT of the current signal -> unit phasor x target magnitude -> ISTFT frame
+// -> overlap-add INSIDE the CTA.  A CTA owns FPC = 8 * fpw consecutive frames of one clip; its warps add their frames into a
+// shared accumulator of (FPC + 3) hops in four conflict-free phases (frames 4 apart do not overlap), then the CTA writes
+// the hops only it touches with plain stores and adds the 3 + 3 boundary hops it shares with its neighbours with atomics
+// (two addends: order-independent).  The 49 MB of frames per iteration never exist; the accumulator holds UN-normalised
+// sums, the window-envelope division happens when the next iteration (or gl_normalize_kernel) reads them.
+// in_norm: sig_in is already normalised (the first iteration, fed by gl_ola_kernel).  acc_out must be zero on entry.
+template <bool ENV>
+__global__ void __launch_bounds__(WARPS * 32, 2) gl_iter_kernel(const float* __restrict__ sig_in, const float* __restrict__ mag_p,
+                                                              float* __restrict__ acc_out, int B, int T, int L, int fpw) {
+  __shared__ __align__(16) float tab[TAB_FLOATS];
+  extern __shared__ __align__(16) float s_acc[];                    // (8 * fpw + 3) * 160
+  const int FPC = WARPS * fpw, NACC = (FPC + 3) * HOP;
+  for (int i = threadIdx.x; i < TAB_FLOATS / 4; i += blockDim.x)
+    reinterpret_cast<float4*>(tab)[i] = reinterpret_cast<const float4*>(g_tab)[i];
+  for (int i = threadIdx.x; i < NACC; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  const cpx* wl_t = reinterpret_cast<const cpx*>(tab + TAB_WL);
+  const cpx* tw2p = reinterpret_cast<const cpx*>(tab + TAB_TW2);
+  const cpx* ws_t = reinterpret_cast<const cpx*>(tab + TAB_WS);
+  const float2* win2 = reinterpret_cast<const float2*>(tab + TAB_WIN);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * FPC;
+  LaneConst c;
+  c.wl = wl_t + lane;
+  c.ws = ws_t + lane;
+  c.k2 = bitrev5(lane);
+  c.src0 = bitrev5((32 - c.k2) & 31);
+  const float* sb = sig_in + (long long)b * L;
+
+#pragma unroll 1
+  for (int f = 0; f < fpw; ++f) {
+    const int tl = f * WARPS + warp, t = t0 + tl;
+    const bool live = t < T;                                          // warp-uniform
+    cpx z[10];
+    if (live) {
+      cpx r[10], y[10], y320;
+      gl_load_frame<ENV>(sb, t, T, L, win2, tab + TAB_WIN, lane, r);
+      gl_analyze(r, c, lane, tw2p, mag_p + ((long long)b * T + t) * NBIN, true, nullptr, 0, y, y320);
+      gl_synthesize(y, y320, c, lane, tw2p, win2, z);
+    }
+    // frames tl, tl + 4 of this pass do not overlap (4 hops apart): four phases, no conflicts, a fixed summation order
+#pragma unroll 1
+    for (int ph = 0; ph < 4; ++ph) {
+      if (live && (warp & 3) == ph) {
+        float2* dst = reinterpret_cast<float2*>(s_acc + tl * HOP);
+#pragma unroll
+        for (int n1 = 0; n1 < 10; ++n1) { float2 a = dst[32 * n1 + lane]; a.x += z[n1].x; a.y += z[n1].y; dst[32 * n1 + lane] = a; }
+      }
+      __syncthreads();
     }
   }
+  // s_acc[i] = sum over this CTA's frames at padded position n = 160 t0 + i; output sample m = n - 320
+  const int nf = min(FPC, T - t0);
+  float* out = acc_out + (long long)b * L;
+  for (int i = threadIdx.x; i < (nf + 3) * HOP; i += blockDim.x) {
+    const int m = t0 * HOP + i - NFFT / 2;
+    if (m < 0 || m >= L) continue;
+    const bool shared_lo = i < NFFT - HOP && t0 > 0;                 // also covered by the previous CTA's last three frames
+    const bool shared_hi = i >= nf * HOP && t0 + nf < T;             // ... by the next CTA's first three
+    if (shared_lo || shared_hi) atomicAdd(out + m, s_acc[i]); else out[m] = s_acc[i];
+  }
+}
+
+// sig[b][m] = acc[b][m] / wss[m + 320]: the normalisation gl_ola_kernel does, for the un-normalised sums of gl_iter_kernel
+__global__ void __launch_bounds__(256) gl_normalize_kernel(const float* __restrict__ acc, float* __restrict__ sig_out, int T, int L) {
+  const int m = blockIdx.x * 256 + threadIdx.x, b = blockIdx.y;
+  if (m >= L) return;
+  const float wss = gl_wss(m + NFFT / 2, T, g_tab + TAB_WIN);
+  const float a = acc[(size_t)b * L + m];
+  sig_out[(size_t)b * L + m] = wss > 1.1754944e-38f ? a / wss : a;
 }
 
 // sig_out[b][m] = (sum_t frames[b][t][m + 320 - 160 t]) / wss[m + 320]   for m in [0, L), L = 160 (T - 1)
@@ -340,6 +463,32 @@ int vca_gl_frames(int mode, const float* sig, const float* angles_t, const float
   const int fpw = g_gl_fpw;
   dim3 grid((T + WARPS * fpw - 1) / (WARPS * fpw), B);
   gl_frames_kernel<<<grid, WARPS * 32, 0, s>>>(mode, sig, angles_t, mag_t, frames, spec_out, B, T, L, fpw);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// One whole Griffin-Lim iteration (STFT -> phase x magnitude -> ISTFT -> overlap-add) in one kernel.  sig_in [B][L]: the
+// current signal, normalised (in_norm != 0: the output of vca_gl_ola / vca_gl_normalize) or the UN-normalised sums a previous
+// call left in its acc_out; mag_p [B][T][321] in the lane-major bin order of vca_gl_permute_bins; acc_out [B][L]: receives
+// the un-normalised overlap-add sums and must be ZERO on entry (boundary hops of neighbouring CTAs are added atomically).
+int vca_gl_iter(const float* sig_in, int in_norm, const float* mag_p, float* acc_out, int B, int T, int L, cudaStream_t s) {
+  VCA_CHECK_ARG(sig_in && mag_p && acc_out && sig_in != acc_out && B > 0 && T > 1 && L == HOP * (T - 1));
+  VCA_CHECK_ARG(B <= 65535);
+  if (int e = gl_ensure_tables(s)) return e;
+  const int fpw = g_gl_fpw;
+  const int FPC = WARPS * fpw;
+  dim3 grid((T + FPC - 1) / FPC, B);
+  const size_t smem = (size_t)(FPC + 3) * HOP * sizeof(float);
+  if (in_norm) gl_iter_kernel<false><<<grid, WARPS * 32, smem, s>>>(sig_in, mag_p, acc_out, B, T, L, fpw);
+  else gl_iter_kernel<true><<<grid, WARPS * 32, smem, s>>>(sig_in, mag_p, acc_out, B, T, L, fpw);
+  VCA_LAUNCH_CHECK();
+  return VCA_OK;
+}
+// sig_out = acc / window envelope (the tail of STFT.inverse, stft.py:110-127) for the sums vca_gl_iter leaves
+int vca_gl_normalize(const float* acc, float* sig_out, int B, int T, int L, cudaStream_t s) {
+  VCA_CHECK_ARG(acc && sig_out && B > 0 && T > 1 && L == HOP * (T - 1));
+  VCA_CHECK_ARG(B <= 65535);
+  if (int e = gl_ensure_tables(s)) return e;
+  gl_normalize_kernel<<<dim3((L + 255) / 256, B), 256, 0, s>>>(acc, sig_out, T, L);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
 }
