@@ -60,11 +60,7 @@ class FlatGroup:
                 self._slab_jobs.append((i, [self.grad.data_ptr() + 4 * o, self.slab.data_ptr() + 4 * o, 0, p.shape[0], p.shape[1], taps]))
         self._slab_tables = {}
 
-    def flush_slabs(self, lo: int = 0, hi: Optional[int] = None):
-        """grad += slab (transposed into the parameter layout), slab = 0, for the parameters whose flat offset lies in
-        [lo, hi) -- the same element ranges FusedAdam.step / the data-parallel all-reduce take.  Call it on a stream that
-        is ordered after every backward kernel of those parameters (Trainer: right after _join_branches)."""
-        hi = self.numel if hi is None else hi
+    def _slab_table(self, lo: int, hi: int):
         key = (lo, hi)
         tab = self._slab_tables.get(key)
         if tab is None:
@@ -75,6 +71,13 @@ class FlatGroup:
                     cta += lib().query("vca_pack_job_ctas", row[3], row[4], row[5])
             tab = (torch.tensor(rows, dtype=torch.int64, device=self.grad.device) if rows else None, len(rows), cta)
             self._slab_tables[key] = tab
+        return tab
+
+    def flush_slabs(self, lo: int = 0, hi: Optional[int] = None):
+        """grad += slab (transposed into the parameter layout), slab = 0, for the parameters whose flat offset lies in
+        [lo, hi) -- the same element ranges FusedAdam.step / the data-parallel all-reduce take.  Call it on a stream that
+        is ordered after every backward kernel of those parameters (Trainer: right after _join_branches)."""
+        tab = self._slab_table(lo, self.numel if hi is None else hi)
         if tab[0] is not None:
             lib().call("vca_grad_unslab_batched", tab[0], tab[1], tab[2])
 
@@ -198,6 +201,10 @@ class Trainer:
         self._d_done = self._ga_done = False
         n_vf = sum(1 for _ in self.mods["v_front"].parameters())
         self._vf_params = self.G.params[:n_vf]
+        # job tables of every slab flush the schedules use, built now (a host-to-device copy is illegal inside a graph capture)
+        vf_numel = self.G.offsets[n_vf]
+        for grp, rng in ((self.D, (0, self.D.numel)), (self.G, (0, self.G.numel)), (self.G, (vf_numel, self.G.numel)), (self.G, (0, vf_numel))):
+            grp._slab_table(*rng)
         self._genpost_params = self.G.params[n_vf:]
         self._vf_numel = self.G.offsets[n_vf]             # v_front gradients are G.grad[:_vf_numel]
         # weight / bias gradients that accumulate straight into the flat .grad buffer overlap the dgrad chain
