@@ -443,3 +443,57 @@ def test_bf16_step_is_reproducible():
     finally:
         V.ops.cfg.param_grad_streams = ()
         V.set_precision("fp32")
+
+
+def test_bf16_step_is_reproducible_at_bench_shape():
+    """The same property at the shape bench.py measures (B = 32, T = 75, random-init weights, device noise / dropout masks from a
+    fixed Philox seed), with and without the concurrent stream branches: the generator / Postnet outputs are bit-identical
+    (the large grids take split-K / statistics paths the B = 2 case above does not), the scalar losses agree to 1e-6 (means
+    reduced with one fp32 atomic per CTA), the D gradient to 1e-5.  The G gradient is compared with the SAME D gradient applied
+    in both runs: what is left between two runs is the fp32 order in which the split-K CTAs of the wgrad kernels add their
+    tiles (2e-7 in the D gradient) -- but Adam's first step turns that into +-lr flips of near-zero-gradient discriminator
+    weights, and the backward through the random-init generator's train-mode BatchNorms amplifies the resulting 1e-6
+    difference in dD/d(mel) to 1e-2 at its first layers (tools/grad_noise_by_param.py), so without pinning the D gradient
+    the G gradients of two identical runs differ by 8e-3."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    B, T = 32, 75
+    g = torch.Generator().manual_seed(3)
+    vid = torch.randn(B, 1, T, 112, 112, generator=g).cuda()
+    mel = (torch.rand(B, 1, 80, 4 * T, generator=g) * 2 - 1).cuda()
+    spec = torch.rand(B, 1, 321, 4 * T, generator=g).cuda()
+    lens = torch.full((B,), T, dtype=torch.int32).cuda()
+    try:
+        res, d_ref = [], None
+        for par in (True, True, False):
+            torch.manual_seed(1); V.manual_seed(1)
+            tr = Trainer(precision="bf16", dropout=True)
+            if not par:
+                tr.parallel_branches = False
+                tr.overlap_gru = False
+                V.ops.cfg.param_grad_streams = ()
+            tr._phase_d(vid, mel, spec, lens)
+            torch.cuda.synchronize()
+            d_own = tr.D.grad.clone()
+            if d_ref is None:
+                d_ref = d_own
+            else:
+                tr.D.grad.copy_(d_ref)
+            tr._phase_g_pre(); tr._phase_g(); tr._phase_g2()
+            torch.cuda.synchronize()
+            out = tr._st["out"]
+            res.append(({k: float(out[k]) for k in ("gen_loss", "dis_loss", "recon", "sync_loss", "g_sync", "real_loss", "fake_loss")},
+                        out["g3"].clone(), out["gs"].clone(), tr.G.grad.clone(), d_own))
+            del tr
+            torch.cuda.empty_cache()
+        l0, g30, gs0, ng0, nd0 = res[0]
+        for l1, g31, gs1, ng1, nd1 in res[1:]:
+            eg, ed = rel_l2(ng1, ng0), rel_l2(nd1, nd0)
+            print("bench-shape losses", l0, l1, "gradient run-to-run rel L2: G (same D gradient applied)", eg, "D", ed)
+            assert torch.equal(g30, g31) and torch.equal(gs0, gs1)          # generator + Postnet outputs: bit-identical
+            for k in l0:
+                assert abs(l0[k] - l1[k]) <= 1e-6 * abs(l0[k]), k
+            assert ed <= 1e-5 and eg <= 1e-4, (eg, ed)
+    finally:
+        V.ops.cfg.param_grad_streams = ()
+        V.set_precision("fp32")
