@@ -189,6 +189,16 @@ int vca_deemphasis_clip(const float* x, float* y, int B, int L, double coef, flo
    hflip + luma + ToTensor + Normalize + erase box; meta int [n][10] = l,u,r,b, flip, ex0,ey0,ex1,ey1, valid.  Bit-exact. */
 int vca_clip_preprocess(const unsigned char* frames, int n_frames, int H, int W, const int* meta, const int* kx, const int* bx, const int* ky, const int* by, int ksx, int ksy, int crop_w, int crop_h, int OW, int OH, float mean, float stdv, float* out, cudaStream_t stream);
 
+/* ---- data-parallel gradient exchange (the replacement of nn.DataParallel's gather / re-broadcast, train.py:112-119): NCCL sum
+ *      all-reduce of flat gradient buckets, one communicator per device of the calling process (one process per GPU).  NCCL is
+ *      bound at run time from the libnccl.so.2 already in the process; vca_comm_available() == 0 when there is none. ---------- */
+int vca_comm_available();
+int vca_comm_unique_id(void* id128);                                   /* rank 0: the 128-byte rendezvous token */
+int vca_comm_init(const void* unique_id, int rank, int world);         /* collective; binds to the current CUDA device */
+int vca_allreduce_bucket(void* ptr, long long count, int dtype, cudaStream_t stream);   /* in place, SUM; VCA_F32 / VCA_BF16 */
+int vca_comm_world();
+int vca_comm_destroy();
+
 #ifdef __cplusplus
 }
 #endif

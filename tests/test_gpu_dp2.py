@@ -97,3 +97,28 @@ def test_two_rank_gradients_equal_per_shard_mean(tmp_path, precision):
             assert abs(float(trs[0].D.flat.double().sum()) - ranks[0]["Dw"]) <= 1e-6 * abs(ranks[0]["Dw"]) + 1e-3
     finally:
         V.set_precision("fp32")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_native_comm_matches_torch_distributed(tmp_path):
+    """include/vcagan.h's NCCL helpers (vca_comm_unique_id / vca_comm_init / vca_allreduce_bucket): bucketed in-place
+    sum all-reduce of fp32 / bf16 buffers is bit-identical to torch.distributed.all_reduce on the same data (two ranks: the
+    sum of two addends is order-independent), and a Trainer step whose gradient exchange runs through it (VCA_NATIVE_COMM=1)
+    ends with the same gradients as the torch.distributed run of test_two_rank_gradients_equal_per_shard_mean."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(ROOT, "tests", "comm_worker.py"), str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ranks = [torch.load(os.path.join(tmp_path, f"comm_rank{i}.pt")) for i in range(2)]
+    for rk in ranks:
+        assert rk["world"] == 2 and rk["f32"] and rk["bf16"] and rk["tiny"] and rk["in_sync"]
+    assert torch.equal(ranks[0]["G"], ranks[1]["G"]) and torch.equal(ranks[0]["D"], ranks[1]["D"])
+    # against the torch.distributed exchange of the same two shards
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29544", os.path.join(ROOT, "tests", "dp2_worker.py"), str(tmp_path), "fp32"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    ref = torch.load(os.path.join(tmp_path, "rank0.pt"))
+    eg, ed = rel_l2(ranks[0]["G"], ref["G"]), rel_l2(ranks[0]["D"], ref["D"])
+    print("native-comm step vs torch.distributed step: G", eg, "D", ed)
+    assert eg < 2e-5 and ed < 2e-5

@@ -42,3 +42,37 @@ def broadcast_flat(flat: torch.Tensor, src: int = 0, group: Optional[dist.Proces
     """Make every replica start from rank `src`'s weights (done once; replicas then stay identical because every rank
     applies the same averaged gradient)."""
     dist.broadcast(flat, src, group=group)
+
+
+class NativeComm:
+    """The library's own NCCL communicator (include/vcagan.h: vca_comm_unique_id / vca_comm_init / vca_allreduce_bucket), one
+    per process and GPU.  torch.distributed is used ONCE, as the side channel that ships rank 0's 128-byte rendezvous token;
+    the gradient exchange itself then runs through the C ABI (what a non-PyTorch host would call)."""
+
+    def __init__(self, group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
+        import ctypes
+        from ._lib import lib, VcaError
+        self._lib = lib()
+        if self._lib.cdll.vca_comm_available() != 1:
+            raise VcaError("NativeComm: no NCCL library could be bound in this process")
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else device
+        tok = torch.zeros(128, dtype=torch.uint8)
+        if self.rank == 0 and self._lib.cdll.vca_comm_unique_id(ctypes.c_void_p(tok.data_ptr())) != 0:
+            raise VcaError(self._lib.cdll.vca_last_error().decode())
+        tok = tok.to(dev)
+        dist.broadcast(tok, 0, group=group)
+        tok = tok.cpu()
+        with torch.cuda.device(dev):
+            if self._lib.cdll.vca_comm_init(ctypes.c_void_p(tok.data_ptr()), self.rank, self.world) != 0:
+                raise VcaError(self._lib.cdll.vca_last_error().decode())
+
+    def allreduce_flat(self, flat: torch.Tensor, bucket_elems: int = 8 << 20):
+        """In-place sum all-reduce of a flat fp32 / bf16 CUDA buffer in buckets, on the current stream."""
+        from .ops import BF16, F32
+        dt = {torch.float32: F32, torch.bfloat16: BF16}[flat.dtype]
+        for s, e in bucket_ranges(flat.numel(), bucket_elems):
+            self._lib.call("vca_allreduce_bucket", flat[s:e], e - s, dt)
+
+    def close(self):
+        self._lib.cdll.vca_comm_destroy()

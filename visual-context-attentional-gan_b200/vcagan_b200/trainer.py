@@ -180,6 +180,9 @@ class Trainer:
         self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
         self.comm_stream = torch.cuda.Stream(device=self.device) if self.world > 1 else None
         self.single_graph = self.world == 1
+        # VCA_NATIVE_COMM=1: the gradient exchange goes through the library's own NCCL communicator (vca_comm_init /
+        # vca_allreduce_bucket) instead of torch.distributed's -- same NCCL, same sums (tests/test_gpu_dp2.py)
+        self.native_comm = dp.NativeComm(process_group, self.device) if (self.world > 1 and os.environ.get("VCA_NATIVE_COMM") == "1") else None
         if self.world > 1:
             self._sync_replicas()
         # Data-parallel runs split the G backward where the generator's last gradient is written: the all-reduce of the
@@ -255,7 +258,10 @@ class Trainer:
         cur = torch.cuda.current_stream()
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
-            dp.allreduce_flat(group.grad[lo:group.numel if hi is None else hi], self.pg, bucket_elems)
+            if self.native_comm is not None:       # the C ABI's own communicator (vca_allreduce_bucket)
+                self.native_comm.allreduce_flat(group.grad[lo:group.numel if hi is None else hi], bucket_elems)
+            else:
+                dp.allreduce_flat(group.grad[lo:group.numel if hi is None else hi], self.pg, bucket_elems)
             done = torch.cuda.Event()
             done.record()
         if wait:
