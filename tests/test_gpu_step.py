@@ -497,3 +497,40 @@ def test_bf16_step_is_reproducible_at_bench_shape():
     finally:
         V.ops.cfg.param_grad_streams = ()
         V.set_precision("fp32")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_reference_two_traversal_schedule_matches_merged_backward(precision):
+    """Trainer.merge_vfront_backward = False is the reference's own schedule: the D backward (train.py:210, retain_graph) walks
+    the visual front-end CNN once (sync loss), the G backward (train.py:236) walks it again, and the two weight gradients
+    add up in .grad.  The default takes d(dis_loss)/d(phon) on a detached leaf and injects it into ONE traversal.  Same
+    losses, same D gradient; G gradient equal up to the re-association (fp32: 1e-4; bf16: the two traversals round their
+    activation gradients to bf16 separately, so the visual front-end slice is held to 5e-2 and the rest to 1e-4)."""
+    import vcagan_b200 as V
+    from vcagan_b200.trainer import Trainer
+    spec = json.load(open(os.path.join(GOLD, "state_spec.json")))
+    vid, mel, sp, noise = golden_inputs()
+    try:
+        res = []
+        for merged in (True, False):
+            tr = Trainer(precision=precision, state={m: make_state(spec, m) for m in O.MODULES}, dropout=False)
+            tr.merge_vfront_backward = merged
+            tr._phase_d(vid.cuda(), mel.cuda(), sp.cuda(), [20, 13], noise)
+            torch.cuda.synchronize()
+            d = tr.D.grad.clone()
+            if res:
+                tr.D.grad.copy_(res[0][0])            # same discriminator update in both runs
+            tr._phase_g_pre(); tr._phase_g(); tr._phase_g2()
+            torch.cuda.synchronize()
+            out = tr._st["out"]
+            res.append((d, tr.G.grad.clone(), {k: float(out[k]) for k in ("gen_loss", "dis_loss", "recon", "sync_loss")}, tr._vf_numel))
+            del tr
+        (d0, g0, l0, cut), (d1, g1, l1, _) = res
+        e_d, e_vf, e_gp = rel_l2(d1, d0), rel_l2(g1[:cut], g0[:cut]), rel_l2(g1[cut:], g0[cut:])
+        print(precision, "two traversals vs merged: D", e_d, "v_front", e_vf, "gen+post", e_gp, l0, l1)
+        for k in l0:
+            assert abs(l0[k] - l1[k]) <= 1e-5 * max(1.0, abs(l0[k])), k
+        assert e_d < 1e-4 and e_gp < 1e-4
+        assert e_vf < (1e-4 if precision == "fp32" else 5e-2)
+    finally:
+        V.set_precision("fp32")
