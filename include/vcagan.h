@@ -69,6 +69,10 @@ int vca_conv_fwd_tc_ws(const ConvGeom* g, const void* x, const void* wd, const f
 int vca_conv_fwd_tc_epi(const ConvGeom* g, const void* x, const void* wd, const float* scale, const float* shift, const void* res, float res_scale, int act, float slope, const float* prelu_w, void* y, cudaStream_t stream);
 /* scale[c] = gamma[c] / sqrt(running_var[c] + eps); shift[c] = beta[c] + (bias[c] - running_mean[c]) * scale[c]  (bias may be null) */
 int vca_bn_fold(const float* running_mean, const float* running_var, const float* gamma, const float* beta, const float* bias, int C, float eps, float* scale, float* shift, cudaStream_t stream);
+/* inference: eval-mode BatchNorm folded into weights (scale) + bias (shift), y = a(conv + shift), a(v) = v > 0 ? v : v * slope[c]
+ * (test.py:126-141 runs the modules in eval mode); weights-stationary geometries only, else VCA_ERR_UNSUPPORTED */
+int vca_conv_fwd_tc_act_supported(const ConvGeom* g);
+int vca_conv_fwd_tc_act(const ConvGeom* g, const void* x, const void* wd, const float* shift, const float* slope, void* y, cudaStream_t stream);
 int vca_conv_fwd_tc_stats_supported(const ConvGeom* g);
 int vca_conv_fwd_tc_stats(const ConvGeom* g, const void* x, const void* wd, const float* bias, void* y, double* stats, cudaStream_t stream);
 int vca_conv_dgrad_tc_ws(const ConvGeom* g, const void* dy, const void* wf, void* dx, float* ws, long long ws_bytes, cudaStream_t stream);

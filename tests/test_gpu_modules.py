@@ -347,3 +347,50 @@ def test_eval_epilogue_fusion_matches_unfused(V, state_spec, golden):
         V.ops.cfg.fuse_eval_epilogue = False      # the default (see ops.Config)
         V.ops.cfg.fuse_stem_pool = True
         V.set_precision("fp32")
+
+
+def test_eval_bn_folded_into_weights_matches_separate_pass(V, state_spec, golden):
+    """Inference (test.py:126-141): eval-mode BatchNorm folded into the conv WEIGHTS + bias with the activation in the
+    weights-stationary kernel's epilogue (ops.conv_folded: stem, BasicBlock conv1, GenResBlk conv1 incl. the pixel-pair
+    merged 32-channel stage) against the separate normalisation pass, bf16, on the golden inputs: same bound as the other
+    bf16 comparisons, both inside the bf16 bound vs the reference, fewer launches; and the cache of folded weights must
+    notice a parameter / running-statistic change that torch's tensor versions do not see (raw-pointer updates)."""
+    vid, mel, spec, noise = golden_inputs()
+    V.set_precision("bf16")
+    try:
+        outs = []
+        for fold in (False, True, True):
+            V.ops.cfg.fold_eval_bn = fold
+            with torch.no_grad():
+                vf = build(V, state_spec, "v_front", False)
+                gen = build(V, state_spec, "gen", False); gen.fixed_noise = noise
+                post = build(V, state_spec, "post", False)
+                n0 = V.lib().launches
+                phon, sent = vf(vid.cuda())
+                g = gen(sent, phon, [20, 13])
+                gs = post(g[2])
+                torch.cuda.synchronize()
+                outs.append(([t.float().cpu() for t in (phon, sent, *g, gs)], V.lib().launches - n0))
+        names = ("phon", "sent", "g1", "g2", "g3", "gs")
+        errs = {n: rel_l2(b, a) for n, a, b in zip(names, outs[0][0], outs[1][0])}
+        print("eval BN fold: folded vs separate pass", errs, "library launches", outs[0][1], "->", outs[1][1], "(cached:", outs[2][1], ")")
+        assert max(errs.values()) < BF16_TOL, errs
+        assert outs[1][1] < outs[0][1] and outs[2][1] <= outs[1][1]
+        for a, b in zip(outs[1][0], outs[2][0]):
+            assert torch.equal(a, b)                                   # the cached folded weights give the same bits
+        for n, key in (("phon", "eval_phon"), ("sent", "eval_sent"), ("g3", "eval_g3"), ("gs", "eval_gs")):
+            assert rel_l2(outs[1][0][names.index(n)], golden[key]) < BF16_TOL, n
+        # cache invalidation: scale a BatchNorm's running variance in place through a raw-pointer style write + touch
+        blk = vf.resnet.layer1[0]
+        x = torch.randn(4, 28, 28, 64, device="cuda").bfloat16()
+        with torch.no_grad():
+            V.ops.cfg.fold_eval_bn = True
+            y0 = blk(x).float()
+            blk.bn1.running_var.mul_(4.0)                              # bumps the version: the fold must be redone
+            y1 = blk(x).float()
+            V.ops.cfg.fold_eval_bn = False
+            y1_ref = blk(x).float()
+        assert rel_l2(y1, y0) > 1e-2 and rel_l2(y1, y1_ref) < BF16_TOL
+    finally:
+        V.ops.cfg.fold_eval_bn = False        # the default (see ops.Config: measured slower)
+        V.set_precision("fp32")

@@ -17,9 +17,13 @@ torch.manual_seed(1)
 vf, gen, post = M.Visual_front().to(dev).eval(), M.Decoder().to(dev).eval(), M.Postnet().to(dev).eval()
 vid = torch.randn(B, 1, T, 112, 112, device=dev)
 lens = torch.full((B,), T, dtype=torch.int32, device=dev)
-for fused in (False, True):
+MODES = [("separate passes", False, False), ("epilogue fusion (scale/shift/residual)", True, False), ("BatchNorm folded into weights", False, True)]
+if len(sys.argv) > 2:
+    MODES = [m for m in MODES if sys.argv[2] in m[0]] or MODES
+for label, fused, fold in MODES:
     V.ops.cfg.fuse_eval_epilogue = fused
-    V.ops.cfg.fuse_stem_pool = fused
+    V.ops.cfg.fuse_stem_pool = True
+    V.ops.cfg.fold_eval_bn = fold
     run = lambda: infer.synthesize(vf, gen, post, vid, lens, n_iters=0, tta=True)
     for _ in range(2):
         run()
@@ -28,7 +32,7 @@ for fused in (False, True):
     a.record(); run(); b.record(); torch.cuda.synchronize()
     prof = V.lib().profile_step(run)
     tot = sum(v["ms"] for v in prof.values())
-    print(f"\n==== fused={fused}: forward {a.elapsed_time(b):.2f} ms; sum of library calls (serialised) {tot:.2f} ms")
+    print(f"\n==== {label}: forward {a.elapsed_time(b):.2f} ms; sum of library calls (serialised) {tot:.2f} ms")
     for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:14]:
         print(f"  {k:32s} n={v['n']:4d} {v['ms']:8.3f} ms   {v['flops'] / max(v['ms'], 1e-9) / 1e9:8.1f} TF/s")
         for g in v["top"][:(24 if k.startswith('vca_conv') or k.startswith('vca_bn_act') else 3)]:

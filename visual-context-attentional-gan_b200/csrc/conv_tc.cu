@@ -22,7 +22,8 @@ using namespace tc;
 
 // conv_tc_ws.cu: weights-stationary / halo-resident variant for <=128-channel layers (1 = launched, 0 = not applicable)
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
+                const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s,
+                const float* slope = nullptr);
 // conv_tc_hs.cu: halo-resident activations + streamed weights for 64..128 output channels (same return convention)
 int conv_hs_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
                 const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s);
@@ -565,6 +566,22 @@ int vca_conv_fwd_tc_epi(const ConvGeom* g, const void* x, const void* wd, const 
   EpiExtra ex{scale, (const bf16*)res, res_scale, act, slope, prelu_w};
   return fwd_like(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, shift, y, s, nullptr, 0, nullptr,
                   nullptr, &ex);
+}
+// Inference forward of a convolution whose eval-mode BatchNorm has been folded into the weights (scale) and the bias (shift):
+//     y = a(conv(x, wd) + shift),   a(v) = v > 0 ? v : v * slope[c]     (slope per output channel: LeakyReLU / PReLU / ReLU = 0)
+// Runs only where the weights-stationary kernel takes the geometry (its stacked MMAs and TMA-store epilogue are untouched:
+// the activation is one select per value on the accumulator row); VCA_ERR_UNSUPPORTED otherwise -- the caller then keeps the
+// separate normalisation pass.  1 / 0 from the _supported query.
+int vca_conv_fwd_tc_act_supported(const ConvGeom* g) {
+  if (!g || !vca_conv_tc_supported(g, 0)) return 0;
+  return conv_ws_try(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, nullptr, nullptr, nullptr, nullptr,
+                     nullptr, nullptr, nullptr) == 1 ? 1 : 0;
+}
+int vca_conv_fwd_tc_act(const ConvGeom* g, const void* x, const void* wd, const float* shift, const float* slope, void* y, cudaStream_t s) {
+  VCA_CHECK_ARG(g && x && wd && y && slope && vca_conv_tc_supported(g, 0));
+  const int r = conv_ws_try(g->N, g->IH, g->IW, g->Cin, g->OH, g->OW, g->Cout, g->KH, g->KW, g->ph, g->pw, 0, x, wd, shift, y, nullptr, nullptr, s, slope);
+  if (r == 0) { vca_set_error("vca_conv_fwd_tc_act: the weights-stationary kernel does not take this geometry"); return VCA_ERR_UNSUPPORTED; }
+  return r < 0 ? r : VCA_OK;
 }
 // 1 when vca_conv_fwd_tc_stats takes this geometry AND the statistics come (almost) for free: the weights-stationary
 // persistent kernel (<= 64 channels in and out: the stem, ResNet layer 1, the 40x150 / 80x300 generator stages -- the

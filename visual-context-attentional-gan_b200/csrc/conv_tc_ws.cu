@@ -64,6 +64,7 @@ struct WsParams {
   uint32_t a_stage_bytes, a_tx_bytes, w_bytes, tmem_cols, out_bytes;
   int base_off_mode, dbg;
   const float* bias;
+  const float* slope;      // inference: per-channel negative-side slope applied after the bias (LeakyReLU / PReLU / ReLU) or null
   double* stats;           // [2 * Cout] BatchNorm sum / sum-of-squares accumulators (fp64, added to) or null
   EpiExtra ex;             // inference epilogue (scale / residual / activation); has_ex = 0: plain bias epilogue
   int has_ex;
@@ -113,6 +114,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(const __grid_
   if (MODE == 2) epi_stage(s_sum, p.BN, blockIdx.y * p.BN, p.Cout, p.ex, p.bias);     // [3][BN] epilogue vectors in the same space
   float* s_bias = s_sum + 2 * p.BN;          // the bias of the plain / statistics epilogues, staged once (no global load per chunk)
   if (MODE != 2) for (int i = threadIdx.x; i < p.BN; i += blockDim.x) s_bias[i] = (p.bias && blockIdx.y * p.BN + i < p.Cout) ? p.bias[blockIdx.y * p.BN + i] : 0.f;
+  float* s_slope = s_bias + p.BN;
+  if (MODE == 0 && p.slope) for (int i = threadIdx.x; i < p.BN; i += blockDim.x) s_slope[i] = blockIdx.y * p.BN + i < p.Cout ? p.slope[blockIdx.y * p.BN + i] : 1.f;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.BN;
@@ -224,6 +227,20 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(const __grid_
     const uint32_t rb = (uint32_t)p.BN * 2u;
     const uint32_t swz = rb == 128 ? (uint32_t)(md & 7) : (uint32_t)((md >> 1) & 3);
     int it = 0;
+    // bias / activation slope of this thread's first two 16-column chunks in REGISTERS (every tile reuses them; as broadcast
+    // LDS they doubled the instruction count of the lean epilogue: the folded-BatchNorm inference convs ran 2x slower)
+    constexpr int NRB = MODE == 0 ? 16 : 1;
+    float rbias[2][NRB], rsl[2][NRB];
+    if (MODE == 0) {
+#pragma unroll
+      for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+        for (int i = 0; i < NRB; ++i) {
+          const int c = (2 * ci + half) * 16 + i;
+          rbias[ci][i] = c < p.BN ? s_bias[c] : 0.f;
+          rsl[ci][i] = (p.slope && c < p.BN) ? s_slope[c] : 1.f;
+        }
+    }
     // BatchNorm statistics (BN <= 64 whenever they are requested): every thread keeps running sums of ITS tile row's
     // 64 columns over all tiles of this persistent CTA -- two FMAs per value; the cross-row reduction happens once, below
     constexpr int NR = MODE == 1 ? 32 : 1;
@@ -280,9 +297,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) conv_tc_ws_kernel(const __grid_
               for (int i = 0; i < 16; ++i) v[i] += __shfl_down_sync(0xffffffffu, __uint_as_float(u[j - 3][i]), j);
           }
         }
-        if (p.bias) {
+        if (MODE == 0 && ci < 2) {
+          if (p.bias) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] += s_bias[c + i];
+            for (int i = 0; i < 16; ++i) v[i] += rbias[ci][i % NRB];
+          }
+          if (p.slope) {                     // inference: the activation that follows a BatchNorm folded into weights + bias
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f) + rsl[ci][i % NRB] * fminf(v[i], 0.f);
+          }
+        } else {
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += s_bias[c + i];
+          }
+          if (MODE == 0 && p.slope) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f) + s_slope[c + i] * fminf(v[i], 0.f);
+          }
         }
         if (MODE == 1 && ci < 2 && row_ok) {
 #pragma unroll
@@ -411,7 +443,8 @@ cudaError_t launch_ws(int sk, dim3 grid, size_t smem, cudaStream_t s, const CUte
 // Tries the weights-stationary kernel.  Returns 1 if it was launched, 0 if the geometry does not fit (caller uses the
 // streaming kernel), negative on error.  Arguments as conv_tc.cu::fwd_like.
 int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int KH, int KW, int ph, int pw, int flip,
-                    const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s) {
+                    const void* x, const void* wpk, const float* bias, void* y, double* stats, const tc::EpiExtra* ex, cudaStream_t s,
+                    const float* slope) {
   // x == nullptr: dry run -- 1 when this kernel would take the geometry (and, with stats != nullptr, emit the statistics)
   if (g_ws_mode == 0) return 0;
   const int taps = KH * KW, kchunks = (Kdim + KC - 1) / KC;
@@ -459,11 +492,11 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   const int rb = bn * 2;
   p.tma_out = g_ws_tma_out && !ex && (rb == 64 || rb == 128) && Nout % bn == 0;
   p.out_bytes = p.tma_out ? (((uint32_t)(p.th * p.tw) * (uint32_t)rb + 1023u) & ~1023u) : 0u;
-  const size_t fixed = (size_t)p.w_bytes + 2 * (size_t)p.out_bytes + 1024 + 5120;   // + alignment + barriers/tables/statistics or epilogue vectors
+  const size_t fixed = (size_t)p.w_bytes + 2 * (size_t)p.out_bytes + 1024 + 6144;   // + alignment + barriers/tables/statistics or epilogue vectors
   int sa = (int)((227 * 1024 - fixed) / p.a_stage_bytes);
   if (sa < 2 && p.tma_out) {                     // no room for the staging tiles: plain stores
     p.tma_out = 0; p.out_bytes = 0;
-    sa = (int)((227 * 1024 - (size_t)p.w_bytes - 1024 - 5120) / p.a_stage_bytes);
+    sa = (int)((227 * 1024 - (size_t)p.w_bytes - 1024 - 6144) / p.a_stage_bytes);
   }
   if (sa > 4) sa = 4;
   if (sa < 2) return 0;
@@ -473,10 +506,10 @@ int conv_ws_try(int NF, int IH, int IW, int Kdim, int OH, int OW, int Nout, int 
   if (stats && bn > 64) return 0;          // the epilogue keeps the statistics of at most 64 columns in registers
   if (!x) return 1;
   p.base_off_mode = g_ws_base_off; p.dbg = g_ws_dbg;
-  p.bias = bias; p.y = (bf16*)y; p.stats = stats;
+  p.bias = bias; p.y = (bf16*)y; p.stats = stats; p.slope = slope;
   p.has_ex = ex != nullptr;
   if (ex) p.ex = *ex; else p.ex = EpiExtra{nullptr, nullptr, 0.f, 0, 0.f, nullptr};
-  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 2 * (size_t)p.out_bytes + 1024 + 5120;
+  const size_t smem = (size_t)p.w_bytes + (size_t)sa * p.a_stage_bytes + 2 * (size_t)p.out_bytes + 1024 + 6144;
 
   CUtensorMap tmA, tmB, tmC;
   long long dA[4] = {Kdim, IW, IH, NF}; int bA[4] = {KC, p.P, p.th + KH - 1, 1};

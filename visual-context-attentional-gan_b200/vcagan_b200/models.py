@@ -95,8 +95,13 @@ class BasicBlock(nn.Module):
             y = self._forward_eval_fused(x, act)
             if y is not None:
                 return y
-        out = _conv(x, self.conv1, self.bn1)
-        out = ops.bn_act(out, self.bn1, act, 0.0, self.relu1.weight if self._prelu else None)
+        out = None
+        if not self.training and ops.fold_ok(x) and tuple(self.conv1.stride) == (1, 1):
+            # inference: bn1 folded into conv1's weights / bias, the activation in its epilogue (ops.conv_folded)
+            out = ops.conv_folded(x, self.conv1.weight, None, self.conv1.padding, self.bn1, act, 0.0, self.relu1.weight if self._prelu else None)
+        if out is None:
+            out = _conv(x, self.conv1, self.bn1)
+            out = ops.bn_act(out, self.bn1, act, 0.0, self.relu1.weight if self._prelu else None)
         out = _conv(out, self.conv2, self.bn2)
         res = x
         if self.downsample is not None:
@@ -186,10 +191,13 @@ class Visual_front(nn.Module):
         c0 = self.frontend[0]
         if (cfg.dtype == torch.bfloat16 and cfg.use_tc and self.in_channels == 1 and c0.kernel_size == (5, 7, 7)
                 and c0.stride == (1, 2, 2) and c0.padding == (2, 3, 3)):
-            x = ops.stem_conv(x, c0.weight, self.frontend[1] if self.frontend[1].training else None)   # im2col(7x7) + (5,1) conv on tcgen05
+            x = ops.stem_conv(x, c0.weight, self.frontend[1] if self.frontend[1].training else None,
+                              fold=None if self.training else (self.frontend[1], self.frontend[2].weight))   # im2col(7x7) + (5,1) conv on tcgen05
         else:
             x = _conv(_in_cl(x), c0)                    # generic exact path: (B,T,112,112,1) -> (B,T,56,56,64)
-        if ops.bn_prelu_maxpool_supported(x, x.shape[-1]):
+        if getattr(x, "_vca_activated", False):           # inference: BN + PReLU already applied in the conv's epilogue
+            x = ops.maxpool3x3s2(x.view(B * T, x.shape[2], x.shape[3], x.shape[4]))
+        elif ops.bn_prelu_maxpool_supported(x, x.shape[-1]):
             stats = getattr(x, "_vca_bn_sums", None)
             x = x.view(B * T, x.shape[2], x.shape[3], x.shape[4])
             if stats is not None:
@@ -299,12 +307,19 @@ class GenResBlk(nn.Module):
                 r = r1          # conv2 has no fused route: finish on the separate kernels
                 r = _conv(r, self.conv2)
                 return ops.add_scale(r, s, INV_SQRT2)
-        if const_channels and not self.upsample and cfg.rowconst:
-            r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding),
-                                  zero_bias_grad=self.norm2.training)
+        rf = None
+        if not self.training and ops.fold_ok(r) and not (const_channels and not self.upsample and cfg.rowconst):
+            # inference: norm2 folded into conv1's weights / bias, LeakyReLU in its epilogue (ops.conv_folded)
+            rf = ops.conv_folded(r, self.conv1.weight, self.conv1.bias, self.conv1.padding, self.norm2, ACT_LRELU, 0.2)
+        if rf is not None:
+            r = rf
         else:
-            r = _conv(r, self.conv1, self.norm2)
-        r = ops.bn_act(r, self.norm2, ACT_LRELU, 0.2)
+            if const_channels and not self.upsample and cfg.rowconst:
+                r = ops.conv_rowconst(r, const_channels, self.conv1.weight, self.conv1.bias, tuple(self.conv1.padding),
+                                      zero_bias_grad=self.norm2.training)
+            else:
+                r = _conv(r, self.conv1, self.norm2)
+            r = ops.bn_act(r, self.norm2, ACT_LRELU, 0.2)
         r = _conv(r, self.conv2)
         s = ops.upsample2(x) if self.upsample else x
         if self.learned_sc:

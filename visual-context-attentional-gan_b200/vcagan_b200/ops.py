@@ -40,6 +40,11 @@ class Config:
     # layer 3: conv 0.448 -> 0.635 ms for a 0.10 ms BatchNorm pass.  The epilogue of these kernels is not hidden behind the
     # MMAs (one accumulator per CTA, or a mainloop of only ~2k cycles per tile), while the separate pass runs at HBM speed.
     fuse_eval_epilogue = False
+    # inference: eval-mode BatchNorm folded into conv weights + bias, activation in the epilogue (conv_folded).  Correct
+    # (tests/test_gpu_modules.py) but a net LOSS: it removes 1.1 ms of bn_act passes and 1.1 ms of the stem tail for 64 clips, and
+    # the convs that carry the bias + activation get 1.5-1.7x slower (their epilogue, not the MMAs, is the critical path of
+    # these HBM-bound layers: 41.8 vs 40.1 ms forward, profiles/infer_profile_r02b.txt).  Off by default.
+    fold_eval_bn = os.environ.get("VCA_FOLD_EVAL_BN", "0") == "1"
     fuse_stem_pool = True   # stem BatchNorm3d + PReLU + MaxPool3d as one pass over the raw conv output (bn_prelu_maxpool)
     fuse_bn_stats = True    # train-mode BatchNorm statistics come out of the producing conv's epilogue (vca_conv_fwd_tc_stats)
     pair_merge = True       # 32-channel 5x5 convs run as 64-channel 5x3 convs over pixel pairs (_conv5_via_pairs)
@@ -644,7 +649,76 @@ def conv_epi(x, w, bias=None, stride=(1, 1), pad=(0, 0), bn=None, act=ACT_NONE, 
     return _conv_epi_raw(x, w, scale, shift, res, res_scale, act, slope, prelu_w, pad)
 
 
-def stem_conv(vid, w, bn=None):
+# ---- inference: eval-mode BatchNorm folded into the conv's WEIGHTS and bias, activation in the epilogue --------------------
+# (SURVEY appendix A #20.)  BN_eval(conv(x, w) + b) = conv(x, w * s) + (b - mean) * s + beta with s = gamma / sqrt(var + eps): the
+# scale goes into the packed bf16 weights, the shift is the conv's bias, and the LeakyReLU / PReLU that follows is one select
+# per value in the weights-stationary kernel's epilogue (vca_conv_fwd_tc_act) -- unlike the scale/shift/residual epilogue
+# of vca_conv_fwd_tc_epi (measured slower than the pass it removed) it adds no loads and keeps the stacked MMAs and the
+# TMA-store epilogue.  The folded, packed weights are cached per (weight, BatchNorm) version.
+_fold_cache = {}
+# Bumped whenever something rewrites parameters or BatchNorm running statistics THROUGH RAW POINTERS (train-mode BatchNorm
+# kernels, the fused Adam kernel): torch's tensor versions do not see those writes, so the cache of folded weights keys on it.
+_train_touch = [0]
+
+
+def fold_ok(x) -> bool:
+    return cfg.fold_eval_bn and cfg.use_tc and x.dtype == torch.bfloat16 and not torch.is_grad_enabled()
+
+
+def _folded_weights(w, bias, bn, act, slope, prelu_w, expand_pairs):
+    vers = (_train_touch[0], w._version, bn.running_mean._version, bn.running_var._version, bn.weight._version, bn.bias._version,
+            -1 if bias is None else bias._version, -1 if prelu_w is None else prelu_w._version, act, float(slope), expand_pairs)
+    key = (w.data_ptr(), bn.running_mean.data_ptr())
+    hit = _fold_cache.get(key)
+    if hit is not None and hit[0] == vers:
+        return hit[1:]
+    Cout = w.shape[0]
+    scale, shift = _fold(bn, bias, Cout, w.device)
+    wf32 = (w.detach().float() * scale.view(-1, *([1] * (w.dim() - 1)))).contiguous()
+    if act == ACT_PRELU:
+        sl = prelu_w.detach().float().clone()
+    else:
+        sl = torch.full((Cout,), float(slope) if act == ACT_LRELU else (0.0 if act == ACT_RELU else 1.0), dtype=torch.float32, device=w.device)
+    if expand_pairs:             # pixel-pair merged 32-channel 5x5 layers: Toeplitz-expanded weight, channels = [pair position][c]
+        KH = wf32.shape[2]
+        w2 = torch.empty((2 * Cout, 2 * wf32.shape[1], KH, 3), dtype=torch.float32, device=w.device)
+        lib().call("vca_pair_expand_weight", wf32, w2, Cout, wf32.shape[1], KH)
+        wf32, shift, sl = w2, torch.cat([shift, shift]), torch.cat([sl, sl])
+    co, ci = wf32.shape[0], wf32.shape[1]
+    taps = wf32.numel() // (co * ci)
+    wf = torch.empty((taps, ci, co), dtype=torch.bfloat16, device=w.device)
+    wd = torch.empty((taps, co, ci), dtype=torch.bfloat16, device=w.device)
+    lib().call("vca_pack_conv_weight", BF16, wf32, wf, wd, co, ci, taps)
+    val = (wd, shift.contiguous(), sl.contiguous(), tuple(wf32.shape))
+    _fold_cache[key] = (vers,) + val
+    return val
+
+
+def conv_folded(x, w, bias, pad, bn, act=ACT_NONE, slope=0.0, prelu_w=None):
+    """Inference only: act(BN_eval(conv(x, w) + bias)) with the BatchNorm folded into weights + bias and the activation in the
+    conv's epilogue; stride-1 2-D convs on the weights-stationary tcgen05 kernel (incl. the pixel-pair merged 32-channel
+    5x5 layers).  Returns None where that kernel does not take the geometry (the caller keeps the separate pass)."""
+    pad = tuple(pad)
+    if x.dim() != 4 or w.dim() != 4 or not x.is_contiguous():
+        return None
+    pairs = (cfg.pair_merge and tuple(w.shape[2:]) == (5, 5) and w.shape[0] == w.shape[1] and w.shape[1] in cfg.pair_merge_channels
+             and pad == (2, 2) and x.shape[-1] == w.shape[1] and x.shape[2] % 2 == 0)
+    N, H, W, C = x.shape
+    xs = x.view(N, H, W // 2, 2 * C) if pairs else x
+    wshape = (2 * w.shape[0], 2 * w.shape[1], w.shape[2], 3) if pairs else tuple(w.shape)
+    g, oshape = _geom(xs.shape, wshape, (1, 1), (w.shape[2] // 2, 1) if pairs else pad)
+    if wshape[0] % 8 or not _tc_ok(g, 0, x.dtype) or lib().query("vca_conv_fwd_tc_act_supported", g) != 1:
+        return None
+    wd, shift, sl, _ = _folded_weights(w, bias, bn, act, slope, prelu_w, pairs)
+    y = torch.empty(oshape, dtype=x.dtype, device=x.device)
+    lib().call("vca_conv_fwd_tc_act", g, xs, wd, shift, sl, y)
+    return y.view(N, oshape[1], W, w.shape[0]) if pairs else y
+
+
+_stem_fold_w = {}
+
+
+def stem_conv(vid, w, bn=None, fold=None):
     """Visual front-end stem Conv3d(1,64,(5,7,7),(1,2,2),(2,3,3)) (visual_front.py:11) on the tcgen05 path:
     a gather kernel unrolls the 7x7 spatial taps of the single input channel into 64 channels (49 used), the
     remaining 5-tap temporal convolution is a (5,1) stride-1 conv over (T, 56*56).  vid: (B,1,T,H,W) fp32 -> (B,T,OH,OW,64)."""
@@ -655,6 +729,18 @@ def stem_conv(vid, w, bn=None):
     lib().call("vca_stem_im2col", _dt(vid), BF16 if cfg.dtype == torch.bfloat16 else F32, vid, cols, B * T, H, W)
     Cout = w.shape[0]
     w2 = torch.nn.functional.pad(w.view(Cout, 5, 49).permute(0, 2, 1), (0, 0, 0, 15)).unsqueeze(-1)   # (Cout,64,5,1)
+    if fold is not None and fold_ok(cols):
+        # inference: BatchNorm3d + PReLU ride in the (5,1) conv (weights scaled, shift as bias, slope in the epilogue)
+        fbn, fprelu = fold
+        key_w = _stem_fold_w.get(w.data_ptr())
+        if key_w is None or key_w[0] != w._version:
+            key_w = (w._version, w2.contiguous())
+            _stem_fold_w[w.data_ptr()] = key_w                    # a stable tensor, so that conv_folded's cache can key on it
+        yf = conv_folded(cols.view(B, T, OH * OW, 64), key_w[1], None, (2, 0), fbn, ACT_PRELU, 0.0, fprelu)
+        if yf is not None:
+            y = yf.view(B, T, OH, OW, Cout)
+            y._vca_activated = True
+            return y
     y4 = _conv_bn(cols.view(B, T, OH * OW, 64), w2, None, (1, 1), (2, 0), False, bn)
     y = y4.view(B, T, OH, OW, Cout)
     if hasattr(y4, "_vca_bn_sums"):
@@ -695,6 +781,8 @@ class BNActFn(Function):
     def forward(ctx, x, res, gamma, beta, running_mean, running_var, prelu_w, training, act, slope, eps, momentum,
                 pre_sums=None, fold=1):
         _require_cuda(x)
+        if training:
+            _train_touch[0] += 1
         x = _c(x)
         res = None if res is None else _c(res)
         C = x.shape[-1]
@@ -773,6 +861,8 @@ class BNPReluMaxPoolFn(Function):
 
     @staticmethod
     def forward(ctx, x, gamma, beta, running_mean, running_var, prelu_w, training, eps, momentum, pre_sums=None, fold=1):
+        if training:
+            _train_touch[0] += 1
         _require_cuda(x)
         x = _c(x)
         NF, H, W, C = x.shape

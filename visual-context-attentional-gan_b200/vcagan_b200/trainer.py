@@ -127,6 +127,7 @@ class FusedAdam:
         vmax = None if self.vmax is None else self.vmax[lo:hi]
         lib().call("vca_adam_step_dev", self.g.flat[lo:hi], self.g.grad[lo:hi], self.m[lo:hi], self.v[lo:hi], vmax, hi - lo, self.lr_dev,
                    self.betas[0], self.betas[1], self.eps, self.wd, self.t_dev, grad_scale, 1 if bump else 0)
+        ops._train_touch[0] += 1   # ... and the cache of BatchNorm-folded inference weights (ops.conv_folded)
         if invalidate:
             self.g.epoch[0] += 1   # the kernel wrote through raw pointers: invalidate the packed-weight cache of this group
 
