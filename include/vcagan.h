@@ -81,7 +81,8 @@ int vca_conv_wgrad_tc(const ConvGeom* g, const void* dy, const void* x, float* d
  * memory + TMA reduce-add (no scattered atomics); vca_grad_unslab_batched folds the slabs of an optimizer group back into
  * the parameter layout ([Cout][Cin][taps], what torch.autograd leaves in train.py:210,236's .grad) and zeroes them */
 int vca_conv_wgrad_tc_tm(const ConvGeom* g, const void* dy, const void* x, float* dw_tm, cudaStream_t stream);
-int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, cudaStream_t stream);
+int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, int max_taps, cudaStream_t stream);
+int vca_unslab_job_ctas(int Cout, int Cin, int taps);
 
 
 /* ---- GEMM (nn.Linear: visual_front.py:21, generator.py:147-152,293,303,336; torch.bmm: generator.py:161,167,354;

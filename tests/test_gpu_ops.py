@@ -809,8 +809,8 @@ def test_wgrad_tap_major_and_unslab(V, case):
         slab2 = torch.randn(4, 24, 20, device="cuda"); grad2 = torch.zeros(24, 20, 2, 2, device="cuda"); ref2 = slab2.permute(1, 2, 0).reshape(24, 20, 2, 2).clone()
         rows, cta = [], 0
         for gr, sl, co, ci, tp in ((grad, slab, Cout, Cin, taps), (grad2, slab2, 24, 20, 4)):
-            rows.append([gr.data_ptr(), sl.data_ptr(), 0, co, ci, tp, cta, 0]); cta += L.query("vca_pack_job_ctas", co, ci, tp)
-        L.call("vca_grad_unslab_batched", torch.tensor(rows, dtype=torch.int64, device="cuda"), 2, cta)
+            rows.append([gr.data_ptr(), sl.data_ptr(), 0, co, ci, tp, cta, 0]); cta += L.query("vca_unslab_job_ctas", co, ci, tp)
+        L.call("vca_grad_unslab_batched", torch.tensor(rows, dtype=torch.int64, device="cuda"), 2, cta, max(taps, 4))
         torch.cuda.synchronize()
         assert rel_l2((grad.cpu() - 0.5) / 2, dwr) < BF16_TOL
         assert torch.equal(grad2, ref2)

@@ -247,8 +247,13 @@ __global__ void __launch_bounds__(256) pack_batched_kernel(const long long* __re
 // The tcgen05 wgrad kernels add a filter's gradient to a TAP-MAJOR fp32 slab [taps][Cout][Cin] (vca_conv_wgrad_tc_tm: TMA
 // reduce-add boxes instead of scattered 4-byte atomics).  Job table as above with j[0] = the parameter's .grad
 // ([Cout][Cin][taps], ADDED to), j[1] = its slab (read, then left ZEROED for the next step), j[2] unused.
+// A CTA owns UCO output channels x UCI input channels x ALL taps of one filter: the slab side is read in 128-byte runs (one
+// per tap and output channel), the gradient side is ONE contiguous run of UCI * taps floats per output channel (the
+// [Cout][Cin][taps] layout keeps (ci, tap) adjacent) -- the first version wrote 8-tap (32-byte) fragments and took three
+// passes over every line: 2 TB/s.  All loads of a phase are issued before the first dependent store.
+constexpr int UCO = 8, UCI = 32;
 __global__ void __launch_bounds__(256) unslab_batched_kernel(const long long* __restrict__ jobs, int njobs) {
-  __shared__ float s[PK_T][PK][PK + 1];
+  extern __shared__ float us[];                  // [UCO][UCI * taps]
   int lo = 0, hi = njobs - 1;
   const long long me = blockIdx.x;
   while (lo < hi) {
@@ -259,42 +264,37 @@ __global__ void __launch_bounds__(256) unslab_batched_kernel(const long long* __
   float* __restrict__ grad = reinterpret_cast<float*>(j[0]);
   float* __restrict__ slab = reinterpret_cast<float*>(j[1]);
   const int Cout = (int)j[3], Cin = (int)j[4], taps = (int)j[5];
-  int local = (int)(me - j[6]);
-  const int tiles_ci = (Cin + PK - 1) / PK, tiles_co = (Cout + PK - 1) / PK;
-  const int bx = local % tiles_ci; local /= tiles_ci;
-  const int by = local % tiles_co; const int bz = local / tiles_co;
-  const int co0 = by * PK, ci0 = bx * PK, t0 = bz * PK_T;
-  const int tc = min(PK_T, taps - t0);
-  const int n = PK * PK * tc;
-  constexpr int IT = PK * PK * PK_T / 256;       // 32 elements per thread: ALL loads of a phase are issued before the first
-  float v[IT];                                   // dependent store (a load-store chain per element ran at 170 GB/s)
+  const int local = (int)(me - j[6]);
+  const int tiles_ci = (Cin + UCI - 1) / UCI;
+  const int ci0 = (local % tiles_ci) * UCI, co0 = (local / tiles_ci) * UCO;
+  const int a = threadIdx.x % UCI, bq = threadIdx.x / UCI;          // this thread's (ci, co) inside the tile
+  const bool ok = co0 + bq < Cout && ci0 + a < Cin;
+  const int row = UCI * taps;
+  float* q = slab + ((long long)(co0 + bq)) * Cin + ci0 + a;         // + t * Cout * Cin per tap
+  const long long tstride = (long long)Cout * Cin;
+  for (int t0 = 0; t0 < taps; t0 += 8) {
+    float v[8];
 #pragma unroll
-  for (int k = 0; k < IT; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int a = i % PK; int r = i / PK; const int b = r % PK; const int t = r / PK;
-    v[k] = (i < n && co0 + b < Cout && ci0 + a < Cin) ? slab[((long long)(t0 + t) * Cout + co0 + b) * Cin + ci0 + a] : 0.f;
-  }
+    for (int k = 0; k < 8; ++k) v[k] = (ok && t0 + k < taps) ? q[(t0 + k) * tstride] : 0.f;
 #pragma unroll
-  for (int k = 0; k < IT; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int a = i % PK; int r = i / PK; const int b = r % PK; const int t = r / PK;
-    if (i < n) {
-      s[t][b][a] = v[k];
-      if (co0 + b < Cout && ci0 + a < Cin) slab[((long long)(t0 + t) * Cout + co0 + b) * Cin + ci0 + a] = 0.f;
-    }
+    for (int k = 0; k < 8; ++k)
+      if (t0 + k < taps) {
+        us[bq * row + a * taps + t0 + k] = v[k];
+        if (ok) q[(t0 + k) * tstride] = 0.f;
+      }
   }
   __syncthreads();
+  const int nci = min(UCI, Cin - ci0);
+  const int n = nci * taps;                                            // valid floats per output-channel row
+  for (int b = 0; b < UCO && co0 + b < Cout; ++b) {
+    float* g = grad + ((long long)(co0 + b) * Cin + ci0) * taps;
+    for (int i0 = 0; i0 < n; i0 += 256 * 4) {
+      float v[4];
 #pragma unroll
-  for (int k = 0; k < IT; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
-    v[k] = (i < n && co0 + co < Cout && ci0 + ci < Cin) ? grad[((long long)(co0 + co) * Cin + ci0 + ci) * taps + t0 + t] : 0.f;
-  }
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256 + (int)threadIdx.x; v[k] = i < n ? g[i] : 0.f; }
 #pragma unroll
-  for (int k = 0; k < IT; ++k) {
-    const int i = threadIdx.x + k * 256;
-    const int t = i % tc; int r = i / tc; const int ci = r % PK; const int co = r / PK;
-    if (i < n && co0 + co < Cout && ci0 + ci < Cin) grad[((long long)(co0 + co) * Cin + ci0 + ci) * taps + t0 + t] = v[k] + s[t][co][ci];
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256 + (int)threadIdx.x; if (i < n) g[i] = v[k] + us[b * row + i]; }
+    }
   }
 }
 
@@ -302,13 +302,29 @@ __global__ void __launch_bounds__(256) unslab_batched_kernel(const long long* __
 
 extern "C" {
 // jobs: device table (8 x int64 per job: grad, slab, 0, Cout, Cin, taps, first CTA, 0); total_ctas = sum of
-// vca_pack_job_ctas over the jobs.  grad += slab (transposed), slab = 0.  Must be ordered after every kernel that adds to
+// vca_unslab_job_ctas over the jobs; max_taps = the largest taps of any job (sizes the shared-memory tile).  grad += slab (transposed), slab = 0.  Must be ordered after every kernel that adds to
 // either buffer (it is a plain read-modify-write).
-int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, cudaStream_t s) {
-  VCA_CHECK_ARG(jobs && njobs > 0 && total_ctas > 0 && total_ctas < 0x7fffffffLL);
-  unslab_batched_kernel<<<(unsigned)total_ctas, 256, 0, s>>>(jobs, njobs);
+int vca_grad_unslab_batched(const long long* jobs, int njobs, long long total_ctas, int max_taps, cudaStream_t s) {
+  VCA_CHECK_ARG(jobs && njobs > 0 && total_ctas > 0 && total_ctas < 0x7fffffffLL && max_taps > 0);
+  const size_t smem = (size_t)UCO * UCI * max_taps * sizeof(float);
+  if (smem > 200 * 1024) { vca_set_error("vca_grad_unslab_batched: %d taps do not fit in shared memory", max_taps); return VCA_ERR_UNSUPPORTED; }
+  if (smem > 48 * 1024) {
+    static size_t attr = 0;
+    if (smem > attr) {
+      if (cudaFuncSetAttribute(unslab_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        vca_set_error("cudaFuncSetAttribute(unslab_batched_kernel) failed"); return VCA_ERR_CUDA;
+      }
+      attr = smem;
+    }
+  }
+  unslab_batched_kernel<<<(unsigned)total_ctas, 256, smem, s>>>(jobs, njobs);
   VCA_LAUNCH_CHECK();
   return VCA_OK;
+}
+// CTAs a job of this shape occupies in vca_grad_unslab_batched
+int vca_unslab_job_ctas(int Cout, int Cin, int taps) {
+  if (Cout <= 0 || Cin <= 0 || taps <= 0) return 0;
+  return ((Cin + UCI - 1) / UCI) * ((Cout + UCO - 1) / UCO);
 }
 // CTAs a job of this shape occupies in vca_pack_conv_weights_batched (the host builds the CTA offsets of the table with it)
 int vca_pack_job_ctas(int Cout, int Cin, int taps) {

@@ -68,8 +68,9 @@ class FlatGroup:
             for i, row in self._slab_jobs:
                 if lo <= self.offsets[i] < hi:
                     rows.append(row + [cta, 0])
-                    cta += lib().query("vca_pack_job_ctas", row[3], row[4], row[5])
-            tab = (torch.tensor(rows, dtype=torch.int64, device=self.grad.device) if rows else None, len(rows), cta)
+                    cta += lib().query("vca_unslab_job_ctas", row[3], row[4], row[5])
+            tab = (torch.tensor(rows, dtype=torch.int64, device=self.grad.device) if rows else None, len(rows), cta,
+                   max((r[5] for r in rows), default=1))
             self._slab_tables[key] = tab
         return tab
 
@@ -79,7 +80,7 @@ class FlatGroup:
         is ordered after every backward kernel of those parameters (Trainer: right after _join_branches)."""
         tab = self._slab_table(lo, self.numel if hi is None else hi)
         if tab[0] is not None:
-            lib().call("vca_grad_unslab_batched", tab[0], tab[1], tab[2])
+            lib().call("vca_grad_unslab_batched", tab[0], tab[1], tab[2], tab[3])
 
     def zero_grad(self):
         self.grad.zero_()
