@@ -840,3 +840,29 @@ def test_first_backward_op_on_fresh_autograd_thread(V):
         "torch.cuda.synchronize(); print('ok')\n")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_batched_weight_repack_matches_single(V, dtype):
+    """vca_pack_conv_weights_batched (one launch for every weight of an optimizer group: full-filter tiles, contiguous
+    parameter reads) == vca_pack_conv_weight per weight, bit for bit: ragged channel counts, 1 / 9 / 15 / 25 taps and a 49-tap
+    filter (two tap chunks)."""
+    from vcagan_b200.ops import BF16, F32
+    L = V.lib()
+    g = torch.Generator().manual_seed(9)
+    shapes = [(64, 64, 9), (40, 24, 25), (512, 640, 25), (321, 256, 1), (128, 96, 15), (16, 8, 49), (33, 70, 5)]
+    ws = [torch.randn(co, ci, t, generator=g).cuda() for co, ci, t in shapes]
+    dt = BF16 if dtype == torch.bfloat16 else F32
+    ref, out, rows, cta = [], [], [], 0
+    for w, (co, ci, t) in zip(ws, shapes):
+        wf, wd = torch.empty(t, ci, co, dtype=dtype, device="cuda"), torch.empty(t, co, ci, dtype=dtype, device="cuda")
+        L.call("vca_pack_conv_weight", dt, w, wf, wd, co, ci, t)
+        ref.append((wf, wd))
+        wf2, wd2 = torch.full_like(wf, float("nan")), torch.full_like(wd, float("nan"))
+        out.append((wf2, wd2))
+        rows.append([w.data_ptr(), wf2.data_ptr(), wd2.data_ptr(), co, ci, t, cta, 0])
+        cta += L.query("vca_pack_job_ctas", co, ci, t)
+    L.call("vca_pack_conv_weights_batched", dt, torch.tensor(rows, dtype=torch.int64, device="cuda"), len(rows), cta)
+    torch.cuda.synchronize()
+    for (a, b), (c, d), sh in zip(ref, out, shapes):
+        assert torch.equal(a, c) and torch.equal(b, d), sh
