@@ -35,6 +35,7 @@ extern int g_hs_mode;       // conv_tc_hs.cu
 extern int g_wgws_waves;    // conv_tc_wgrad_ws.cu
 extern int g_wgws_mstack, g_wg_dbg;
 extern int g_fwd_smem_kb, g_wg_smem_kb;   // conv_tc.cu
+extern int g_im2col_rb;                    // pool.cu
 extern int g_gl_fpw;        // stft.cu
 
 namespace {
@@ -552,6 +553,7 @@ int vca_set_option(const char* key, int value) {
   if (eq("gru_cluster")) { g_gru_cluster = value; return VCA_OK; }
   if (eq("gru_bs")) { g_gru_bs = value; return VCA_OK; }
   if (eq("hs_mode")) { g_hs_mode = value; return VCA_OK; }
+  if (eq("im2col_rb")) { g_im2col_rb = value < 0 ? 0 : value; return VCA_OK; }   // 0: the untiled reference kernel
   if (eq("wg_smem_kb")) { g_wg_smem_kb = value; return VCA_OK; }
   if (eq("fwd_smem_kb")) { g_fwd_smem_kb = value; return VCA_OK; }
   if (eq("wg_dbg")) { g_wg_dbg = value; return VCA_OK; }

@@ -255,10 +255,9 @@ __global__ void stem_im2col_kernel(const TI* __restrict__ x, TO* __restrict__ y,
 // Tiled form: a CTA stages the (2*RB+5) x (W+6) input rows of one band of RB output rows in shared memory (zero padded,
 // coalesced loads), then every thread emits (pixel, 8-channel group) items from shared memory -- 8 LDS + one 128-bit
 // store instead of 8 scattered global loads per store; the kernel is then bound by the 963 MB it has to write.
-constexpr int IM2COL_RB = 4;
 template <class TI, class TO>
 __global__ void __launch_bounds__(256) stem_im2col_tiled_kernel(const TI* __restrict__ x, TO* __restrict__ y, int H, int W, int OH,
-                                                                int OW, int bands) {
+                                                                int OW, int bands, int IM2COL_RB) {
   extern __shared__ float sx[];
   const long long f = blockIdx.x / bands;
   const int oh0 = (blockIdx.x % bands) * IM2COL_RB;
@@ -269,21 +268,30 @@ __global__ void __launch_bounds__(256) stem_im2col_tiled_kernel(const TI* __rest
     sx[i] = ((unsigned)h < (unsigned)H && (unsigned)w < (unsigned)W) ? to_f(x[(f * H + h) * W + w]) : 0.f;
   }
   __syncthreads();
-  const int items = IM2COL_RB * OW * 8;
-  for (int i = threadIdx.x; i < items; i += blockDim.x) {
-    const int cg = i & 7, px = i >> 3;
-    const int r = px / OW, ow = px - r * OW, oh = oh0 + r;
-    if (oh >= OH) continue;
+  // thread = (channel group cg, pixel lane): its 8 taps' offsets inside the staged band are constants, the pixel walks
+  // forward 32 at a time with an incremental (row, column) -- the item loop used to spend ~40 integer instructions per
+  // 16-byte store on index arithmetic (tap -> (kh, kw), item -> (row, column)).  8 consecutive threads still cover one
+  // pixel's 128 bytes, so a warp stores four whole lines.
+  const int cg = threadIdx.x & 7, plane = threadIdx.x >> 3;
+  int off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int t = cg * 8 + k;
+    const int kh = (t * 37) >> 8, kw = t - kh * 7;          // t / 7 for t < 64
+    off[k] = t < 49 ? kh * PW + kw : -1;
+  }
+  int r = plane / OW, ow = plane - r * OW;
+  const int rstep = 32 / OW, cstep = 32 - rstep * OW;
+  for (; r < IM2COL_RB && oh0 + r < OH; ) {
+    const float* b = sx + (2 * r) * PW + 2 * ow;
     float v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int t = cg * 8 + k;
-      const int kh = (t * 37) >> 8, kw = t - kh * 7;          // t / 7 for t < 64
-      v[k] = t < 49 ? sx[(2 * r + kh) * PW + 2 * ow + kw] : 0.f;
-    }
-    TO* o = y + (((f * OH + oh) * OW + ow) * 64 + cg * 8);
+    for (int k = 0; k < 8; ++k) v[k] = off[k] >= 0 ? b[off[k]] : 0.f;
+    TO* o = y + (((f * OH + oh0 + r) * OW + ow) * 64 + cg * 8);
     if (sizeof(TO) == 2) Vec<bf16>::store(reinterpret_cast<bf16*>(o), v);
     else { Vec<float>::store(reinterpret_cast<float*>(o), v); Vec<float>::store(reinterpret_cast<float*>(o) + 4, v + 4); }
+    r += rstep; ow += cstep;
+    if (ow >= OW) { ow -= OW; ++r; }
   }
 }
 
@@ -303,6 +311,8 @@ bool use_vec(int C, const void* a, const void* b) { return C % Vec<T>::N == 0 &&
 
 #define TP(T, p) ((T*)(p))
 #define CTP(T, p) ((const T*)(p))
+
+int g_im2col_rb = 14;  // output rows per CTA of the tiled stem im2col ("im2col_rb")
 
 extern "C" {
 
@@ -375,14 +385,15 @@ int vca_d2s(int dtype, const void* y, void* x, int NF, int H, int W, int C, int 
 int vca_stem_im2col(int dt_in, int dt_out, const void* x, void* y, long long NF, int H, int W, cudaStream_t s) {
   VCA_CHECK_ARG(x && y && NF > 0 && H > 0 && W > 0);
   int OH = (H + 6 - 7) / 2 + 1, OW = (W + 6 - 7) / 2 + 1;
+  const int IM2COL_RB = g_im2col_rb > 0 ? g_im2col_rb : 4;
   const int bands = (OH + IM2COL_RB - 1) / IM2COL_RB;
   const size_t smem = (size_t)(2 * IM2COL_RB + 5) * (W + 6) * sizeof(float);
-  if (smem <= 48 * 1024 && NF * bands < (1ll << 31)) {
+  if (g_im2col_rb > 0 && smem <= 48 * 1024 && NF * bands < (1ll << 31)) {
     const unsigned g = (unsigned)(NF * bands);
-    if (dt_in == VCA_F32 && dt_out == VCA_F32) stem_im2col_tiled_kernel<float, float><<<g, 256, smem, s>>>((const float*)x, (float*)y, H, W, OH, OW, bands);
-    else if (dt_in == VCA_F32) stem_im2col_tiled_kernel<float, bf16><<<g, 256, smem, s>>>((const float*)x, (bf16*)y, H, W, OH, OW, bands);
-    else if (dt_out == VCA_F32) stem_im2col_tiled_kernel<bf16, float><<<g, 256, smem, s>>>((const bf16*)x, (float*)y, H, W, OH, OW, bands);
-    else stem_im2col_tiled_kernel<bf16, bf16><<<g, 256, smem, s>>>((const bf16*)x, (bf16*)y, H, W, OH, OW, bands);
+    if (dt_in == VCA_F32 && dt_out == VCA_F32) stem_im2col_tiled_kernel<float, float><<<g, 256, smem, s>>>((const float*)x, (float*)y, H, W, OH, OW, bands, IM2COL_RB);
+    else if (dt_in == VCA_F32) stem_im2col_tiled_kernel<float, bf16><<<g, 256, smem, s>>>((const float*)x, (bf16*)y, H, W, OH, OW, bands, IM2COL_RB);
+    else if (dt_out == VCA_F32) stem_im2col_tiled_kernel<bf16, float><<<g, 256, smem, s>>>((const bf16*)x, (float*)y, H, W, OH, OW, bands, IM2COL_RB);
+    else stem_im2col_tiled_kernel<bf16, bf16><<<g, 256, smem, s>>>((const bf16*)x, (bf16*)y, H, W, OH, OW, bands, IM2COL_RB);
     VCA_LAUNCH_CHECK();
     return VCA_OK;
   }
