@@ -54,3 +54,31 @@ def test_no_cpu_fallbacks():
         audio.lrs_denormalize_spec(torch.zeros(1, 321, 4))
     with pytest.raises(RuntimeError):
         preprocess.preprocess_clips(torch.zeros(1, 1, 8, 8, 3, dtype=torch.uint8))
+
+
+def test_flat_group_slab_job_tables():
+    """trainer.FlatGroup: tap-major gradient slabs are given to 2-D conv filters with more than one tap (Cin % 4 == 0) only; the
+    job table of a flush over an element range [lo, hi) lists exactly the slab parameters whose flat offset lies inside it,
+    with cumulative CTA offsets from vca_unslab_job_ctas and the largest tap count (host logic only: no kernel is launched)."""
+    import torch
+    import torch.nn as nn
+    from vcagan_b200._lib import lib
+    from vcagan_b200.trainer import FlatGroup
+    a = nn.Sequential(nn.Conv2d(8, 16, 3), nn.BatchNorm2d(16), nn.Conv2d(16, 16, 1))       # 3x3 filter: slab; 1x1: none
+    b = nn.Sequential(nn.Conv2d(16, 32, 5), nn.Linear(32, 4), nn.Conv2d(3, 8, 3))             # 5x5: slab; Cin = 3: none
+    grp = FlatGroup([a, b])
+    with_slab = [p for p in grp.params if hasattr(p, "_vca_slab")]
+    assert [tuple(p.shape) for p in with_slab] == [(16, 8, 3, 3), (32, 16, 5, 5)]
+    for p in with_slab:
+        taps = p.shape[2] * p.shape[3]
+        assert tuple(p._vca_slab.shape) == (taps, p.shape[0], p.shape[1]) and p._vca_slab.numel() == p.numel()
+        assert p._vca_slab.data_ptr() % 16 == 0 and p.grad.data_ptr() % 16 == 0
+    tab, n, ctas, max_taps = grp._slab_table(0, grp.numel)
+    assert n == 2 and max_taps == 25
+    c0 = lib().query("vca_unslab_job_ctas", 16, 8, 9)
+    assert tab[0, 3:7].tolist() == [16, 8, 9, 0] and tab[1, 3:7].tolist() == [32, 16, 25, c0]
+    assert ctas == c0 + lib().query("vca_unslab_job_ctas", 32, 16, 25)
+    cut = grp.offsets[len(list(a.parameters()))]                 # first parameter of module b
+    t_lo = grp._slab_table(0, cut); t_hi = grp._slab_table(cut, grp.numel)
+    assert t_lo[1] == 1 and t_hi[1] == 1 and t_lo[3] == 9 and t_hi[3] == 25 and t_hi[0][0, 6] == 0
+    assert grp._slab_table(0, cut) is t_lo                      # cached
